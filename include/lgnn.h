@@ -1,0 +1,174 @@
+/*
+ * lgnn.h — C ABI of the B200-native GCN + KFAC-GGN Laplace hot path.
+ *
+ * Plain C types only: device pointers, sizes, a CUDA stream handle.  No torch types,
+ * no exceptions, no hidden allocation (the caller owns every buffer; kernels that need
+ * scratch take a caller-provided workspace whose size comes from a *_workspace_bytes()
+ * query).  Every entry point returns 0 on success or a negative LGNN_E_* code and
+ * records a message retrievable with lgnn_last_error() (thread-local).
+ * All pointers are DEVICE pointers unless a parameter is documented as "host".
+ * Kernels are enqueued on `stream` and never synchronise the device.
+ *
+ * The reference (anitasyang/Laplace-GNN, pure Python) has no FFI; each entry point
+ * cites the reference lines whose arithmetic it replaces (paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes binding a maintainer would add.
+ */
+#ifndef LGNN_H_
+#define LGNN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGNN_ABI_VERSION 1
+
+enum {
+  LGNN_OK = 0,
+  LGNN_E_BADARG = -1,      /* null pointer, negative size, unknown mode */
+  LGNN_E_ALIGN = -2,       /* pointer / leading dimension not aligned as documented */
+  LGNN_E_NOMEM = -3,       /* workspace too small */
+  LGNN_E_CUDA = -4,        /* a CUDA runtime call or launch failed */
+  LGNN_E_UNSUPPORTED = -5  /* shape outside what the kernel supports */
+};
+
+/* Hessian-square-root mode of lgnn_hess_rhs_f32 */
+enum {
+  LGNN_HESS_REFERENCE = 0, /* curvlinops/kfac.py:631-661 as vendored (sqrt not detached) */
+  LGNN_HESS_GGN = 1        /* textbook sqrt(p_c)(e_c - p): upstream curvlinops / asdl / backpack */
+};
+
+/* SpMM epilogue flags */
+enum { LGNN_SPMM_NONE = 0, LGNN_SPMM_RELU = 1 };
+
+/* SYRK implementation selector */
+enum {
+  LGNN_SYRK_AUTO = 0,      /* tcgen05 3xTF32 when the shape allows, else SIMT fp32 */
+  LGNN_SYRK_SIMT = 1,      /* CUDA-core fp32 FMA */
+  LGNN_SYRK_TCGEN05 = 2    /* tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators */
+};
+
+typedef void* lgnn_stream_t; /* cudaStream_t */
+
+int lgnn_abi_version(void);
+const char* lgnn_last_error(void);
+/* sm count and compute capability of the current device (host out-params). */
+int lgnn_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * (c) integer kernels — bit-exact contract
+ * ---------------------------------------------------------------------------------------- */
+
+/* Edge list -> CSR pattern of the binary adjacency A with self loops.
+ * Replaces gnn/utils.py:325-330 (edge_index_to_adj: scipy coo -> dense, duplicates summed),
+ * gnn/marglik_training.py:403-405 (clamp to 1), gnn/models/base_gnn.py:68-73 (optional
+ * A + A^T clamp) and gnn/models/models.py:23 (fill_diagonal_(1)).
+ * A[src[e], dst[e]] = 1; duplicates collapse; the diagonal is set; columns ascend within a row.
+ *
+ * Two calls because nnz is only known after de-duplication:
+ *   lgnn_csr_build_count  fills rowptr[0..n] (rowptr[n] = nnz) and keeps the sorted rows in ws;
+ *   the caller reads rowptr[n], allocates col[nnz], then
+ *   lgnn_csr_build_fill   compacts the unique columns into col.
+ * src/dst: int64 [n_edges] (the two rows of the reference's edge_index). */
+size_t lgnn_csr_build_workspace_bytes(int64_t n, int64_t n_edges, int symmetric);
+int lgnn_csr_build_count(const int64_t* src, const int64_t* dst, int64_t n_edges, int64_t n,
+                         int symmetric, void* ws, size_t ws_bytes, int64_t* rowptr,
+                         lgnn_stream_t stream);
+int lgnn_csr_build_fill(const void* ws, size_t ws_bytes, int64_t n, int64_t n_edges, int symmetric,
+                        const int64_t* rowptr, int32_t* col, lgnn_stream_t stream);
+
+/* Pattern transpose of an [n_rows x n_cols] CSR (columns ascend within each output row).
+ * Â's pattern is A^T (gnn/models/utils.py:112: (adj @ D).T @ D). */
+size_t lgnn_csr_transpose_workspace_bytes(int64_t n_rows, int64_t n_cols, int64_t nnz);
+int lgnn_csr_transpose(int64_t n_rows, int64_t n_cols, const int64_t* rowptr, const int32_t* col,
+                       int64_t* t_rowptr, int32_t* t_col, void* ws, size_t ws_bytes,
+                       lgnn_stream_t stream);
+
+/* Degree normalisation, gnn/models/utils.py:106-109: deg = row sums of A (int64, exact),
+ * dis = deg^-1/2 in fp32 computed as IEEE 1/sqrt (inf -> 0). */
+int lgnn_degree_norm(int64_t n, const int64_t* a_rowptr, int64_t* deg, float* dis,
+                     lgnn_stream_t stream);
+
+/* Edge values of Â (or Â^T): val[k] = dis[row_offset + i] * dis[col[k]] for k in row i.
+ * gnn/models/utils.py:112. */
+int lgnn_edge_values(int64_t n_rows, int64_t row_offset, const int64_t* rowptr, const int32_t* col,
+                     const float* dis, float* val, lgnn_stream_t stream);
+
+/* nnz-balanced contiguous row blocks (new: the reference is single-device).
+ * bounds[r] = first row i with rowptr[i] >= floor(r*nnz/nparts); bounds[0]=0, bounds[nparts]=n. */
+int lgnn_row_partition(const int64_t* rowptr, int64_t n, int32_t nparts, int64_t* bounds,
+                       lgnn_stream_t stream);
+
+/* Halo of a row block: flags[c] = 1 for every column c referenced by rows [lo, hi) that lies
+ * outside [lo, hi); flags (uint8 [n_cols]) must be zeroed by the caller. */
+int lgnn_halo_mark(const int64_t* rowptr, const int32_t* col, int64_t lo, int64_t hi,
+                   uint8_t* flags, lgnn_stream_t stream);
+
+/* Slice rows [lo, hi) of a CSR into a local CSR whose columns are remapped for a padded
+ * all-gather layout: column c owned by rank q (bounds[q] <= c < bounds[q+1]) becomes
+ * q*pad + (c - bounds[q]).  out_rowptr has hi-lo+1 entries starting at 0. */
+int lgnn_csr_slice_remap(const int64_t* rowptr, const int32_t* col, const float* val, int64_t lo,
+                         int64_t hi, const int64_t* bounds, int32_t nparts, int64_t pad,
+                         int64_t* out_rowptr, int32_t* out_col, float* out_val,
+                         lgnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a) CSR SpMM — HBM-bound
+ * ---------------------------------------------------------------------------------------- */
+
+/* Y[i, 0:d] = epilogue( sum_k val[k] * X[col[k], 0:d] ), k in [rowptr[i], rowptr[i+1]).
+ * Replaces `adj @ self.lin(x)` (gnn/models/layers.py:45-46) with a sparse Â, its autograd
+ * backward Â^T @ grad, and — with d = (number of Hessian-sqrt columns) x (layer width) — the C
+ * backward passes of curvlinops/kfac.py:653-661 in ONE multi-RHS pass.
+ * X: [*, ldx] row-major fp32; Y: [n_rows, ldy].  The 128-bit path needs X, Y 16-byte aligned
+ * and d, ldx, ldy multiples of 4; anything else takes the scalar path. */
+int lgnn_spmm_f32(int64_t n_rows, const int64_t* rowptr, const int32_t* col, const float* val,
+                  const float* x, int64_t ldx, float* y, int64_t ldy, int64_t d, int flags,
+                  lgnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * loss + Hessian-sqrt right-hand sides
+ * ---------------------------------------------------------------------------------------- */
+
+/* loss[0] += sum_m CE(logits[idx[m], :], y[m])  (laplace/curvature/curvlinops.py:106,
+ * CrossEntropyLoss(reduction="sum")).  loss is a device double the caller zeroes.
+ * If n_correct != NULL it also counts argmax hits (int64 device counter). */
+int lgnn_softmax_ce_sum(const float* logits, int64_t ld, int32_t C, const int64_t* idx,
+                        const int64_t* y, int64_t m, double* loss, int64_t* n_correct,
+                        lgnn_stream_t stream);
+
+/* delta[idx[m], g, 0:C] += v_{m, c0+g}  for g in [0, ncols): the vector the reference injects at
+ * the logits of train node idx[m] for Hessian-sqrt column c0+g
+ * (curvlinops/kfac_utils.py:122-126 + curvlinops/kfac.py:631-661).  delta: [n_nodes, ncols, ldc]
+ * row-major, zeroed by the caller (duplicate idx accumulate, like autograd's index backward).
+ *   GGN:        v = sqrt(p_c) (e_c - p)
+ *   REFERENCE:  v = sqrt(p_c) [ (e_c - p)(1 + (f_c - fbar)/2) - p*(f - fbar) ],  fbar = p.f */
+int lgnn_hess_rhs_f32(const float* logits, int64_t ld, int32_t C, const int64_t* idx, int64_t m,
+                      int32_t c0, int32_t ncols, int32_t ldc, int mode, float* delta,
+                      lgnn_stream_t stream);
+
+/* out[r, j] = in[r, j] * (act[(r / group), j] > 0)   (relu' mask of the layer below;
+ * autograd of base_gnn.py:150 inside kfac.py:653-661).  in/out: [n_rows*group, d], act: [n_rows, d]. */
+int lgnn_relu_mask_mul_f32(const float* in, int64_t ldi, const float* act, int64_t lda, float* out,
+                           int64_t ldo, int64_t n_rows, int32_t group, int64_t d,
+                           lgnn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (b) Kronecker-factor accumulation — dense SYRK, tensor-core bound
+ * ---------------------------------------------------------------------------------------- */
+
+/* C[n x n] = beta * C + alpha * X^T X,  X: [k_rows, ldx] row-major fp32 (first n columns used),
+ * C: [n, ldc] row-major, both triangles written.
+ * A_l = H^T H / N (curvlinops/kfac.py:819-875), G_l = sum_c gZ^T gZ (kfac.py:777-817).
+ * Deterministic split-K: partial tiles go to the workspace and are reduced in fixed order. */
+size_t lgnn_syrk_workspace_bytes(int64_t k_rows, int64_t n, int impl);
+int lgnn_syrk_f32(const float* x, int64_t ldx, int64_t k_rows, int64_t n, float alpha, float beta,
+                  float* c, int64_t ldc, void* ws, size_t ws_bytes, int impl,
+                  lgnn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGNN_H_ */

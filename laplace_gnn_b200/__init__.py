@@ -1,0 +1,17 @@
+"""laplace_gnn_b200 — B200-native GCN forward/backward + KFAC-GGN Kronecker-factor accumulation
+behind the reference's curvature-backend plugin API (anitasyang/Laplace-GNN hot path).
+
+Public surface:
+    Graph, SparseGCN, SparseGCNConv, GCNConvFunction   model side (mirrors gnn/models)
+    B200GGN, make_backend                              curvature backend (laplace/curvature contract)
+    Laplace, KronLaplace, DiagLaplace, Kron            stand-ins when the `laplace` package is absent
+    ops                                                tensor-level wrappers over the C-ABI (include/lgnn.h)
+"""
+from . import _lib, ops  # noqa: F401
+from .graph import Graph  # noqa: F401
+from .gcn import GCNConvFunction, SparseGCN, SparseGCNConv  # noqa: F401
+from .curvature import B200GGN, make_backend  # noqa: F401
+from .kron import DiagLaplace, Kron, KronDecomposed, KronLaplace, Laplace  # noqa: F401
+
+__all__ = ["Graph", "SparseGCN", "SparseGCNConv", "GCNConvFunction", "B200GGN", "make_backend",
+           "Laplace", "KronLaplace", "DiagLaplace", "Kron", "KronDecomposed", "ops"]

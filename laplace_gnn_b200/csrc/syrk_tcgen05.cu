@@ -1,0 +1,410 @@
+// C += X^T X on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM),
+// with the 3xTF32 split for fp32-faithful results:  x = hi + lo (hi = x with the 13 low mantissa
+// bits cleared — exactly the value the tensor core sees — lo = x - hi, exact in fp32), and
+//     X^T X  ~=  hi^T hi + hi^T lo + lo^T hi        (the lo^T lo term is below fp32 rounding).
+//
+// Shape: extreme-K, tiny-N (K = nodes x Hessian columns up to 1e8 rows, n <= 256).  One persistent
+// CTA per SM owns a contiguous slice of rows and the FULL n x n accumulator in TMEM (two M=128
+// blocks x up to 256 fp32 columns = all 512 TMEM columns), so X is read from HBM exactly once.
+//
+// Pipeline per CTA (6 warps):
+//   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes [BK rows x NP cols] of raw fp32 into a
+//               4-deep shared-memory ring (out-of-bounds rows / columns arrive as zeros, which makes
+//               every edge case — row tail, n not a multiple of 16 — free);
+//   warps 2..5  transform: read a raw box, split hi / lo, write both as K-major no-swizzle UMMA
+//               operands (8-row x 16-byte core matrices, padded 144-byte group stride so the 128-bit
+//               transposed stores are bank-conflict free) into a 3-deep operand ring;
+//   warp 1      one elected lane issues, per 8-wide k-step and per M block, three tcgen05.mma
+//               (hi.hi, hi.lo, lo.hi; A and B descriptors point into the SAME operand buffers because
+//               both operands are X), then tcgen05.commit frees the operand stage;
+//   warps 2..5  epilogue: tcgen05.ld the accumulator (each warp its own 32-lane TMEM quarter) and
+//               store this CTA's partial n x NP block; a second kernel reduces the <=148 partials in
+//               fixed order (deterministic) and writes both triangles of C.
+//
+// Tensor roofline accounting: useful flops = k_rows * n * (n+1); the 3x issue factor
+// of the split is not counted as useful work.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "syrk_internal.cuh"
+
+namespace lgnn {
+
+constexpr int TC_BK = 16;          // rows of X per pipeline stage (two k=8 UMMA steps)
+constexpr int TC_RAW_STAGES = 4;
+constexpr int TC_OP_STAGES = 3;
+constexpr int TC_SBO = 144;        // byte stride between 8-row core-matrix groups (128 + 16 pad)
+constexpr int TC_THREADS = 192;
+constexpr int TC_TRANSFORM_THREADS = 128;
+
+struct TcGeom {
+  int n, np, mb, npa;   // n, n padded to 16, #128-row M blocks, A-operand rows (mb*128)
+  int lbo;              // byte stride between the 16-byte k-chunks of one row group set
+  int op_bytes;         // bytes of one (hi or lo) operand stage
+  int raw_bytes;        // bytes of one raw stage
+  int tmem_cols;        // power of two >= mb*np, >= 32
+  size_t smem_bytes;
+};
+
+static TcGeom tc_geom(int n) {
+  TcGeom g;
+  g.n = n;
+  g.np = (n + 15) / 16 * 16;
+  g.mb = (g.np + 127) / 128;
+  g.npa = g.mb * 128;
+  g.lbo = (g.npa / 8) * TC_SBO;
+  g.op_bytes = (TC_BK / 4) * g.lbo;
+  g.raw_bytes = TC_BK * g.np * 4;
+  int cols = g.mb * g.np;
+  g.tmem_cols = 32;
+  while (g.tmem_cols < cols) g.tmem_cols <<= 1;
+  g.smem_bytes = 1024 /*align slack*/ + (size_t)TC_RAW_STAGES * g.raw_bytes +
+                 (size_t)TC_OP_STAGES * 2 * g.op_bytes + 256 /*barriers*/;
+  return g;
+}
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, no swizzle: 8-row x 16-byte core matrices; LBO = stride between the k-chunks,
+// SBO = stride between 8-row groups (cute/arch/mma_sm100_desc.hpp SmemDescriptor, version 1).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+
+struct TcParams {
+  int n, np, mb, lbo, op_bytes, raw_bytes, tmem_cols;
+  int swap_lbo_sbo;  // debug switch (env LGNN_SYRK_SWAP_LBO_SBO) for descriptor bring-up
+  int64_t steps_total;
+  int64_t steps_per_cta;
+  float* part;  // [gridDim.x][n][np]
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) {
+  extern __shared__ uint8_t smem_raw_[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw_) + 1023) & ~(uintptr_t)1023);
+  uint8_t* raw_base = smem;
+  uint8_t* op_base = raw_base + (size_t)TC_RAW_STAGES * P.raw_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(op_base + (size_t)TC_OP_STAGES * 2 * P.op_bytes);
+  // barrier slots
+  uint64_t* full_raw = bars;                       // [RAW]
+  uint64_t* empty_raw = bars + TC_RAW_STAGES;      // [RAW]
+  uint64_t* full_op = empty_raw + TC_RAW_STAGES;   // [OP]
+  uint64_t* empty_op = full_op + TC_OP_STAGES;     // [OP]
+  uint64_t* acc_full = empty_op + TC_OP_STAGES;    // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t step_beg = (int64_t)blockIdx.x * P.steps_per_cta;
+  int64_t step_end = step_beg + P.steps_per_cta;
+  if (step_end > P.steps_total) step_end = P.steps_total;
+  const int64_t my_steps = step_end > step_beg ? step_end - step_beg : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_RAW_STAGES; ++i) {
+      mbar_init(smem_u32(&full_raw[i]), 1);
+      mbar_init(smem_u32(&empty_raw[i]), TC_TRANSFORM_THREADS / 32);
+    }
+    for (int i = 0; i < TC_OP_STAGES; ++i) {
+      mbar_init(smem_u32(&full_op[i]), TC_TRANSFORM_THREADS / 32);
+      mbar_init(smem_u32(&empty_op[i]), 1);
+    }
+    mbar_init(smem_u32(acc_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)P.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+      for (int64_t s = 0; s < my_steps; ++s) {
+        int st = (int)(s % TC_RAW_STAGES);
+        uint32_t ph = (uint32_t)((s / TC_RAW_STAGES) & 1);
+        mbar_wait(smem_u32(&empty_raw[st]), ph ^ 1);
+        uint32_t bar = smem_u32(&full_raw[st]);
+        mbar_arrive_expect_tx(bar, (uint32_t)P.raw_bytes);
+        tma_load_2d(smem_u32(raw_base + (size_t)st * P.raw_bytes), &tmap, 0,
+                    (int)((step_beg + s) * TC_BK), bar);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0 && my_steps > 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.np >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      const uint32_t lbo = P.swap_lbo_sbo ? TC_SBO : P.lbo;
+      const uint32_t sbo = P.swap_lbo_sbo ? P.lbo : TC_SBO;
+      for (int64_t s = 0; s < my_steps; ++s) {
+        int st = (int)(s % TC_OP_STAGES);
+        uint32_t ph = (uint32_t)((s / TC_OP_STAGES) & 1);
+        mbar_wait(smem_u32(&full_op[st]), ph);
+        tc_fence_after();
+        const uint32_t hi = smem_u32(op_base + (size_t)st * 2 * P.op_bytes);
+        const uint32_t lo = hi + P.op_bytes;
+#pragma unroll
+        for (int ks = 0; ks < TC_BK / 8; ++ks) {
+          const uint32_t koff = (uint32_t)ks * 2u * (uint32_t)P.lbo;  // two 16-byte k-chunks per k=8 step
+          const uint64_t b_hi = make_smem_desc(hi + koff, lbo, sbo);
+          const uint64_t b_lo = make_smem_desc(lo + koff, lbo, sbo);
+          for (int m = 0; m < P.mb; ++m) {
+            const uint32_t aoff = koff + (uint32_t)m * 16u * TC_SBO;  // 128 rows = 16 groups
+            const uint64_t a_hi = make_smem_desc(hi + aoff, lbo, sbo);
+            const uint64_t a_lo = make_smem_desc(lo + aoff, lbo, sbo);
+            const uint32_t d = tmem_base + (uint32_t)(m * P.np);
+            const uint32_t first = (s == 0 && ks == 0) ? 0u : 1u;
+            tc_mma_tf32(d, a_hi, b_hi, idesc, first);
+            tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
+            tc_mma_tf32(d, a_lo, b_hi, idesc, 1u);
+          }
+        }
+        tc_commit(smem_u32(&empty_op[st]));  // implies fence::before_thread_sync
+      }
+      tc_commit(smem_u32(acc_full));
+    }
+  } else {
+    // ===================================================================== transform warps
+    const int t = threadIdx.x - 64;  // 0..127
+    const int np4 = P.np >> 2;
+    const int items = (TC_BK / 4) * np4;
+    for (int64_t s = 0; s < my_steps; ++s) {
+      const int rs = (int)(s % TC_RAW_STAGES);
+      const uint32_t rph = (uint32_t)((s / TC_RAW_STAGES) & 1);
+      const int os = (int)(s % TC_OP_STAGES);
+      const uint32_t oph = (uint32_t)((s / TC_OP_STAGES) & 1);
+      mbar_wait(smem_u32(&full_raw[rs]), rph);
+      mbar_wait(smem_u32(&empty_op[os]), oph ^ 1);
+      const float* raw = reinterpret_cast<const float*>(raw_base + (size_t)rs * P.raw_bytes);
+      uint8_t* hi = op_base + (size_t)os * 2 * P.op_bytes;
+      uint8_t* lo = hi + P.op_bytes;
+      for (int it = t; it < items; it += TC_TRANSFORM_THREADS) {
+        const int kq = it / np4, i4 = it - kq * np4;
+        float4 r[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          r[q] = *reinterpret_cast<const float4*>(raw + (size_t)(4 * kq + q) * P.np + 4 * i4);
+        const float v[4][4] = {{r[0].x, r[1].x, r[2].x, r[3].x},
+                               {r[0].y, r[1].y, r[2].y, r[3].y},
+                               {r[0].z, r[1].z, r[2].z, r[3].z},
+                               {r[0].w, r[1].w, r[2].w, r[3].w}};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = 4 * i4 + j;
+          const uint32_t off = (uint32_t)(i >> 3) * TC_SBO + (uint32_t)kq * (uint32_t)P.lbo + (uint32_t)(i & 7) * 16u;
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(v[j][0]) & 0xffffe000u);
+          h.y = __uint_as_float(__float_as_uint(v[j][1]) & 0xffffe000u);
+          h.z = __uint_as_float(__float_as_uint(v[j][2]) & 0xffffe000u);
+          h.w = __uint_as_float(__float_as_uint(v[j][3]) & 0xffffe000u);
+          l.x = v[j][0] - h.x;
+          l.y = v[j][1] - h.y;
+          l.z = v[j][2] - h.z;
+          l.w = v[j][3] - h.w;
+          *reinterpret_cast<float4*>(hi + off) = h;
+          *reinterpret_cast<float4*>(lo + off) = l;
+        }
+      }
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor-core (async) proxy
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(smem_u32(&full_op[os]));
+        mbar_arrive(smem_u32(&empty_raw[rs]));
+      }
+    }
+    // ===================================================================== epilogue
+    if (my_steps > 0) {
+      mbar_wait(smem_u32(acc_full), 0);
+      tc_fence_after();
+      const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+      float* out = P.part + (size_t)blockIdx.x * P.n * P.np;
+      for (int m = 0; m < P.mb; ++m) {
+        const int row = m * 128 + quarter * 32 + lane;
+        for (int c0 = 0; c0 < P.np; c0 += 16) {
+          uint32_t v[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(m * P.np + c0);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                "=r"(v[14]), "=r"(v[15])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (row < P.n) {
+            float4* dst = reinterpret_cast<float4*>(out + (size_t)row * P.np + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                   __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          }
+        }
+      }
+    } else {
+      // idle CTA (more CTAs than steps): contribute zeros
+      float* out = P.part + (size_t)blockIdx.x * P.n * P.np;
+      for (int i = t; i < P.n * P.np; i += TC_TRANSFORM_THREADS) out[i] = 0.f;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)P.tmem_cols)
+                 : "memory");
+  }
+}
+
+// C[i][j] (i <= j) = beta*C + alpha * sum_s part[s][i][j], mirrored; fixed order over s.
+__global__ void syrk_tc_reduce_kernel(const float* __restrict__ part, int n_parts, int n, int np,
+                                      float alpha, float beta, float* __restrict__ c, int64_t ldc) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n * np) return;
+  int i = e / np, j = e - i * np;
+  if (j >= n || j < i) return;
+  float s = 0.f;
+  for (int p = 0; p < n_parts; ++p) s += part[(size_t)p * n * np + e];
+  float v = alpha * s;
+  if (beta != 0.f) v = fmaf(beta, c[(int64_t)i * ldc + j], v);
+  c[(int64_t)i * ldc + j] = v;
+  if (i != j) c[(int64_t)j * ldc + i] = v;
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) return nullptr;
+  if (q != cudaDriverEntryPointSuccess) return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+static int tc_grid(int64_t steps_total) {
+  int64_t g = sm_count();
+  if (g > steps_total) g = steps_total;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+bool syrk_tcgen05_supported(int64_t k_rows, int64_t n) {
+  return n >= 8 && n <= 256 && k_rows >= 1 && k_rows < ((int64_t)1 << 31) - 64;
+}
+
+size_t syrk_tcgen05_workspace_bytes(int64_t k_rows, int64_t n) {
+  (void)k_rows;
+  TcGeom g = tc_geom((int)n);
+  return (size_t)sm_count() * n * g.np * sizeof(float);
+}
+
+int syrk_tcgen05_launch(const float* x, int64_t ldx, int64_t k_rows, int n, float alpha, float beta,
+                        float* c, int64_t ldc, void* ws, cudaStream_t st) {
+  TcGeom g = tc_geom(n);
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return fail(LGNN_E_CUDA, "syrk_tcgen05: cuTensorMapEncodeTiled not available");
+  CUtensorMap tmap;
+  cuuint64_t gdim[2] = {(cuuint64_t)n, (cuuint64_t)k_rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ldx * 4};
+  cuuint32_t box[2] = {(cuuint32_t)g.np, (cuuint32_t)TC_BK};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(x), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LGNN_E_CUDA, "syrk_tcgen05: cuTensorMapEncodeTiled failed (%d)", (int)r);
+
+  TcParams P;
+  P.n = n; P.np = g.np; P.mb = g.mb; P.lbo = g.lbo; P.op_bytes = g.op_bytes; P.raw_bytes = g.raw_bytes;
+  P.tmem_cols = g.tmem_cols;
+  const char* sw = getenv("LGNN_SYRK_SWAP_LBO_SBO");
+  P.swap_lbo_sbo = (sw && sw[0] == '1') ? 1 : 0;
+  P.steps_total = (k_rows + TC_BK - 1) / TC_BK;
+  int grid = tc_grid(P.steps_total);
+  P.steps_per_cta = (P.steps_total + grid - 1) / grid;
+  P.part = reinterpret_cast<float*>(ws);
+  LGNN_CUDA_TRY(cudaFuncSetAttribute(syrk_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)g.smem_bytes));
+  syrk_tcgen05_kernel<<<grid, TC_THREADS, g.smem_bytes, st>>>(tmap, P);
+  LGNN_LAUNCH_CHECK("syrk_tcgen05_kernel");
+  int elems = n * g.np;
+  syrk_tc_reduce_kernel<<<(elems + 255) / 256, 256, 0, st>>>(P.part, grid, n, g.np, alpha, beta, c, ldc);
+  LGNN_LAUNCH_CHECK("syrk_tc_reduce_kernel");
+  return LGNN_OK;
+}
+
+}  // namespace lgnn

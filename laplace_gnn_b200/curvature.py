@@ -1,0 +1,247 @@
+"""B200GGN — curvature backend implementing the reference's ``CurvatureInterface.kron()/diag()``
+contract (laplace/curvature/curvature.py:236-289) for the sparse GCN, on hand-written sm_100a
+kernels.  It replaces ``CurvlinopsGGN.kron`` (laplace/curvature/curvlinops.py:77-108) and the
+vendored ``KFACLinearOperator._compute_kfac`` (curvlinops/kfac.py:540-875) for this model family.
+
+Select it exactly like any other backend::
+
+    la = Laplace(model, "classification", subset_of_weights="all", hessian_structure="kron",
+                 backend=B200GGN, backend_kwargs={"hess_sqrt": "reference"})
+    la.fit(train_loader); la.log_marginal_likelihood()
+
+What one ``kron(idx, y, N)`` call does on the device (M = len(idx), all graph nodes take part,
+SURVEY §0-T2):
+
+  forward      Z_l = H_{l-1} W_l^T + b_l (cuBLAS fp32, a plain library GEMM), P_l = Â Z_l (SpMM
+               kernel, relu fused for l < L), once — the reference runs three forwards
+  A_l          = H_{l-1}^T H_{l-1} / M * (M / N)                         (SYRK kernel)
+  loss         = sum CE(P_L[idx], y)                                      (fused softmax kernel)
+  backward     for a group of g Hessian-sqrt columns at a time (g sized to the HBM budget):
+               delta_L[idx, c, :] = v_{m,c}  (fused softmax + Hessian-sqrt kernel, both modes),
+               gZ_l = Â^T delta_l as ONE multi-RHS SpMM of width g*d_l, G_l += gZ_l^T gZ_l (SYRK,
+               K = N*g), delta_{l-1} = (gZ_l W_l) ⊙ 1[H_{l-1} > 0]  (cuBLAS GEMM + mask kernel)
+  packing      [[G_1, A_1], [G_1], [G_2, A_2], [G_2], ...]  (curvlinops.py:55-75)
+
+``hess_sqrt="reference"`` (default) reproduces the fork's non-detached Hessian square root
+(curvlinops/kfac.py:631-661); ``"ggn"`` is the textbook GGN of upstream
+curvlinops / asdl / backpack.  Returned tensors are fresh, detached, fp32, on the model's device.
+"""
+from __future__ import annotations
+
+import sys
+from typing import Any
+
+import torch
+from torch import nn
+
+from . import ops
+from .gcn import SparseGCN
+
+
+class CurvatureInterfaceLite:
+    """Attribute-compatible stand-in for ``laplace.curvature.CurvatureInterface.__init__``
+    (curvature.py:46-83) used when the ``laplace`` package is not installed."""
+
+    def __init__(self, model: nn.Module, likelihood: str, last_layer: bool = False,
+                 subnetwork_indices=None, dict_key_x: str = "input_ids", dict_key_y: str = "labels"):
+        if likelihood not in ("classification", "regression"):
+            raise ValueError(f"Invalid likelihood type {likelihood}")
+        self.likelihood = likelihood
+        self.model = model
+        self.last_layer = last_layer
+        self.subnetwork_indices = subnetwork_indices
+        self.dict_key_x, self.dict_key_y = dict_key_x, dict_key_y
+        if likelihood == "regression":
+            self.lossfunc = nn.MSELoss(reduction="sum")
+            self.factor = 0.5
+        else:
+            self.lossfunc = nn.CrossEntropyLoss(reduction="sum")
+            self.factor = 1.0
+        self.params, self.params_dict = [], {}
+        for k, v in model.named_parameters():
+            if v.requires_grad and "adj" not in k and "norms" not in k:
+                self.params.append(v)
+                self.params_dict[k] = v
+        self.buffers_dict = dict(model.named_buffers())
+
+
+def _kron_class():
+    """The ``Kron`` of whichever ``laplace`` package is driving us, else the local stand-in."""
+    mod = sys.modules.get("laplace.utils")
+    if mod is not None and hasattr(mod, "Kron"):
+        return mod.Kron
+    from .kron import Kron
+    return Kron
+
+
+class _B200KFAC:
+    """kron()/diag() on the B200 kernels; mixed into a CurvatureInterface subclass."""
+
+    def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
+                    rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows"):
+        if hess_sqrt not in ("reference", "ggn"):
+            raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
+        if differentiable:
+            raise NotImplementedError(
+                "differentiable=True (gradients of the factors w.r.t. the adjacency) is outside the "
+                "fixed-adjacency GCN hot path (SURVEY §8f row 3)")
+        if self.likelihood != "classification":
+            raise ValueError("B200GGN implements the classification (softmax CE) hot path only")
+        if not isinstance(self.model, SparseGCN):
+            raise TypeError("B200GGN needs a laplace_gnn_b200.SparseGCN model")
+        if self.last_layer or self.subnetwork_indices is not None:
+            raise NotImplementedError("last_layer / subnetwork Laplace are outside the hot path")
+        self.hess_sqrt = hess_sqrt
+        self.process_group = process_group
+        self.rhs_tile_bytes = rhs_tile_bytes
+        self.syrk_impl = syrk_impl
+        self.backward_parallel = backward_parallel
+        self.n_outputs = self.model.out_channels
+        self.last_stats: dict[str, Any] = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _layers(self):
+        Ws, bs = [], []
+        for conv in self.model.convs:
+            w = conv.lin.weight.detach()
+            if w.dtype != torch.float32:
+                raise TypeError("B200GGN computes in float32; cast the model to float32")
+            Ws.append(w.contiguous())
+            bs.append(None if conv.lin.bias is None else conv.lin.bias.detach().contiguous())
+        return Ws, bs
+
+    def _forward(self, Ws, bs):
+        """Eval-mode forward.  Returns Hs = [X, H_1, ..., H_{L-1}] and the logits P_L [n, C]."""
+        g = self.model.graph
+        h = self.model.X
+        if h.dtype != torch.float32 or not h.is_contiguous():
+            h = h.float().contiguous()
+        Hs = [h]
+        L = len(Ws)
+        for l in range(L):
+            z = torch.mm(h, Ws[l].t()) if bs[l] is None else torch.addmm(bs[l], h, Ws[l].t())
+            h = ops.spmm(g.ahat, z, relu=(l < L - 1))
+            if l < L - 1:
+                Hs.append(h)
+        return Hs, h
+
+    def _group_size(self, n: int, dmax: int, C: int, device) -> int:
+        budget = self.rhs_tile_bytes
+        if budget is None:
+            if device.type == "cuda":
+                free, total = torch.cuda.mem_get_info(device)
+                budget = min(int(0.6 * free), int(0.4 * total))
+            else:
+                budget = 1 << 30
+        g = int(budget // (2 * n * dmax * 4))
+        return max(1, min(C, g))
+
+    # ------------------------------------------------------------------ kron
+    def kron(self, x: torch.Tensor, y: torch.Tensor, N: int, **kwargs):
+        """(loss, Kron) for the batch of train-node indices ``x`` with labels ``y``; ``N`` is the
+        size of the whole training set (curvature.py:236-265)."""
+        if self.process_group is not None:
+            from .dist import kron_partitioned
+            return kron_partitioned(self, x, y, N)
+        model = self.model
+        g = model.graph
+        n = g.n
+        Ws, bs = self._layers()
+        L = len(Ws)
+        M = int(y.shape[0])
+        if x.shape[0] != M:
+            raise ValueError("x (node indices) and y (labels) must have the same length")
+        idx = x.to(torch.int64).contiguous()
+        yy = y.to(torch.int64).contiguous()
+        Hs, logits = self._forward(Ws, bs)
+        C = logits.shape[1]
+        loss, _hits = ops.softmax_ce_sum(logits, idx, yy)
+
+        # input-side factors A_l over ALL n nodes (kfac.py:870), then the M/N rescale (curvlinops.py:46-53)
+        A = []
+        for l in range(L):
+            a = ops.syrk(Hs[l], alpha=1.0 / M, impl=self._impl(Hs[l].shape[1]))
+            a *= M / N
+            A.append(a)
+
+        # output-side factors G_l, multi-RHS backward in groups of Hessian-sqrt columns
+        dims = [w.shape[0] for w in Ws]                 # d_1 .. d_L (d_L = C)
+        c_pad = (C + 3) // 4 * 4
+        dmax = max([c_pad] + dims[:-1])
+        grp = self._group_size(n, dmax, C, logits.device)
+        buf_a = torch.empty(n * grp * dmax, dtype=torch.float32, device=logits.device)
+        buf_b = torch.empty(n * grp * dmax, dtype=torch.float32, device=logits.device)
+        G = [torch.zeros(d, d, dtype=torch.float32, device=logits.device) for d in dims]
+        for c0 in range(0, C, grp):
+            gc = min(grp, C - c0)
+            delta = buf_a[: n * gc * c_pad].view(n, gc * c_pad)
+            delta.zero_()
+            ops.hess_rhs(logits, idx, c0, gc, delta, c_pad, self.hess_sqrt)
+            width, ld = C, c_pad
+            for l in range(L - 1, -1, -1):
+                gz = buf_b[: n * gc * ld].view(n, gc * ld)
+                ops.spmm(g.ahat_t, delta, out=gz)
+                gz_rows = gz.view(n * gc, ld)
+                ops.syrk(gz_rows, n=width, alpha=1.0, beta=1.0, out=G[l], impl=self._impl(width))
+                if l > 0:
+                    d_prev = dims[l - 1]
+                    nxt = buf_a[: n * gc * d_prev].view(n * gc, d_prev)
+                    torch.mm(gz_rows[:, :width], Ws[l], out=nxt)
+                    ops.relu_mask_mul(nxt, Hs[l], gc)
+                    delta = nxt.view(n, gc * d_prev)
+                    width, ld = d_prev, d_prev
+        self.last_stats = {"group": grp, "n_groups": (C + grp - 1) // grp, "M": M, "C": C}
+
+        Kron = _kron_class()
+        kfacs = []
+        for l in range(L):
+            kfacs.append([G[l], A[l]])
+            if bs[l] is not None:
+                kfacs.append([G[l].clone()])
+        kron = Kron(kfacs)
+        return (self.factor * loss).to(torch.float32), kron
+
+    def _impl(self, n: int) -> str:
+        return self.syrk_impl
+
+    # ------------------------------------------------------------------ diag
+    def diag(self, x: torch.Tensor, y: torch.Tensor, N: int | None = None, **kwargs):
+        """(loss, diag GGN [P]) with the true Λ = diag(p) - pp^T (curvature.py:365-372, 412-432).
+
+        Exact, and therefore — like the reference, which materialises an (M, C, P) Jacobian — only
+        for small graphs: one back-propagated column per (train node, class) pair, processed as
+        multi-RHS tiles through the same SpMM kernel."""
+        from .diag import diag_ggn_exact
+        return diag_ggn_exact(self, x, y)
+
+
+def make_backend(base: type, name: str = "B200GGN") -> type:
+    """Build the backend class on top of a given ``CurvatureInterface`` base (the reference's
+    ``laplace.curvature.GGNInterface`` when integrating into that package)."""
+
+    def __init__(self, model, likelihood, last_layer=False, subnetwork_indices=None,
+                 dict_key_x="input_ids", dict_key_y="labels", stochastic=False,
+                 hess_sqrt="reference", differentiable=False, process_group=None,
+                 rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows"):
+        if stochastic:
+            raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
+        try:
+            base.__init__(self, model, likelihood, last_layer, subnetwork_indices, dict_key_x, dict_key_y)
+        except TypeError:  # GGNInterface takes a `stochastic` argument in some versions
+            base.__init__(self, model, likelihood, last_layer, subnetwork_indices, dict_key_x,
+                          dict_key_y, stochastic)
+        self.stochastic = False
+        self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
+                         backward_parallel)
+
+    return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
+
+
+def _default_base() -> type:
+    mod = sys.modules.get("laplace.curvature")
+    if mod is not None and hasattr(mod, "GGNInterface"):
+        return mod.GGNInterface
+    return CurvatureInterfaceLite
+
+
+B200GGN = make_backend(_default_base())

@@ -1,0 +1,315 @@
+"""Minimal stand-ins for the pieces of the ``laplace`` package that sit on either side of the
+curvature-backend boundary, for machines where that package is not installed (the GPU box).
+
+When ``laplace`` *is* importable (the reference fork or upstream laplace-torch), ``B200GGN``
+returns that package's own ``Kron`` and is driven by its own ``KronLaplace`` — this module is not
+used.  Here only the algebra the hot path needs is restated (device-resident, no host syncs):
+
+* ``Kron`` / ``KronDecomposed``: block lists ``[[G, A], [G], ...]``, ``+``, scalar ``*``,
+  ``decompose`` (eigh with eigenvalues clamped at 0) and ``logdet`` with per-block prior
+  precisions            (reference: laplace/utils/matrix.py:16-145, 277-394; utils.py:193-226)
+* ``KronLaplace`` / ``DiagLaplace`` / ``Laplace``: ``fit``, ``log_marginal_likelihood``,
+  ``optimize_prior_precision``   (reference: laplace/baselaplace.py:778-973, 342-492, 1507-1627,
+  1838-1919; laplace/laplace.py:13-47)
+"""
+from __future__ import annotations
+
+import math
+from typing import Iterable, Sequence
+
+import torch
+from torch.nn.utils import parameters_to_vector
+
+
+def _eigh_psd(m: torch.Tensor):
+    lam, q = torch.linalg.eigh(m, UPLO="U")
+    return torch.nan_to_num(lam.clamp(min=0.0)), torch.nan_to_num(q)
+
+
+class Kron:
+    """Block-diagonal Kronecker-factored matrix: one block per parameter tensor, a block is
+    ``[G, A]`` (weight: G ⊗ A, output-side factor first) or ``[G]`` (bias)."""
+
+    def __init__(self, kfacs: Sequence[Sequence[torch.Tensor]]):
+        self.kfacs = [list(block) for block in kfacs]
+
+    @classmethod
+    def init_from_model(cls, model_or_params, device=None, dtype=None) -> "Kron":
+        params = model_or_params.parameters() if isinstance(model_or_params, torch.nn.Module) \
+            else model_or_params
+        blocks = []
+        for p in params:
+            dev = device if device is not None else p.device
+            dt = dtype if dtype is not None else p.dtype
+            if p.ndim == 1:
+                blocks.append([torch.zeros(p.shape[0], p.shape[0], device=dev, dtype=dt)])
+            elif p.ndim >= 2:
+                out_f, in_f = p.shape[0], int(p[0].numel())
+                blocks.append([torch.zeros(out_f, out_f, device=dev, dtype=dt),
+                               torch.zeros(in_f, in_f, device=dev, dtype=dt)])
+            else:
+                raise ValueError("scalar parameters are not supported")
+        return cls(blocks)
+
+    def __len__(self):
+        return len(self.kfacs)
+
+    def __add__(self, other: "Kron") -> "Kron":
+        if not isinstance(other, Kron) or len(other) != len(self):
+            raise ValueError("can only add a Kron with the same block structure")
+        return Kron([[a + b for a, b in zip(fa, fb)] for fa, fb in zip(self.kfacs, other.kfacs)])
+
+    def __mul__(self, s) -> "Kron":
+        if isinstance(s, torch.Tensor) and s.numel() != 1:
+            raise ValueError("Kron can only be scaled by a scalar")
+        # spread the scalar evenly over the factors of a block so that the block scales by s
+        return Kron([[(s ** (1.0 / len(f))) * h for h in f] for f in self.kfacs])
+
+    __rmul__ = __mul__
+
+    def decompose(self, damping: bool = False) -> "KronDecomposed":
+        vecs, vals = [], []
+        for f in self.kfacs:
+            pairs = [_eigh_psd(h) for h in f]
+            vals.append([p[0] for p in pairs])
+            vecs.append([p[1] for p in pairs])
+        return KronDecomposed(vecs, vals, damping=damping)
+
+    def diag(self) -> torch.Tensor:
+        parts = []
+        for f in self.kfacs:
+            if len(f) == 1:
+                parts.append(f[0].diagonal())
+            else:
+                parts.append(torch.outer(f[0].diagonal(), f[1].diagonal()).reshape(-1))
+        return torch.cat(parts)
+
+    def logdet(self) -> torch.Tensor:
+        total = 0.0
+        for f in self.kfacs:
+            if len(f) == 1:
+                total = total + torch.logdet(f[0])
+            else:
+                (g, a) = f
+                total = total + a.shape[0] * torch.logdet(g) + g.shape[0] * torch.logdet(a)
+        return total
+
+
+class KronDecomposed:
+    """Eigendecomposed ``Kron`` plus an additive per-block ``delta`` (the prior precision)."""
+
+    def __init__(self, eigenvectors, eigenvalues, deltas: torch.Tensor | None = None,
+                 damping: bool = False):
+        self.eigenvectors = eigenvectors
+        self.eigenvalues = eigenvalues
+        dev = eigenvalues[0][0].device
+        self.deltas = torch.zeros(len(eigenvalues), device=dev) if deltas is None else deltas
+        self.damping = damping
+
+    def __len__(self):
+        return len(self.eigenvalues)
+
+    def __add__(self, deltas: torch.Tensor) -> "KronDecomposed":
+        deltas = torch.as_tensor(deltas, device=self.deltas.device, dtype=self.deltas.dtype)
+        if deltas.ndim == 0 or deltas.numel() == 1:
+            deltas = deltas.reshape(-1).expand(len(self))
+        if deltas.numel() != len(self):
+            raise ValueError("prior precision must be a scalar or one value per parameter tensor")
+        return KronDecomposed(self.eigenvectors, self.eigenvalues, self.deltas + deltas, self.damping)
+
+    def __mul__(self, s) -> "KronDecomposed":
+        vals = [[f[0] * s] + list(f[1:]) for f in self.eigenvalues]
+        return KronDecomposed(self.eigenvectors, vals, self.deltas, self.damping)
+
+    __rmul__ = __mul__
+
+    def logdet(self) -> torch.Tensor:
+        total = 0.0
+        for lams, delta in zip(self.eigenvalues, self.deltas):
+            if len(lams) == 1:
+                total = total + torch.log(lams[0] + delta).sum()
+            elif self.damping:
+                total = total + torch.log(torch.outer(lams[0] + delta.sqrt(), lams[1] + delta.sqrt())).sum()
+            else:
+                total = total + torch.log(torch.outer(lams[0], lams[1]) + delta).sum()
+        return total
+
+
+class _ParametricLaplaceLite:
+    """The subset of ``ParametricLaplace`` on the hot path (classification, all weights)."""
+
+    def __init__(self, model: torch.nn.Module, likelihood: str = "classification",
+                 prior_precision=1.0, prior_mean=0.0, temperature: float = 1.0,
+                 backend=None, backend_kwargs: dict | None = None, **unused):
+        if likelihood != "classification":
+            raise NotImplementedError("the GCN Laplace hot path is classification only")
+        if backend is None:
+            from .curvature import B200GGN
+            backend = B200GGN
+        self.model = model
+        self.likelihood = likelihood
+        # same filter as the fork (baselaplace.py:118-122): skip adj / norms parameters
+        self.params = [p for k, p in model.named_parameters()
+                       if p.requires_grad and "adj" not in k and "norms" not in k]
+        self.n_params = sum(p.numel() for p in self.params)
+        self.n_layers = len(self.params)
+        self._device = self.params[0].device
+        self.prior_precision = prior_precision
+        self.prior_mean = prior_mean
+        self.temperature = temperature
+        self._backend_cls = backend
+        self._backend_kwargs = dict(backend_kwargs or {})
+        self._backend = None
+        self.loss = 0.0
+        self.n_data = 0
+        self.n_outputs = 0
+        self.H = None
+
+    @property
+    def backend(self):
+        if self._backend is None:
+            self._backend = self._backend_cls(self.model, self.likelihood, **self._backend_kwargs)
+        return self._backend
+
+    # ---- prior
+    @property
+    def prior_precision_diag(self) -> torch.Tensor:
+        pp = torch.as_tensor(self.prior_precision, device=self._device, dtype=torch.float32)
+        if pp.ndim == 0 or pp.numel() == 1:
+            return pp.reshape(-1) * torch.ones(self.n_params, device=self._device)
+        if pp.numel() == self.n_params:
+            return pp
+        if pp.numel() == self.n_layers:
+            return torch.cat([v * torch.ones(p.numel(), device=self._device)
+                              for v, p in zip(pp, self.params)])
+        raise ValueError("prior precision must be scalar, per parameter tensor, or diagonal")
+
+    @property
+    def _H_factor(self) -> float:
+        return 1.0 / self.temperature
+
+    @property
+    def log_likelihood(self) -> torch.Tensor:
+        return -self._H_factor * self.loss
+
+    @property
+    def scatter(self) -> torch.Tensor:
+        d = self.mean - self.prior_mean
+        return (d * self.prior_precision_diag) @ d
+
+    @property
+    def log_det_prior_precision(self) -> torch.Tensor:
+        return self.prior_precision_diag.log().sum()
+
+    @property
+    def log_det_ratio(self) -> torch.Tensor:
+        return self.log_det_posterior_precision - self.log_det_prior_precision
+
+    def log_marginal_likelihood(self, prior_precision=None) -> torch.Tensor:
+        if prior_precision is not None:
+            self.prior_precision = prior_precision
+        return self.log_likelihood - 0.5 * (self.log_det_ratio + self.scatter)
+
+    # ---- fit
+    def _init_H(self):
+        raise NotImplementedError
+
+    def _curv_closure(self, X, y, N):
+        raise NotImplementedError
+
+    def fit(self, train_loader: Iterable, override: bool = True) -> None:
+        if override:
+            self._init_H()
+            self.loss = 0.0
+            self.n_data = 0
+        self.model.eval()
+        self.mean = parameters_to_vector(self.params).detach()
+        N = len(train_loader.dataset)
+        for X, y in train_loader:
+            X, y = X.to(self._device), y.to(self._device)
+            loss_b, H_b = self._curv_closure(X, y, N)
+            self.loss = self.loss + loss_b
+            self.H = H_b if self.H is None else self.H + H_b
+        self.n_outputs = getattr(self.backend, "n_outputs", self.n_outputs)
+        self.n_data += N
+
+    def optimize_prior_precision(self, init_prior_prec=1.0, n_steps: int = 100, lr: float = 0.1,
+                                 prior_structure: str = "scalar", verbose: bool = False):
+        """Marginal-likelihood tuning of the prior precision (baselaplace.py:419-463): Adam on
+        log prior precision; every step only re-evaluates the cheap marglik algebra."""
+        if prior_structure == "scalar":
+            shape = (1,)
+        elif prior_structure == "layerwise":
+            shape = (self.n_layers,)
+        elif prior_structure == "diag":
+            shape = (self.n_params,)
+        else:
+            raise ValueError(prior_structure)
+        log_pp = (torch.ones(shape, device=self._device) * math.log(float(init_prior_prec))).requires_grad_(True)
+        opt = torch.optim.Adam([log_pp], lr=lr)
+        for _ in range(n_steps):
+            opt.zero_grad()
+            neg = -self.log_marginal_likelihood(prior_precision=log_pp.exp())
+            neg.backward()
+            opt.step()
+        self.prior_precision = log_pp.detach().exp()
+        return self.prior_precision
+
+
+class KronLaplace(_ParametricLaplaceLite):
+    """``Laplace(model, "classification", subset_of_weights="all", hessian_structure="kron")``."""
+
+    def _init_H(self):
+        self.H = None
+        self.H_facs = None
+
+    def _curv_closure(self, X, y, N):
+        return self.backend.kron(X, y, N=N)
+
+    def fit(self, train_loader, override: bool = True) -> None:
+        if override:
+            self.H_facs = None
+        self.H = self.H_facs
+        super().fit(train_loader, override=override)
+        self.H_facs = self.H
+        self.H = self.H_facs.decompose()
+
+    @property
+    def posterior_precision(self) -> KronDecomposed:
+        pp = torch.as_tensor(self.prior_precision, device=self._device, dtype=torch.float32)
+        if pp.ndim and pp.numel() == self.n_params and self.n_params != self.n_layers:
+            raise ValueError("a diagonal prior is not representable in a Kron posterior")
+        return self.H * self._H_factor + pp
+
+    @property
+    def log_det_posterior_precision(self) -> torch.Tensor:
+        return self.posterior_precision.logdet()
+
+
+class DiagLaplace(_ParametricLaplaceLite):
+    """``hessian_structure="diag"``: H is the vector diag(GGN)."""
+
+    def _init_H(self):
+        self.H = None
+
+    def _curv_closure(self, X, y, N):
+        return self.backend.diag(X, y, N=N)
+
+    @property
+    def posterior_precision(self) -> torch.Tensor:
+        return self._H_factor * self.H + self.prior_precision_diag
+
+    @property
+    def log_det_posterior_precision(self) -> torch.Tensor:
+        return self.posterior_precision.log().sum()
+
+
+def Laplace(model, likelihood="classification", subset_of_weights="all", hessian_structure="kron",
+            **kwargs):
+    """Factory with the reference's signature (laplace/laplace.py:13-47), hot-path subset."""
+    if subset_of_weights != "all":
+        raise NotImplementedError("only subset_of_weights='all' is on the hot path")
+    table = {"kron": KronLaplace, "diag": DiagLaplace}
+    if hessian_structure not in table:
+        raise NotImplementedError(f"hessian_structure={hessian_structure!r} is outside the hot path")
+    return table[hessian_structure](model, likelihood, **kwargs)

@@ -1,0 +1,270 @@
+"""Tensor-level wrappers over the C-ABI (``include/lgnn.h``).  Every function enqueues
+hand-written sm_100a kernels on torch's current CUDA stream and returns torch tensors that
+only serve as device-memory handles.  No CPU path exists here.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream
+
+
+@dataclass
+class CSR:
+    """Row-compressed sparse matrix on the device: rowptr int64 [n_rows+1], col int32 [nnz],
+    val fp32 [nnz] (or None for a pattern)."""
+    n_rows: int
+    n_cols: int
+    rowptr: torch.Tensor
+    col: torch.Tensor
+    val: torch.Tensor | None = None
+
+    @property
+    def nnz(self) -> int:
+        return int(self.col.numel())
+
+
+# bench.py sets PROFILE = [] to collect one record per SpMM / SYRK launch: CUDA events on the
+# launching stream plus the algorithmic bytes (SpMM) or flops (SYRK) of that launch.
+PROFILE: list | None = None
+
+
+class _Timed:
+    def __init__(self, kind: str, d: int, work: float):
+        self.rec = None
+        if PROFILE is not None:
+            self.rec = {"kind": kind, "d": d, "bytes": work,
+                        "start": torch.cuda.Event(enable_timing=True),
+                        "end": torch.cuda.Event(enable_timing=True)}
+
+    def __enter__(self):
+        if self.rec is not None:
+            self.rec["start"].record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.rec is not None:
+            self.rec["end"].record()
+            PROFILE.append(self.rec)
+        return False
+
+
+def spmm_algorithmic_bytes(n_rows: int, nnz: int, d: int) -> int:
+    """col int32 + val fp32 per non-zero, int64 rowptr, one gathered source row of d floats per
+    non-zero (no-reuse model), the output."""
+    return nnz * 8 + (n_rows + 1) * 8 + nnz * d * 4 + n_rows * d * 4
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name}: expected float32, got {t.dtype}")
+    if t.dim() != 2 or t.stride(1) != 1:
+        raise ValueError(f"{name}: expected a 2-D row-major tensor (unit column stride)")
+    return t
+
+
+# ------------------------------------------------------------------------------ integer kernels
+def csr_from_edge_index(edge_index: torch.Tensor, num_nodes: int, symmetric: bool = False) -> CSR:
+    """Binary adjacency A with self loops as a CSR pattern (columns ascending, duplicates
+    collapsed).  Mirrors edge_index_to_adj + clamp + fill_diagonal_(1) (+ optional A + A^T)."""
+    lib = _lib.load()
+    if edge_index.dtype != torch.int64 or edge_index.dim() != 2 or edge_index.shape[0] != 2:
+        raise TypeError("edge_index must be an int64 tensor of shape [2, E]")
+    ei = edge_index.contiguous()
+    n, e = int(num_nodes), int(ei.shape[1])
+    dev = ei.device
+    ws_bytes = lib.lgnn_csr_build_workspace_bytes(n, e, int(symmetric))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    rowptr = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    src, dst = ei[0], ei[1]
+    check(lib.lgnn_csr_build_count(ptr(src), ptr(dst), e, n, int(symmetric), ptr(ws), ws_bytes,
+                                   ptr(rowptr), stream()), "lgnn_csr_build_count")
+    _lib.count_launches(11)
+    if int(ws[:4].view(torch.int32).item()) != 0:  # err flag (also syncs before reading nnz)
+        raise ValueError("edge_index contains node ids outside [0, num_nodes)")
+    nnz = int(rowptr[-1].item())
+    col = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
+    check(lib.lgnn_csr_build_fill(ptr(ws), ws_bytes, n, e, int(symmetric), ptr(rowptr), ptr(col),
+                                  stream()), "lgnn_csr_build_fill")
+    _lib.count_launches(1)
+    return CSR(n, n, rowptr, col, None)
+
+
+def csr_transpose(a: CSR) -> CSR:
+    lib = _lib.load()
+    dev = a.rowptr.device
+    ws_bytes = lib.lgnn_csr_transpose_workspace_bytes(a.n_rows, a.n_cols, a.nnz)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    t_rowptr = torch.empty(a.n_cols + 1, dtype=torch.int64, device=dev)
+    t_col = torch.empty(max(a.nnz, 1), dtype=torch.int32, device=dev)[: a.nnz]
+    check(lib.lgnn_csr_transpose(a.n_rows, a.n_cols, ptr(a.rowptr), ptr(a.col), ptr(t_rowptr),
+                                 ptr(t_col), ptr(ws), ws_bytes, stream()), "lgnn_csr_transpose")
+    _lib.count_launches(7)
+    return CSR(a.n_cols, a.n_rows, t_rowptr, t_col, None)
+
+
+def degree_norm(a: CSR):
+    """(deg int64 [n], dis fp32 [n]) from the pattern of A (row sums incl. self loop)."""
+    lib = _lib.load()
+    dev = a.rowptr.device
+    deg = torch.empty(a.n_rows, dtype=torch.int64, device=dev)
+    dis = torch.empty(a.n_rows, dtype=torch.float32, device=dev)
+    check(lib.lgnn_degree_norm(a.n_rows, ptr(a.rowptr), ptr(deg), ptr(dis), stream()), "lgnn_degree_norm")
+    _lib.count_launches(1)
+    return deg, dis
+
+
+def edge_values(a: CSR, dis: torch.Tensor, row_offset: int = 0) -> torch.Tensor:
+    lib = _lib.load()
+    val = torch.empty(max(a.nnz, 1), dtype=torch.float32, device=a.rowptr.device)[: a.nnz]
+    check(lib.lgnn_edge_values(a.n_rows, row_offset, ptr(a.rowptr), ptr(a.col), ptr(dis), ptr(val),
+                               stream()), "lgnn_edge_values")
+    _lib.count_launches(1)
+    return val
+
+
+def row_partition(rowptr: torch.Tensor, nparts: int) -> torch.Tensor:
+    lib = _lib.load()
+    n = int(rowptr.numel()) - 1
+    bounds = torch.empty(nparts + 1, dtype=torch.int64, device=rowptr.device)
+    check(lib.lgnn_row_partition(ptr(rowptr), n, nparts, ptr(bounds), stream()), "lgnn_row_partition")
+    _lib.count_launches(1)
+    return bounds
+
+
+def halo_columns(a: CSR, lo: int, hi: int) -> torch.Tensor:
+    """Sorted unique column ids referenced by rows [lo, hi) outside [lo, hi)."""
+    lib = _lib.load()
+    flags = torch.zeros(a.n_cols, dtype=torch.uint8, device=a.rowptr.device)
+    check(lib.lgnn_halo_mark(ptr(a.rowptr), ptr(a.col), lo, hi, ptr(flags), stream()), "lgnn_halo_mark")
+    _lib.count_launches(1)
+    return torch.nonzero(flags, as_tuple=False).flatten()
+
+
+def csr_slice_remap(a: CSR, lo: int, hi: int, bounds: torch.Tensor, pad: int) -> CSR:
+    """Rows [lo, hi) of ``a`` with columns remapped to the padded all-gather layout."""
+    lib = _lib.load()
+    dev = a.rowptr.device
+    nparts = int(bounds.numel()) - 1
+    b = int(a.rowptr[lo].item())
+    e = int(a.rowptr[hi].item())
+    nnz = e - b
+    out_rowptr = torch.empty(hi - lo + 1, dtype=torch.int64, device=dev)
+    out_col = torch.empty(max(nnz, 1), dtype=torch.int32, device=dev)[:nnz]
+    out_val = torch.empty(max(nnz, 1), dtype=torch.float32, device=dev)[:nnz] if a.val is not None else None
+    check(lib.lgnn_csr_slice_remap(ptr(a.rowptr), ptr(a.col), ptr(a.val), lo, hi, ptr(bounds), nparts,
+                                   pad, ptr(out_rowptr), ptr(out_col), ptr(out_val), stream()),
+          "lgnn_csr_slice_remap")
+    _lib.count_launches(1)
+    return CSR(hi - lo, nparts * pad, out_rowptr, out_col, out_val)
+
+
+# ------------------------------------------------------------------------------ SpMM
+def spmm(a: CSR, x: torch.Tensor, relu: bool = False, out: torch.Tensor | None = None,
+         d: int | None = None) -> torch.Tensor:
+    """Y = A @ X[:, :d]  (optionally relu'd).  x: [>= n_cols, ld] row-major fp32."""
+    lib = _lib.load()
+    _f32c(x, "x")
+    if x.shape[0] < a.n_cols:
+        raise ValueError(f"spmm: x has {x.shape[0]} rows, matrix has {a.n_cols} columns")
+    d = int(x.shape[1]) if d is None else int(d)
+    if out is None:
+        out = torch.empty(a.n_rows, d, dtype=torch.float32, device=x.device)
+    _f32c(out, "out")
+    if out.shape[0] < a.n_rows or out.shape[1] < d:
+        raise ValueError("spmm: out too small")
+    with _Timed("spmm", d, spmm_algorithmic_bytes(a.n_rows, a.nnz, d)):
+        check(lib.lgnn_spmm_f32(a.n_rows, ptr(a.rowptr), ptr(a.col), ptr(a.val), ptr(x), x.stride(0),
+                                ptr(out), out.stride(0), d, _lib.SPMM_RELU if relu else _lib.SPMM_NONE,
+                                stream()), "lgnn_spmm_f32")
+    _lib.count_launches(1)
+    return out
+
+
+# ------------------------------------------------------------------------------ loss / Hessian sqrt
+def softmax_ce_sum(logits: torch.Tensor, idx: torch.Tensor, y: torch.Tensor, C: int | None = None):
+    """(sum CE as a 0-d float64 tensor, number of argmax hits as 0-d int64)."""
+    lib = _lib.load()
+    _f32c(logits, "logits")
+    C = int(logits.shape[1]) if C is None else int(C)
+    loss = torch.zeros((), dtype=torch.float64, device=logits.device)
+    hits = torch.zeros((), dtype=torch.int64, device=logits.device)
+    idx = idx.contiguous()
+    y = y.contiguous()
+    if idx.dtype != torch.int64 or y.dtype != torch.int64:
+        raise TypeError("idx and y must be int64")
+    check(lib.lgnn_softmax_ce_sum(ptr(logits), logits.stride(0), C, ptr(idx), ptr(y), idx.numel(),
+                                  ptr(loss), ptr(hits), stream()), "lgnn_softmax_ce_sum")
+    _lib.count_launches(1)
+    return loss, hits
+
+
+def hess_rhs(logits: torch.Tensor, idx: torch.Tensor, c0: int, ncols: int, delta: torch.Tensor,
+             ldc: int, mode: str = "reference", C: int | None = None) -> torch.Tensor:
+    """Scatter-add the Hessian-sqrt columns [c0, c0+ncols) into delta ([n_nodes, ncols*ldc], zeroed)."""
+    lib = _lib.load()
+    _f32c(logits, "logits")
+    C = int(logits.shape[1]) if C is None else int(C)
+    m = {"reference": _lib.HESS_REFERENCE, "ggn": _lib.HESS_GGN}.get(mode)
+    if m is None:
+        raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {mode!r}")
+    idx = idx.contiguous()
+    check(lib.lgnn_hess_rhs_f32(ptr(logits), logits.stride(0), C, ptr(idx), idx.numel(), c0, ncols, ldc, m,
+                                ptr(delta), stream()), "lgnn_hess_rhs_f32")
+    _lib.count_launches(1)
+    return delta
+
+
+def relu_mask_mul(inp: torch.Tensor, act: torch.Tensor, group: int, out: torch.Tensor | None = None,
+                  d: int | None = None) -> torch.Tensor:
+    """out[r, :] = inp[r, :] * (act[r // group, :] > 0)."""
+    lib = _lib.load()
+    _f32c(inp, "inp"); _f32c(act, "act")
+    d = int(inp.shape[1]) if d is None else int(d)
+    out = inp if out is None else out
+    n_rows = int(act.shape[0])
+    if inp.shape[0] < n_rows * group:
+        raise ValueError("relu_mask_mul: inp has too few rows")
+    check(lib.lgnn_relu_mask_mul_f32(ptr(inp), inp.stride(0), ptr(act), act.stride(0), ptr(out),
+                                     out.stride(0), n_rows, group, d, stream()), "lgnn_relu_mask_mul_f32")
+    _lib.count_launches(1)
+    return out
+
+
+# ------------------------------------------------------------------------------ SYRK
+_SYRK_IMPL = {"auto": _lib.SYRK_AUTO, "simt": _lib.SYRK_SIMT, "tcgen05": _lib.SYRK_TCGEN05}
+_ws_cache: dict = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device.type, device.index)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def syrk(x: torch.Tensor, n: int | None = None, alpha: float = 1.0, beta: float = 0.0,
+         out: torch.Tensor | None = None, impl: str = "auto", k_rows: int | None = None) -> torch.Tensor:
+    """out = beta*out + alpha * X[:k_rows, :n]^T X[:k_rows, :n]  (both triangles)."""
+    lib = _lib.load()
+    _f32c(x, "x")
+    n = int(x.shape[1]) if n is None else int(n)
+    k_rows = int(x.shape[0]) if k_rows is None else int(k_rows)
+    if out is None:
+        if beta != 0.0:
+            raise ValueError("syrk: beta != 0 needs out")
+        out = torch.empty(n, n, dtype=torch.float32, device=x.device)
+    _f32c(out, "out")
+    code = _SYRK_IMPL[impl]
+    nbytes = lib.lgnn_syrk_workspace_bytes(k_rows, n, code)
+    ws = _workspace(nbytes, x.device)
+    with _Timed("syrk", n, float(k_rows) * n * (n + 1)):
+        check(lib.lgnn_syrk_f32(ptr(x), x.stride(0), k_rows, n, float(alpha), float(beta), ptr(out),
+                                out.stride(0), ptr(ws), ws.numel(), code, stream()), "lgnn_syrk_f32")
+    _lib.count_launches(2)
+    return out

@@ -1,0 +1,110 @@
+"""TEST DOUBLE for ``laplace_gnn_b200.ops`` — CPU implementations built on the oracle, with the
+same signatures.  Installed only by the ``fake_ops`` fixture (tests/conftest.py) so that the
+host-side logic (backend orchestration, Kron packing, Laplace drivers, the partitioned
+multi-rank path under gloo) can be exercised on a machine without a GPU.  Never shipped, never
+imported by the package.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from laplace_gnn_b200.ops import CSR
+from oracle import gcn_kfac_oracle as O
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def csr_from_edge_index(edge_index, num_nodes, symmetric=False):
+    rp, col = O.coo_to_adj_csr(_np(edge_index), num_nodes, symmetric)
+    return CSR(num_nodes, num_nodes, torch.from_numpy(rp), torch.from_numpy(col), None)
+
+
+def csr_transpose(a):
+    rp, col, _ = O.csr_transpose_pattern(_np(a.rowptr), _np(a.col), a.n_cols)
+    return CSR(a.n_cols, a.n_rows, torch.from_numpy(rp), torch.from_numpy(col), None)
+
+
+def degree_norm(a):
+    deg = np.diff(_np(a.rowptr)).astype(np.int64)
+    return torch.from_numpy(deg), torch.from_numpy(O.inv_sqrt_degree(deg))
+
+
+def edge_values(a, dis, row_offset=0):
+    rows = np.repeat(np.arange(a.n_rows, dtype=np.int64), np.diff(_np(a.rowptr))) + row_offset
+    d = _np(dis)
+    return torch.from_numpy((d[rows] * d[_np(a.col)]).astype(np.float32))
+
+
+def row_partition(rowptr, nparts):
+    return torch.from_numpy(O.row_partition(_np(rowptr), nparts))
+
+
+def halo_columns(a, lo, hi):
+    return torch.from_numpy(O.halo_columns(_np(a.rowptr), _np(a.col), lo, hi))
+
+
+def csr_slice_remap(a, lo, hi, bounds, pad):
+    rp, col = _np(a.rowptr), _np(a.col).astype(np.int64)
+    b = _np(bounds)
+    s, e = rp[lo], rp[hi]
+    c = col[s:e]
+    owner = np.searchsorted(b, c, side="right") - 1
+    new_col = (owner * pad + (c - b[owner])).astype(np.int32)
+    val = None if a.val is None else a.val[s:e].clone()
+    return CSR(hi - lo, (len(b) - 1) * pad, torch.from_numpy(rp[lo:hi + 1] - s), torch.from_numpy(new_col), val)
+
+
+def spmm(a, x, relu=False, out=None, d=None):
+    d = x.shape[1] if d is None else d
+    m = torch.sparse_csr_tensor(a.rowptr, a.col.to(torch.int64), a.val, size=(a.n_rows, x.shape[0]))
+    y = m @ x[:, :d].contiguous()
+    if relu:
+        y = torch.relu(y)
+    if out is None:
+        return y
+    out[: a.n_rows, :d] = y
+    return out
+
+
+def softmax_ce_sum(logits, idx, y, C=None):
+    C = logits.shape[1] if C is None else C
+    f = logits[idx][:, :C]
+    loss = torch.nn.functional.cross_entropy(f, y, reduction="sum").double()
+    hits = (f.argmax(1) == y).sum()
+    return loss, hits
+
+
+def hess_rhs(logits, idx, c0, ncols, delta, ldc, mode="reference", C=None):
+    C = logits.shape[1] if C is None else C
+    V = O.hess_sqrt_rhs(logits[idx][:, :C], mode)          # [m, C(col), C]
+    d3 = delta.view(delta.shape[0], ncols, ldc)
+    for g in range(ncols):
+        d3[:, g, :C].index_add_(0, idx, V[:, c0 + g, :])
+    return delta
+
+
+def relu_mask_mul(inp, act, group, out=None, d=None):
+    d = inp.shape[1] if d is None else d
+    out = inp if out is None else out
+    n = act.shape[0]
+    mask = (act[:, :d] > 0).to(inp.dtype).repeat_interleave(group, dim=0)
+    out[: n * group, :d] = inp[: n * group, :d] * mask
+    return out
+
+
+def syrk(x, n=None, alpha=1.0, beta=0.0, out=None, impl="auto", k_rows=None):
+    n = x.shape[1] if n is None else n
+    k_rows = x.shape[0] if k_rows is None else k_rows
+    xs = x[:k_rows, :n]
+    c = alpha * (xs.T @ xs)
+    if out is None:
+        return c
+    out[:n, :n] = beta * out[:n, :n] + c if beta != 0.0 else c
+    return out
+
+
+ALL = ["csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
+       "halo_columns", "csr_slice_remap", "spmm", "softmax_ce_sum", "hess_rhs", "relu_mask_mul", "syrk"]

@@ -1,0 +1,56 @@
+"""CPU: the C-ABI library loads and exports every symbol include/lgnn.h declares.
+No compute entry point is called here (there is no GPU in this environment)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+from laplace_gnn_b200 import _lib
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "lgnn.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lgnn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_all_exported_and_bound():
+    lib = _lib.load()
+    names = _declared_symbols()
+    assert len(names) >= 19
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in lgnn.h but not exported by liblgnn.so"
+        assert n in _lib.PROTOTYPES, f"{n} has no ctypes prototype in _lib.PROTOTYPES"
+    assert sorted(_lib.PROTOTYPES) == names
+
+
+def test_abi_version_and_host_only_queries():
+    lib = _lib.load()
+    assert lib.lgnn_abi_version() == 1
+    # pure host arithmetic, no device needed
+    assert lib.lgnn_csr_build_workspace_bytes(1000, 5000, 0) > 5000 * 4
+    assert lib.lgnn_csr_build_workspace_bytes(1000, 5000, 1) > lib.lgnn_csr_build_workspace_bytes(1000, 5000, 0)
+    assert lib.lgnn_syrk_workspace_bytes(10000, 64, _lib.SYRK_SIMT) > 0
+    assert lib.lgnn_csr_transpose_workspace_bytes(10, 10, 30) > 0
+
+
+def test_bad_arguments_are_rejected_before_any_launch():
+    lib = _lib.load()
+    rc = lib.lgnn_spmm_f32(-1, None, None, None, None, 4, None, 4, 4, 0, None)
+    assert rc == -1 and b"spmm" in lib.lgnn_last_error()
+    rc = lib.lgnn_hess_rhs_f32(None, 4, 4, None, 1, 0, 4, 4, 7, None, None)
+    assert rc == -1
+    rc = lib.lgnn_syrk_f32(None, 8, 10, 8, 1.0, 0.0, None, 8, None, 0, 0, None)
+    assert rc == -1
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    import pytest
+    with pytest.raises(_lib.LgnnError, match="no CPU fallback"):
+        _lib.load(str(tmp_path / "nope.so"))
+
+
+def test_cpu_tensors_are_refused():
+    import pytest, torch
+    with pytest.raises(_lib.LgnnError, match="CUDA tensors only"):
+        _lib.ptr(torch.zeros(4))

@@ -1,0 +1,295 @@
+"""GPU parity tests: every call goes through the C-ABI (liblgnn.so) on cuda:0 and is compared with
+the CPU oracle on the same seeded inputs and with the committed golden fixtures (reference outputs).
+
+Tolerances (BASELINE.json north star): bit-exact for CSR / normalisation indices / partitioning;
+<= 1e-5 relative for SpMM; <= 1e-4 relative for Kronecker factors; <= 1e-3 relative for the log
+marginal likelihood.  "relative" = max |a-b| / max |b| over the tensor.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import Golden, max_rel_err
+from helpers import build_model, check_against_golden, loader_for
+from oracle import gcn_kfac_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _ops():
+    from laplace_gnn_b200 import ops
+    return ops
+
+
+def _dev_graph(ei, n, symmetric=False):
+    import laplace_gnn_b200 as L
+    return L.Graph.from_edge_index(torch.from_numpy(ei).to(DEV), n, symmetric=symmetric)
+
+
+def _assert_graph_bit_exact(G, R):
+    for name, a, b in [("rowptr", G.ahat.rowptr, R.rowptr), ("col", G.ahat.col, R.col),
+                       ("t_rowptr", G.ahat_t.rowptr, R.t_rowptr), ("t_col", G.ahat_t.col, R.t_col),
+                       ("deg", G.deg, R.deg)]:
+        assert np.array_equal(a.cpu().numpy(), b), name
+    # fp32 values are bit-exact too: IEEE sqrt / div / mul on both sides
+    assert np.array_equal(G.dis.cpu().numpy().view(np.uint32), R.dis.view(np.uint32))
+    assert np.array_equal(G.ahat.val.cpu().numpy().view(np.uint32), R.val.view(np.uint32))
+    assert np.array_equal(G.ahat_t.val.cpu().numpy().view(np.uint32), R.t_val.view(np.uint32))
+
+
+# ---------------------------------------------------------------------------------- integer kernels
+@pytest.mark.parametrize("n,U,directed,symmetric,rmat", [
+    (1, 0, False, False, False),            # single node, no edges
+    (7, 0, True, False, False),             # empty edge list: self loops only
+    (40, 70, False, False, False),
+    (50, 400, True, False, False),          # directed, duplicates likely
+    (36, 60, True, True, False),            # symmetrise on the device
+    (2708, 5278, False, False, False),      # Cora shape
+    (19717, 44324, False, False, False),    # Pubmed shape
+    (4096, 200000, True, False, True),      # R-MAT: rows > 256 (block sort) and heavy duplicates
+    (300, 120000, True, False, False),      # dense-ish: every row long
+])
+def test_csr_build_bit_exact(n, U, directed, symmetric, rmat):
+    ei = O.synthetic_edges(n, U, seed=n + U, directed=directed, rmat=rmat)
+    G = _dev_graph(ei, n, symmetric)
+    R = O.build_graph(ei, n, symmetric)
+    _assert_graph_bit_exact(G, R)
+
+
+def test_csr_build_very_long_row_global_sort():
+    # one hub with > 8192 distinct neighbours -> in-place global-memory bitonic path
+    n = 20000
+    rng = np.random.Generator(np.random.PCG64(5))
+    hub_dst = rng.permutation(n)[:12000]
+    ei = np.concatenate([np.stack([np.zeros(12000, np.int64), hub_dst]),
+                         O.synthetic_edges(n, 30000, seed=9, directed=True)], axis=1)
+    _assert_graph_bit_exact(_dev_graph(ei, n), O.build_graph(ei, n))
+
+
+def test_csr_build_rejects_out_of_range():
+    ei = torch.tensor([[0, 1], [1, 9]], dtype=torch.int64, device=DEV)
+    with pytest.raises(ValueError):
+        _ops().csr_from_edge_index(ei, 5)
+
+
+def test_golden_graphs_bit_exact(golden):
+    g = golden
+    _assert_graph_bit_exact(_dev_graph(g.edge_index, g.n, g.symmetric), O.build_graph(g.edge_index, g.n, g.symmetric))
+
+
+@pytest.mark.parametrize("parts", [1, 2, 3, 8, 64])
+def test_row_partition_and_halo_bit_exact(parts):
+    ops = _ops()
+    ei = O.synthetic_edges(5000, 40000, seed=1, rmat=True)
+    G = _dev_graph(ei, 5000)
+    R = O.build_graph(ei, 5000)
+    b = ops.row_partition(G.ahat.rowptr, parts).cpu().numpy()
+    assert np.array_equal(b, O.row_partition(R.rowptr, parts))
+    r = min(1, parts - 1)
+    lo, hi = int(b[r]), int(b[r + 1])
+    assert np.array_equal(ops.halo_columns(G.ahat, lo, hi).cpu().numpy(), O.halo_columns(R.rowptr, R.col, lo, hi))
+    # padded all-gather remap: decoding the remapped columns gives the original ones back
+    pad = int(np.diff(b).max())
+    sl = ops.csr_slice_remap(G.ahat, lo, hi, torch.from_numpy(b).to(DEV), pad)
+    c = sl.col.cpu().numpy().astype(np.int64)
+    decoded = b[c // pad] + c % pad
+    assert np.array_equal(decoded, R.col[R.rowptr[lo]:R.rowptr[hi]])
+    assert np.array_equal(sl.rowptr.cpu().numpy(), R.rowptr[lo:hi + 1] - R.rowptr[lo])
+    assert np.array_equal(sl.val.cpu().numpy(), R.val[R.rowptr[lo]:R.rowptr[hi]])
+
+
+# ---------------------------------------------------------------------------------- SpMM
+@pytest.mark.parametrize("d", [1, 3, 7, 16, 47, 64, 100, 128, 256, 376, 1024, 2048])
+@pytest.mark.parametrize("relu", [False, True])
+def test_spmm_matches_oracle(d, relu):
+    ops = _ops()
+    n = 3000
+    ei = O.synthetic_edges(n, 20000, seed=d, directed=True, rmat=(d % 2 == 0))
+    G, R = _dev_graph(ei, n), O.build_graph(ei, n)
+    rng = np.random.Generator(np.random.PCG64(d))
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    xd = torch.from_numpy(x).to(DEV)
+    for transpose, csr in ((False, G.ahat), (True, G.ahat_t)):
+        ref = O.spmm(R, x, transpose=transpose, dtype=torch.float64)
+        if relu:
+            ref = torch.relu(ref)
+        y = ops.spmm(csr, xd, relu=relu)
+        assert max_rel_err(y.cpu().numpy(), ref.numpy()) <= 1e-5
+
+
+def test_spmm_strided_and_unaligned_operands():
+    ops = _ops()
+    n, d = 1000, 24
+    ei = O.synthetic_edges(n, 6000, seed=2)
+    G, R = _dev_graph(ei, n), O.build_graph(ei, n)
+    big = torch.randn(n, 40, device=DEV)
+    ref = O.spmm(R, big[:, :d].cpu().numpy(), dtype=torch.float64).numpy()
+    out = torch.zeros(n, 32, device=DEV)
+    ops.spmm(G.ahat, big, out=out, d=d)                      # ld != d, vector path
+    assert max_rel_err(out[:, :d].cpu().numpy(), ref) <= 1e-5 and float(out[:, d:].abs().max()) == 0.0
+    odd = torch.randn(n, 41, device=DEV)[:, 1:]              # misaligned base -> scalar path
+    ref2 = O.spmm(R, odd[:, :d].cpu().numpy(), dtype=torch.float64).numpy()
+    assert max_rel_err(ops.spmm(G.ahat, odd, d=d).cpu().numpy(), ref2) <= 1e-5
+
+
+def test_spmm_linearity_and_transpose_adjoint_at_scale():
+    """Size-independent properties on a graph far too big for the oracle's comfort:
+    Â(ax + by) = aÂx + bÂy and <Âx, y> = <x, Â^T y>."""
+    ops = _ops()
+    n, d = 400_000, 256
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    ei = torch.randint(0, n, (2, 4_000_000), device=DEV, generator=gen)
+    import laplace_gnn_b200 as L
+    G = L.Graph.from_edge_index(ei, n)
+    x = torch.randn(n, d, device=DEV, generator=gen)
+    y = torch.randn(n, d, device=DEV, generator=gen)
+    lhs = ops.spmm(G.ahat, 0.5 * x - 2.0 * y)
+    rhs = 0.5 * ops.spmm(G.ahat, x) - 2.0 * ops.spmm(G.ahat, y)
+    assert float((lhs - rhs).abs().max()) <= 1e-5 * float(rhs.abs().max())
+    a = (ops.spmm(G.ahat, x).double() * y.double()).sum()
+    b = (x.double() * ops.spmm(G.ahat_t, y).double()).sum()
+    assert abs(float(a - b)) <= 1e-6 * abs(float(a))
+    # rows of a row-stochastic-like check: Â 1 has entries sum_j dis_i dis_j over in-neighbours
+    ones = torch.ones(n, 4, device=DEV)
+    deg_in = ops.spmm(G.ahat, ones)[:, 0]
+    assert torch.isfinite(deg_in).all() and float(deg_in.min()) > 0
+
+
+# ---------------------------------------------------------------------------------- loss / Hessian sqrt / mask
+@pytest.mark.parametrize("C", [2, 3, 7, 40, 47, 200])
+@pytest.mark.parametrize("mode", ["reference", "ggn"])
+def test_hess_rhs_and_loss_match_oracle(C, mode):
+    ops = _ops()
+    n, m = 500, 300
+    rng = np.random.Generator(np.random.PCG64(C))
+    logits = (3 * rng.standard_normal((n, C))).astype(np.float32)
+    idx = np.sort(rng.permutation(n)[:m]).astype(np.int64)
+    idx[5] = idx[4]                                       # duplicate train index accumulates
+    y = rng.integers(0, C, m).astype(np.int64)
+    ld = (C + 3) // 4 * 4
+    lg = torch.zeros(n, ld, device=DEV)
+    lg[:, :C] = torch.from_numpy(logits).to(DEV)
+    idx_d, y_d = torch.from_numpy(idx).to(DEV), torch.from_numpy(y).to(DEV)
+    loss, hits = ops.softmax_ce_sum(lg, idx_d, y_d, C=C)
+    f = torch.from_numpy(logits)[torch.from_numpy(idx)]
+    ref_loss = O.cross_entropy_sum(f.double(), y)
+    assert abs(float(loss) - float(ref_loss)) <= 1e-6 * abs(float(ref_loss))
+    assert int(hits) == int((f.argmax(1).numpy() == y).sum())
+    V = O.hess_sqrt_rhs(f.double(), mode)                 # [m, C, C]
+    c0, g = (1, min(3, C - 1))
+    delta = torch.zeros(n, g * ld, device=DEV)
+    ops.hess_rhs(lg, idx_d, c0, g, delta, ld, mode, C=C)
+    ref = torch.zeros(n, g, ld, dtype=torch.float64)
+    for k in range(g):
+        ref[:, k, :C].index_add_(0, torch.from_numpy(idx), V[:, c0 + k, :])
+    assert max_rel_err(delta.cpu().numpy(), ref.view(n, g * ld).numpy()) <= 1e-5
+
+
+def test_relu_mask_mul():
+    ops = _ops()
+    n, g, d = 777, 5, 64
+    act = torch.relu(torch.randn(n, d, device=DEV))
+    x = torch.randn(n * g, d, device=DEV)
+    ref = x * (act > 0).float().repeat_interleave(g, dim=0)
+    assert torch.equal(ops.relu_mask_mul(x.clone(), act, g), ref)
+    x2 = torch.randn(n * g, 7, device=DEV)                # scalar path
+    act2 = torch.relu(torch.randn(n, 7, device=DEV))
+    assert torch.equal(ops.relu_mask_mul(x2.clone(), act2, g), x2 * (act2 > 0).float().repeat_interleave(g, dim=0))
+
+
+# ---------------------------------------------------------------------------------- SYRK (CUDA cores)
+@pytest.mark.parametrize("k,n", [(1, 5), (100, 3), (2708, 16), (5000, 47), (19717, 64), (3000, 256),
+                                  (2708, 1433), (50_000, 100), (33, 130)])
+def test_syrk_simt_matches_fp64(k, n):
+    ops = _ops()
+    x = torch.randn(k, n, device=DEV)
+    ref = (x.double().T @ x.double())
+    c = ops.syrk(x, impl="simt")
+    assert max_rel_err(c.cpu().numpy(), ref.cpu().numpy()) <= 1e-5
+    assert torch.equal(c, c.T)
+    c2 = ops.syrk(x, alpha=0.5, beta=1.0, out=c.clone(), impl="simt")
+    assert max_rel_err(c2.cpu().numpy(), (1.5 * ref).cpu().numpy()) <= 1e-5
+    # run-to-run bit reproducibility (fixed-order split-K reduction)
+    assert torch.equal(ops.syrk(x, impl="simt"), c)
+
+
+# ---------------------------------------------------------------------------------- end to end vs the reference goldens
+@pytest.mark.parametrize("impl", ["simt"])
+def test_kron_fit_marglik_match_reference_goldens(golden, impl):
+    import laplace_gnn_b200 as L
+    g = golden
+    model = build_model(g, DEV)
+    la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs={"syrk_impl": impl})
+    la.fit(loader_for(g, DEV))
+    check_against_golden(g, la.loss, la.H_facs.kfacs, la.log_marginal_likelihood())
+    assert la.H_facs.kfacs[0][0].is_cuda
+
+
+def test_column_grouping_and_ggn_mode_match_oracle():
+    import laplace_gnn_b200 as L
+    g = Golden("tiny_directed_3l")
+    model = build_model(g, DEV)
+    idx, y = torch.from_numpy(g.idx).to(DEV), torch.from_numpy(g.y).to(DEV)
+    R = O.build_graph(g.edge_index, g.n)
+    for mode in ("reference", "ggn"):
+        _, ref = O.kron_factors(R, g.x, g.Ws, g.bs, g.idx, g.y, len(g.y), mode, torch.float64)
+        for budget in (None, 1):   # 1 byte -> one Hessian-sqrt column per group
+            be = L.B200GGN(model, "classification", hess_sqrt=mode, rhs_tile_bytes=budget, syrk_impl="simt")
+            _, kron = be.kron(idx, y, N=len(y))
+            for fa, fb in zip(kron.kfacs, ref):
+                for a, b in zip(fa, fb):
+                    assert max_rel_err(a.cpu().numpy(), b.numpy()) <= 1e-4
+
+
+def test_training_step_gradients_match_dense_autograd():
+    """GCNConvFunction backward vs the reference formulation (dense Â, torch autograd)."""
+    g = Golden("tiny_directed_dups_2l")
+    model = build_model(g, DEV)
+    model.eval()
+    idx, y = torch.from_numpy(g.idx).to(DEV), torch.from_numpy(g.y).to(DEV)
+    torch.nn.functional.cross_entropy(model(idx), y).backward()
+    ahat = torch.from_numpy(g.z["ahat_dense"]).double()
+    Ws = [torch.from_numpy(w).double().requires_grad_(True) for w in g.Ws]
+    bs = [torch.from_numpy(b).double().requires_grad_(True) for b in g.bs]
+    h = torch.from_numpy(g.x).double()
+    for l in range(g.L):
+        h = ahat @ (h @ Ws[l].T + bs[l])
+        if l < g.L - 1:
+            h = torch.relu(h)
+    torch.nn.functional.cross_entropy(h[torch.from_numpy(g.idx)], torch.from_numpy(g.y)).backward()
+    for l, conv in enumerate(model.convs):
+        assert max_rel_err(conv.lin.weight.grad.cpu().numpy(), Ws[l].grad.numpy()) <= 1e-4
+        assert max_rel_err(conv.lin.bias.grad.cpu().numpy(), bs[l].grad.numpy()) <= 1e-4
+
+
+def test_arxiv_shape_properties():
+    """ogbn-arxiv-shaped synthetic graph (too slow for the reference): structural properties of the
+    result — symmetric PSD factors, A_l = H^T H / N reproduced by torch, finite marglik — and
+    agreement of the two Hessian-sqrt column groupings."""
+    import laplace_gnn_b200 as L
+    n, F, C, h, Lyr = 169_343, 128, 40, 256, 3
+    gen = torch.Generator(device=DEV).manual_seed(0)
+    src = torch.randint(0, n, (1_166_243,), device=DEV, generator=gen)
+    dst = torch.randint(0, n, (1_166_243,), device=DEV, generator=gen)
+    ei = torch.stack([torch.cat([src, dst]), torch.cat([dst, src])])
+    graph = L.Graph.from_edge_index(ei, n, assume_undirected=True)
+    X = torch.randn(n, F, device=DEV, generator=gen)
+    torch.manual_seed(0)
+    model = L.SparseGCN(F, h, C, Lyr, X, graph).to(DEV)
+    idx = torch.randperm(n, device=DEV, generator=gen)[: int(0.6 * n)].sort().values
+    y = torch.randint(0, C, (idx.numel(),), device=DEV, generator=gen)
+    be = L.B200GGN(model, "classification", syrk_impl="simt")
+    loss, kron = be.kron(idx, y, N=idx.numel())
+    be2 = L.B200GGN(model, "classification", syrk_impl="simt", rhs_tile_bytes=2 * n * 256 * 4 * 7)
+    _, kron2 = be2.kron(idx, y, N=idx.numel())
+    assert be2.last_stats["group"] == 7 and be.last_stats["group"] > 7
+    for fa, fb in zip(kron.kfacs, kron2.kfacs):
+        for a, b in zip(fa, fb):
+            assert torch.equal(a, a.T)
+            assert float(torch.linalg.eigvalsh(a.double()).min()) >= -1e-4 * float(a.abs().max())
+            assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-4
+    A0 = (X.double().T @ X.double() / idx.numel()).float()
+    assert max_rel_err(kron.kfacs[0][1].cpu().numpy(), A0.cpu().numpy()) <= 1e-4
+    assert torch.isfinite(loss)

@@ -1,0 +1,62 @@
+"""GPU: the tcgen05 / TMA 3xTF32 SYRK kernel against fp64 and against the CUDA-core kernel.
+Tolerance: Kronecker factors <= 1e-4 relative (north star); 3xTF32 lands near 1e-6."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import Golden, max_rel_err
+from helpers import build_model, check_against_golden, loader_for
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ops():
+    from laplace_gnn_b200 import ops
+    return ops
+
+
+@pytest.mark.parametrize("k,n", [(16, 16), (1, 8), (100, 16), (2708, 16), (5000, 47), (19717, 64),
+                                  (4096, 128), (3000, 130), (10_000, 256), (1_000_000, 256),
+                                  (333_333, 47), (17, 255)])
+def test_syrk_tcgen05_matches_fp64(k, n):
+    ops = _ops()
+    gen = torch.Generator(device=DEV).manual_seed(k + n)
+    x = torch.randn(k, n, device=DEV, generator=gen) * 3.0 + 0.5     # non-zero mean: sums do not cancel
+    ref = x.double().T @ x.double()
+    c = ops.syrk(x, impl="tcgen05")
+    err = max_rel_err(c.cpu().numpy(), ref.cpu().numpy())
+    assert err <= 2e-6, err                                           # fp32-faithful, far inside 1e-4
+    assert torch.equal(c, c.T)
+    assert torch.equal(ops.syrk(x, impl="tcgen05"), c)                # deterministic reduction
+    simt = ops.syrk(x, impl="simt")
+    assert max_rel_err(c.cpu().numpy(), simt.cpu().numpy()) <= 1e-5
+
+
+def test_syrk_tcgen05_alpha_beta_and_leading_dimension():
+    ops = _ops()
+    x = torch.randn(5000, 64, device=DEV)
+    ref = (x[:, :47].double().T @ x[:, :47].double())
+    c0 = torch.ones(47, 47, device=DEV)
+    c = ops.syrk(x, n=47, alpha=0.25, beta=2.0, out=c0.clone(), impl="tcgen05")   # ldx=64 > n=47
+    assert max_rel_err(c.cpu().numpy(), (0.25 * ref + 2.0).cpu().numpy()) <= 2e-6
+    c = ops.syrk(x, n=47, k_rows=1234, impl="tcgen05")
+    ref2 = x[:1234, :47].double().T @ x[:1234, :47].double()
+    assert max_rel_err(c.cpu().numpy(), ref2.cpu().numpy()) <= 2e-6
+
+
+def test_syrk_tcgen05_is_3xtf32_not_plain_tf32():
+    """A plain (1x) TF32 product would be off by ~1e-3 on this input; 3xTF32 is fp32-faithful."""
+    ops = _ops()
+    x = (1.0 + torch.rand(200_000, 32, device=DEV) * 1e-3)            # mantissa bits below tf32 matter
+    ref = x.double().T @ x.double()
+    assert max_rel_err(ops.syrk(x, impl="tcgen05").cpu().numpy(), ref.cpu().numpy()) <= 2e-6
+
+
+def test_kron_fit_with_tcgen05_matches_reference_goldens(golden):
+    import laplace_gnn_b200 as L
+    g = golden
+    model = build_model(g, DEV)
+    la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs={"syrk_impl": "auto"})
+    la.fit(loader_for(g, DEV))
+    check_against_golden(g, la.loss, la.H_facs.kfacs, la.log_marginal_likelihood())
