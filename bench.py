@@ -210,8 +210,6 @@ def main():
             host[k] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
             host[k].copy_(t)
 
-    from torch.utils.data import DataLoader, TensorDataset
-
     def build_model(ei_d, X_d):
         graph = L.Graph.from_edge_index(ei_d, n, assume_undirected=True)
         torch.manual_seed(0)
@@ -224,7 +222,7 @@ def main():
     bk = {"hess_sqrt": args.hess_sqrt, "syrk_impl": args.syrk}
     if pg is not None:
         bk["process_group"] = pg
-    loader = DataLoader(TensorDataset(idx, y), batch_size=idx.numel(), shuffle=False)
+    loader = L.TensorBatchLoader(idx, y)      # one full batch, no per-sample collation
 
     def step(mdl, ldr):
         la = L.Laplace(mdl, "classification", subset_of_weights="all", hessian_structure="kron",
@@ -274,17 +272,23 @@ def main():
             a = groups.setdefault(gk, {"ms": 0.0, "launches": 0, "bytes": rec["bytes"]})
             a["ms"] += ms
             a["launches"] += 1
-        (kind, d), top = max(groups.items(), key=lambda kv: kv[1]["ms"])
-        avg_ms = top["ms"] / top["launches"]
-        achieved = top["bytes"] / (avg_ms * 1e-3) / 1e9
         spmm_ms = sum(v["ms"] for (k, _), v in groups.items() if k == "spmm") / args.steps
         syrk_ms = sum(v["ms"] for (k, _), v in groups.items() if k == "syrk") / args.steps
+        by_kind = {}
+        for (k, _), v in groups.items():
+            by_kind[k] = by_kind.get(k, 0.0) + v["ms"] / args.steps
+        # the dominant kernel is the multi-RHS SpMM; report the roofline of its widest launch group
+        spmm_groups = {kv[0]: kv[1] for kv in groups.items() if kv[0][0] == "spmm"}
+        (kind, d), top = max(spmm_groups.items(), key=lambda kv: kv[1]["ms"])
+        avg_ms = top["ms"] / top["launches"]
+        achieved = top["bytes"] / (avg_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None, "kernel": f"{kind} d={d}",
                 "avg_launch_ms": avg_ms, "launches_per_step": top["launches"] / args.steps,
                 "share_of_step": top["ms"] / args.steps / ms_step, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": top["bytes"],
-                "spmm_ms_per_step": spmm_ms, "syrk_ms_per_step": syrk_ms}
+                "spmm_ms_per_step": spmm_ms, "syrk_ms_per_step": syrk_ms,
+                "ms_per_step_by_kind": {k: round(v, 2) for k, v in sorted(by_kind.items())}}
 
     # ---------------- end to end from pinned host buffers through the public API
     e2e = None
@@ -299,7 +303,7 @@ def main():
             idx_d = host["idx"].to(dev, non_blocking=True)
             y_d = host["y"].to(dev, non_blocking=True)
             mdl = build_model(ei_d, X_d)
-            ldr = DataLoader(TensorDataset(idx_d, y_d), batch_size=idx_d.numel(), shuffle=False)
+            ldr = L.TensorBatchLoader(idx_d, y_d)
             _, ml_ = step(mdl, ldr)
             return float(ml_.cpu())           # D2H read of the result
 

@@ -11,7 +11,8 @@ from . import _lib, ops  # noqa: F401
 from .graph import Graph  # noqa: F401
 from .gcn import GCNConvFunction, SparseGCN, SparseGCNConv  # noqa: F401
 from .curvature import B200GGN, make_backend  # noqa: F401
+from .data import TensorBatchLoader  # noqa: F401
 from .kron import DiagLaplace, Kron, KronDecomposed, KronLaplace, Laplace  # noqa: F401
 
 __all__ = ["Graph", "SparseGCN", "SparseGCNConv", "GCNConvFunction", "B200GGN", "make_backend",
-           "Laplace", "KronLaplace", "DiagLaplace", "Kron", "KronDecomposed", "ops"]
+           "TensorBatchLoader", "Laplace", "KronLaplace", "DiagLaplace", "Kron", "KronDecomposed", "ops"]

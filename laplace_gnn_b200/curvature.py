@@ -119,7 +119,8 @@ class _B200KFAC:
         Hs = [h]
         L = len(Ws)
         for l in range(L):
-            z = torch.mm(h, Ws[l].t()) if bs[l] is None else torch.addmm(bs[l], h, Ws[l].t())
+            with ops.timed("gemm_fwd", Ws[l].shape[0], 2.0 * h.shape[0] * Ws[l].numel()):
+                z = torch.mm(h, Ws[l].t()) if bs[l] is None else torch.addmm(bs[l], h, Ws[l].t())
             h = ops.spmm(g.ahat, z, relu=(l < L - 1))
             if l < L - 1:
                 Hs.append(h)
@@ -175,8 +176,9 @@ class _B200KFAC:
         for c0 in range(0, C, grp):
             gc = min(grp, C - c0)
             delta = buf_a[: n * gc * c_pad].view(n, gc * c_pad)
-            delta.zero_()
-            ops.hess_rhs(logits, idx, c0, gc, delta, c_pad, self.hess_sqrt)
+            with ops.timed("hess_rhs", gc):
+                delta.zero_()
+                ops.hess_rhs(logits, idx, c0, gc, delta, c_pad, self.hess_sqrt)
             width, ld = C, c_pad
             for l in range(L - 1, -1, -1):
                 gz = buf_b[: n * gc * ld].view(n, gc * ld)
@@ -186,8 +188,10 @@ class _B200KFAC:
                 if l > 0:
                     d_prev = dims[l - 1]
                     nxt = buf_a[: n * gc * d_prev].view(n * gc, d_prev)
-                    torch.mm(gz_rows[:, :width], Ws[l], out=nxt)
-                    ops.relu_mask_mul(nxt, Hs[l], gc)
+                    with ops.timed("gemm_bwd", d_prev, 2.0 * n * gc * width * d_prev):
+                        torch.mm(gz_rows[:, :width], Ws[l], out=nxt)
+                    with ops.timed("relu_mask", d_prev, 2.0 * n * gc * d_prev * 4):
+                        ops.relu_mask_mul(nxt, Hs[l], gc)
                     delta = nxt.view(n, gc * d_prev)
                     width, ld = d_prev, d_prev
         self.last_stats = {"group": grp, "n_groups": (C + grp - 1) // grp, "M": M, "C": C}

@@ -32,6 +32,11 @@ class CSR:
 PROFILE: list | None = None
 
 
+def timed(kind: str, d: int = 0, work: float = 0.0):
+    """Context manager used by the backend around library GEMMs / small kernels when profiling."""
+    return _Timed(kind, d, work)
+
+
 class _Timed:
     def __init__(self, kind: str, d: int, work: float):
         self.rec = None
