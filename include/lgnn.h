@@ -41,7 +41,12 @@ enum {
 };
 
 /* SpMM epilogue flags */
-enum { LGNN_SPMM_NONE = 0, LGNN_SPMM_RELU = 1 };
+enum {
+  LGNN_SPMM_NONE = 0,
+  LGNN_SPMM_RELU = 1,       /* y = max(y, 0) fused into the store */
+  LGNN_SPMM_FORCE_LDG = 2,  /* kernel selection override (tests / profiling): warp-per-row LDG.128 kernel */
+  LGNN_SPMM_FORCE_BULK = 4  /* kernel selection override: bulk-async (TMA 1-D copy) shared-memory ring kernel */
+};
 
 /* SYRK implementation selector */
 enum {
@@ -122,11 +127,13 @@ int lgnn_csr_slice_remap(const int64_t* rowptr, const int32_t* col, const float*
  * Replaces `adj @ self.lin(x)` (gnn/models/layers.py:45-46) with a sparse Â, its autograd
  * backward Â^T @ grad, and — with d = (number of Hessian-sqrt columns) x (layer width) — the C
  * backward passes of curvlinops/kfac.py:653-661 in ONE multi-RHS pass.
- * X: [*, ldx] row-major fp32; Y: [n_rows, ldy].  The 128-bit path needs X, Y 16-byte aligned
- * and d, ldx, ldy multiples of 4; anything else takes the scalar path. */
-int lgnn_spmm_f32(int64_t n_rows, const int64_t* rowptr, const int32_t* col, const float* val,
-                  const float* x, int64_t ldx, float* y, int64_t ldy, int64_t d, int flags,
-                  lgnn_stream_t stream);
+ * X: [*, ldx] row-major fp32; Y: [n_rows, ldy]; nnz = rowptr[n_rows] (host copy, sizes the grid).
+ * The 128-bit paths need X, Y 16-byte aligned and d, ldx, ldy multiples of 4; anything else takes
+ * the scalar path.  d >= 512 uses the bulk-async shared-memory ring kernel, narrower d the
+ * warp-per-row kernel. */
+int lgnn_spmm_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr, const int32_t* col,
+                  const float* val, const float* x, int64_t ldx, float* y, int64_t ldy, int64_t d,
+                  int flags, lgnn_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * loss + Hessian-sqrt right-hand sides

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "liblgnn.so")
 
 OK = 0
 HESS_REFERENCE, HESS_GGN = 0, 1
-SPMM_NONE, SPMM_RELU = 0, 1
+SPMM_NONE, SPMM_RELU, SPMM_FORCE_LDG, SPMM_FORCE_BULK = 0, 1, 2, 4
 SYRK_AUTO, SYRK_SIMT, SYRK_TCGEN05 = 0, 1, 2
 
 _i64, _i32, _f32, _vp, _sz = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_size_t
@@ -36,7 +36,7 @@ PROTOTYPES = {
     "lgnn_row_partition": (C.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "lgnn_halo_mark": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "lgnn_csr_slice_remap": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
-    "lgnn_spmm_f32": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, C.c_int, _vp]),
+    "lgnn_spmm_f32": (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, C.c_int, _vp]),
     "lgnn_softmax_ce_sum": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
     "lgnn_hess_rhs_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, C.c_int, _vp, _vp]),
     "lgnn_relu_mask_mul_f32": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i64, _vp]),

@@ -29,7 +29,7 @@ __device__ __forceinline__ void fma4(float4& a, float v, const float4& x) {
 
 // VEC float4 per lane per chunk (chunk = VEC*128 floats); d4 = d/4.
 template <int VEC, int UNROLL>
-__global__ void __launch_bounds__(SPMM_THREADS) spmm_vec_kernel(
+__global__ void __launch_bounds__(SPMM_THREADS, 2) spmm_vec_kernel(
     int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     const float* __restrict__ val, const float* __restrict__ x, int64_t ldx, float* __restrict__ y,
     int64_t ldy, int d4, int n_chunks, int flags) {
@@ -137,39 +137,251 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm_scalar_kernel(
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Wide SpMM (d >= 512): bulk-async gather through a shared-memory ring.
+//
+// One CTA owns a block of consecutive rows holding ~BULK_NNZ_PER_CTA non-zeros (found by a binary
+// search in rowptr, so CTAs are nnz-balanced) and one column range of at most 4096 floats.  A
+// producer warp walks the (col, val) stream of those rows; every lane issues, for its neighbour, ONE
+// cp.async.bulk (the TMA engine's 1-D copy) of the whole <= 16 KB piece of the source row into a
+// ring stage, completion signalled on the stage's mbarrier.  Up to ~190 KB of gathered rows are in
+// flight per SM without holding a single register, which is what it takes to keep HBM busy with
+// dependent random accesses.  Eight consumer warps wait on the stage, read it back conflict-free
+// (consecutive float4 per lane), FMA into register accumulators, and release the stage; at the end
+// of a row they store the row of Y (relu fused).
+constexpr int BULK_CONSUMERS = 256;
+constexpr int BULK_THREADS = BULK_CONSUMERS + 32;
+constexpr int BULK_MAX_STAGES = 32;
+constexpr int BULK_NNZ_PER_CTA = 4096;
+constexpr int BULK_SMEM_RING = 192 * 1024;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void bulk_mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void bulk_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 27)) __trap();  // a protocol bug traps instead of hanging the GPU
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+      : "memory");
+}
+
+// first row r in [0, n_rows] with rowptr[r] >= target
+__device__ __forceinline__ int64_t row_lower_bound(const int64_t* __restrict__ rowptr, int64_t n_rows,
+                                                   int64_t target) {
+  int64_t lo = 0, hi = n_rows;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (__ldg(rowptr + mid) < target) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+template <int VPT>  // float4 accumulators per consumer thread; column range <= VPT*256 float4
+__global__ void __launch_bounds__(BULK_THREADS, 1) spmm_bulk_kernel(
+    int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+    const float* __restrict__ val, const float* __restrict__ x, int64_t ldx, float* __restrict__ y,
+    int64_t ldy, int d4, int range4, int stages, int stage_bytes, int64_t nnz_per_cta, int flags) {
+  extern __shared__ uint8_t bulk_smem_[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bulk_smem_) + 127) & ~(uintptr_t)127);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)stages * stage_bytes);
+  uint64_t* empty = full + BULK_MAX_STAGES;
+  float* meta = reinterpret_cast<float*>(empty + BULK_MAX_STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c4_0 = blockIdx.x * range4;                       // first float4 column of this range
+  const int w4 = min(range4, d4 - c4_0);                      // float4 columns in this range
+  const uint32_t bytes = (uint32_t)w4 * 16u;
+
+  const int64_t nnz = __ldg(rowptr + n_rows);
+  const int64_t t_beg = (int64_t)blockIdx.y * nnz_per_cta;
+  if (blockIdx.y > 0 && t_beg >= nnz) return;
+  const int64_t row_beg = blockIdx.y == 0 ? 0 : row_lower_bound(rowptr, n_rows, t_beg);
+  const int64_t row_end = (blockIdx.y == gridDim.y - 1 || t_beg + nnz_per_cta >= nnz)
+                              ? n_rows
+                              : row_lower_bound(rowptr, n_rows, t_beg + nnz_per_cta);
+  if (row_beg >= row_end) return;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) {
+      bulk_mbar_init(smem_addr(&full[i]), 1);
+      bulk_mbar_init(smem_addr(&empty[i]), BULK_CONSUMERS / 32);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t k_beg = __ldg(rowptr + row_beg), k_end = __ldg(rowptr + row_end);
+
+  if (warp == BULK_CONSUMERS / 32) {
+    // ===================================================================== producer warp
+    const float* xb = x + (int64_t)c4_0 * 4;
+    for (int64_t k0 = k_beg; k0 < k_end; k0 += 32) {
+      const int64_t k = k0 + lane;
+      const bool valid = k < k_end;
+      int32_t c = 0;
+      float v = 0.f;
+      if (valid) {
+        c = __ldg(col + k);
+        v = __ldg(val + k);
+      }
+      const int64_t it = k - k_beg;
+      const int st = (int)(it % stages);
+      const uint32_t ph = (uint32_t)((it / stages) & 1);
+      // lanes whose stages coincide (stages < 32) go in successive sub-batches
+      for (int sub = 0; sub * stages < 32; ++sub) {
+        if (valid && lane / stages == sub) {
+          bulk_mbar_wait(smem_addr(&empty[st]), ph ^ 1u);
+          meta[st] = v;
+          const uint32_t bar = smem_addr(&full[st]);
+          bulk_mbar_expect_tx(bar, bytes);
+          bulk_g2s(smem_addr(ring + (size_t)st * stage_bytes), xb + (int64_t)c * ldx, bytes, bar);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================================================================== consumer warps
+    const int t = threadIdx.x;
+    bool act[VPT];
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) act[j] = (t + j * BULK_CONSUMERS) < w4;
+    int64_t it = 0;
+    int64_t k_row = k_beg;
+    for (int64_t row = row_beg; row < row_end; ++row) {
+      const int64_t k_next = __ldg(rowptr + row + 1);
+      float4 acc[VPT];
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int64_t k = k_row; k < k_next; ++k, ++it) {
+        const int st = (int)(it % stages);
+        const uint32_t ph = (uint32_t)((it / stages) & 1);
+        bulk_mbar_wait(smem_addr(&full[st]), ph);
+        const float v = meta[st];
+        const float4* src = reinterpret_cast<const float4*>(ring + (size_t)st * stage_bytes) + t;
+        float4 b[VPT];
+#pragma unroll
+        for (int j = 0; j < VPT; ++j)
+          if (act[j]) b[j] = src[j * BULK_CONSUMERS];
+#pragma unroll
+        for (int j = 0; j < VPT; ++j)
+          if (act[j]) fma4(acc[j], v, b[j]);
+        __syncwarp();
+        if (lane == 0) bulk_mbar_arrive(smem_addr(&empty[st]));
+      }
+      k_row = k_next;
+      float4* dst = reinterpret_cast<float4*>(y + row * ldy) + c4_0 + t;
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        if (!act[j]) continue;
+        float4 a = acc[j];
+        if (flags & LGNN_SPMM_RELU) {
+          a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+        }
+        dst[j * BULK_CONSUMERS] = a;
+      }
+    }
+  }
+}
+
+template <int VPT>
+static int launch_bulk(int64_t n_rows, const int64_t* rowptr, const int32_t* col, const float* val,
+                       const float* x, int64_t ldx, float* y, int64_t ldy, int d4, int n_ranges,
+                       int range4, int64_t nnz_hint, int flags, cudaStream_t st) {
+  const int stage_bytes = (range4 * 16 + 127) / 128 * 128;
+  int stages = BULK_SMEM_RING / stage_bytes;
+  if (stages > BULK_MAX_STAGES) stages = BULK_MAX_STAGES;
+  const size_t smem = 128 + (size_t)stages * stage_bytes + 2 * BULK_MAX_STAGES * sizeof(uint64_t) +
+                      BULK_MAX_STAGES * sizeof(float);
+  LGNN_CUDA_TRY(cudaFuncSetAttribute(spmm_bulk_kernel<VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t blocks_y = (nnz_hint + BULK_NNZ_PER_CTA - 1) / BULK_NNZ_PER_CTA;
+  if (blocks_y < 1) blocks_y = 1;
+  int64_t per_cta = BULK_NNZ_PER_CTA;
+  if (blocks_y > 65535) {  // grid.y limit: fatter CTAs
+    per_cta = (nnz_hint + 65534) / 65535;
+    blocks_y = (nnz_hint + per_cta - 1) / per_cta;
+  }
+  dim3 grid((unsigned)n_ranges, (unsigned)blocks_y);
+  spmm_bulk_kernel<VPT><<<grid, BULK_THREADS, smem, st>>>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4,
+                                                         range4, stages, stage_bytes, per_cta, flags);
+  LGNN_LAUNCH_CHECK("spmm_bulk_kernel");
+  return LGNN_OK;
+}
+
 }  // namespace lgnn
 
 using namespace lgnn;
 
-extern "C" int lgnn_spmm_f32(int64_t n_rows, const int64_t* rowptr, const int32_t* col,
+extern "C" int lgnn_spmm_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr, const int32_t* col,
                              const float* val, const float* x, int64_t ldx, float* y, int64_t ldy,
                              int64_t d, int flags, lgnn_stream_t stream) {
-  if (n_rows < 0 || d < 0 || ldx < d || ldy < d) return fail(LGNN_E_BADARG, "spmm: bad shape (n_rows=%lld d=%lld ldx=%lld ldy=%lld)", (long long)n_rows, (long long)d, (long long)ldx, (long long)ldy);
+  if (n_rows < 0 || nnz < 0 || d < 0 || ldx < d || ldy < d) return fail(LGNN_E_BADARG, "spmm: bad shape (n_rows=%lld d=%lld ldx=%lld ldy=%lld)", (long long)n_rows, (long long)d, (long long)ldx, (long long)ldy);
   if (n_rows == 0 || d == 0) return LGNN_OK;
   if (!rowptr || !x || !y) return fail(LGNN_E_BADARG, "spmm: null pointer");
+  if (nnz > 0 && (!col || !val)) return fail(LGNN_E_BADARG, "spmm: null col / val");
   if (d > (int64_t)1 << 24) return fail(LGNN_E_UNSUPPORTED, "spmm: d too large");
   cudaStream_t st = as_stream(stream);
   const bool vec_ok = (d % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) &&
                       ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
   const int warps_per_block = SPMM_THREADS / 32;
+  const int epi = flags & LGNN_SPMM_RELU;
+  bool bulk = vec_ok && d >= 512;
+  if (flags & LGNN_SPMM_FORCE_LDG) bulk = false;
+  if (flags & LGNN_SPMM_FORCE_BULK) {
+    if (!vec_ok) return fail(LGNN_E_ALIGN, "spmm: the bulk path needs 16-byte aligned x / y and d, ldx, ldy %% 4 == 0");
+    bulk = true;
+  }
+  if (bulk) {
+    const int d4 = (int)(d / 4);
+    const int n_ranges = (d4 + 767) / 768;
+    const int range4 = (d4 + n_ranges - 1) / n_ranges;
+    const int vpt = (range4 + BULK_CONSUMERS - 1) / BULK_CONSUMERS;
+    switch (vpt) {
+      case 1: return launch_bulk<1>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_ranges, range4, nnz, epi, st);
+      case 2: return launch_bulk<2>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_ranges, range4, nnz, epi, st);
+      default: return launch_bulk<3>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_ranges, range4, nnz, epi, st);
+    }
+  }
   if (vec_ok) {
     int d4 = (int)(d / 4);
     if (d4 <= 32) {
       int64_t warps = n_rows;
       spmm_vec_kernel<1, 8><<<(unsigned)((warps + warps_per_block - 1) / warps_per_block), SPMM_THREADS, 0, st>>>(
-          n_rows, rowptr, col, val, x, ldx, y, ldy, d4, 1, flags);
+          n_rows, rowptr, col, val, x, ldx, y, ldy, d4, 1, epi);
     } else if (d4 <= 64) {
       int64_t warps = n_rows;
       spmm_vec_kernel<2, 4><<<(unsigned)((warps + warps_per_block - 1) / warps_per_block), SPMM_THREADS, 0, st>>>(
-          n_rows, rowptr, col, val, x, ldx, y, ldy, d4, 1, flags);
+          n_rows, rowptr, col, val, x, ldx, y, ldy, d4, 1, epi);
     } else {
       int n_chunks = (d4 + 127) / 128;
       int64_t warps = n_rows * n_chunks;
       int64_t blocks = (warps + warps_per_block - 1) / warps_per_block;
       if (blocks > 0x7fffffffLL) return fail(LGNN_E_UNSUPPORTED, "spmm: grid too large");
       spmm_vec_kernel<4, 2><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(
-          n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_chunks, flags);
+          n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_chunks, epi);
     }
     LGNN_LAUNCH_CHECK("spmm_vec_kernel");
   } else {
@@ -178,7 +390,7 @@ extern "C" int lgnn_spmm_f32(int64_t n_rows, const int64_t* rowptr, const int32_
     int64_t blocks = (warps + warps_per_block - 1) / warps_per_block;
     if (blocks > 0x7fffffffLL) return fail(LGNN_E_UNSUPPORTED, "spmm: grid too large");
     spmm_scalar_kernel<<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(n_rows, rowptr, col, val, x, ldx, y,
-                                                                 ldy, d, n_chunks, flags);
+                                                                 ldy, d, n_chunks, epi);
     LGNN_LAUNCH_CHECK("spmm_scalar_kernel");
   }
   return LGNN_OK;

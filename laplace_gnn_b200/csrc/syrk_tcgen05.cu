@@ -7,7 +7,17 @@
 // CTA per SM owns a contiguous slice of rows and the FULL n x n accumulator in TMEM (two M=128
 // blocks x up to 256 fp32 columns = all 512 TMEM columns), so X is read from HBM exactly once.
 //
-// Pipeline per CTA (6 warps):
+// Tensor-core accumulation rounds toward zero, so a long all-positive chain (H^T H of relu outputs,
+// the diagonal of any Gram matrix) drifts low by ~4e-8 per accumulate.  The chain is therefore cut
+// into SEGMENTS of TC_SEG_STEPS steps (192 accumulates): after each segment four dedicated epilogue
+// warps drain TMEM and add it to the CTA's fp32 partial in global memory (L2-resident) with
+// round-to-nearest adds while the TMA / transform warps keep the operand ring full; the next
+// segment restarts the TMEM accumulator from zero.
+//
+// Only the upper block-triangle is computed: M block 0 (rows 0..127) against all np columns, M block
+// 1 (rows 128..255) against columns 128..np-1 only — 25 % fewer MMAs and TMEM columns at n = 256.
+//
+// Pipeline per CTA (10 warps):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes [BK rows x NP cols] of raw fp32 into a
 //               4-deep shared-memory ring (out-of-bounds rows / columns arrive as zeros, which makes
 //               every edge case — row tail, n not a multiple of 16 — free);
@@ -17,9 +27,9 @@
 //   warp 1      one elected lane issues, per 8-wide k-step and per M block, three tcgen05.mma
 //               (hi.hi, hi.lo, lo.hi; A and B descriptors point into the SAME operand buffers because
 //               both operands are X), then tcgen05.commit frees the operand stage;
-//   warps 2..5  epilogue: tcgen05.ld the accumulator (each warp its own 32-lane TMEM quarter) and
-//               store this CTA's partial n x NP block; a second kernel reduces the <=148 partials in
-//               fixed order (deterministic) and writes both triangles of C.
+//   warps 6..9  epilogue, once per segment: tcgen05.ld the accumulator (each warp its own 32-lane
+//               TMEM quarter), add into this CTA's partial n x NP block; a second kernel reduces the
+//               <=148 partials in fixed order (deterministic) and writes both triangles of C.
 //
 // Tensor roofline accounting: useful flops = k_rows * n * (n+1); the 3x issue factor
 // of the split is not counted as useful work.
@@ -35,8 +45,10 @@ constexpr int TC_BK = 16;          // rows of X per pipeline stage (two k=8 UMMA
 constexpr int TC_RAW_STAGES = 4;
 constexpr int TC_OP_STAGES = 3;
 constexpr int TC_SBO = 144;        // byte stride between 8-row core-matrix groups (128 + 16 pad)
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;
 constexpr int TC_TRANSFORM_THREADS = 128;
+constexpr int TC_EPILOGUE_WARPS = 4;
+constexpr int TC_SEG_STEPS_DEFAULT = 32;  // 32 steps x 2 k-steps x 3 products = 192 accumulates per chain
 
 struct TcGeom {
   int n, np, mb, npa;   // n, n padded to 16, #128-row M blocks, A-operand rows (mb*128)
@@ -56,7 +68,7 @@ static TcGeom tc_geom(int n) {
   g.lbo = (g.npa / 8) * TC_SBO;
   g.op_bytes = (TC_BK / 4) * g.lbo;
   g.raw_bytes = TC_BK * g.np * 4;
-  int cols = g.mb * g.np;
+  int cols = g.mb == 1 ? g.np : g.np + (g.np - 128);   // block 1 only holds columns 128..np-1
   g.tmem_cols = 32;
   while (g.tmem_cols < cols) g.tmem_cols <<= 1;
   g.smem_bytes = 1024 /*align slack*/ + (size_t)TC_RAW_STAGES * g.raw_bytes +
@@ -133,7 +145,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo, 
 
 struct TcParams {
   int n, np, mb, lbo, op_bytes, raw_bytes, tmem_cols;
-  int swap_lbo_sbo;  // debug switch (env LGNN_SYRK_SWAP_LBO_SBO) for descriptor bring-up
+  int seg_steps;     // steps per TMEM accumulation segment
   int64_t steps_total;
   int64_t steps_per_cta;
   float* part;  // [gridDim.x][n][np]
@@ -152,7 +164,8 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
   uint64_t* full_op = empty_raw + TC_RAW_STAGES;   // [OP]
   uint64_t* empty_op = full_op + TC_OP_STAGES;     // [OP]
   uint64_t* acc_full = empty_op + TC_OP_STAGES;    // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  uint64_t* acc_empty = acc_full + 1;              // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t step_beg = (int64_t)blockIdx.x * P.steps_per_cta;
@@ -170,6 +183,7 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
       mbar_init(smem_u32(&empty_op[i]), 1);
     }
     mbar_init(smem_u32(acc_full), 1);
+    mbar_init(smem_u32(acc_empty), TC_EPILOGUE_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -200,11 +214,18 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0 && my_steps > 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(P.np >> 3) << 17) |
-                             ((uint32_t)(128 >> 4) << 24);
-      const uint32_t lbo = P.swap_lbo_sbo ? TC_SBO : P.lbo;
-      const uint32_t sbo = P.swap_lbo_sbo ? P.lbo : TC_SBO;
+      // instruction descriptor: D fp32, A/B tf32, both K-major, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc0 = idesc_base | ((uint32_t)(P.np >> 3) << 17);
+      const uint32_t idesc1 = idesc_base | ((uint32_t)((P.np - 128) >> 3) << 17);
+      const uint32_t lbo = P.lbo, sbo = TC_SBO;
       for (int64_t s = 0; s < my_steps; ++s) {
+        const bool seg_first = (s % P.seg_steps) == 0;
+        if (seg_first && s > 0) {
+          // the epilogue warps have drained the previous segment out of TMEM
+          mbar_wait(smem_u32(acc_empty), (uint32_t)((s / P.seg_steps - 1) & 1));
+          tc_fence_after();
+        }
         int st = (int)(s % TC_OP_STAGES);
         uint32_t ph = (uint32_t)((s / TC_OP_STAGES) & 1);
         mbar_wait(smem_u32(&full_op[st]), ph);
@@ -214,24 +235,29 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
           const uint32_t koff = (uint32_t)ks * 2u * (uint32_t)P.lbo;  // two 16-byte k-chunks per k=8 step
-          const uint64_t b_hi = make_smem_desc(hi + koff, lbo, sbo);
-          const uint64_t b_lo = make_smem_desc(lo + koff, lbo, sbo);
-          for (int m = 0; m < P.mb; ++m) {
-            const uint32_t aoff = koff + (uint32_t)m * 16u * TC_SBO;  // 128 rows = 16 groups
-            const uint64_t a_hi = make_smem_desc(hi + aoff, lbo, sbo);
-            const uint64_t a_lo = make_smem_desc(lo + aoff, lbo, sbo);
-            const uint32_t d = tmem_base + (uint32_t)(m * P.np);
-            const uint32_t first = (s == 0 && ks == 0) ? 0u : 1u;
-            tc_mma_tf32(d, a_hi, b_hi, idesc, first);
-            tc_mma_tf32(d, a_hi, b_lo, idesc, 1u);
-            tc_mma_tf32(d, a_lo, b_hi, idesc, 1u);
+          const uint32_t acc = (seg_first && ks == 0) ? 0u : 1u;
+          {  // M block 0: rows 0..127 x columns 0..np-1
+            const uint64_t a_hi = make_smem_desc(hi + koff, lbo, sbo);
+            const uint64_t a_lo = make_smem_desc(lo + koff, lbo, sbo);
+            tc_mma_tf32(tmem_base, a_hi, a_hi, idesc0, acc);
+            tc_mma_tf32(tmem_base, a_hi, a_lo, idesc0, 1u);
+            tc_mma_tf32(tmem_base, a_lo, a_hi, idesc0, 1u);
+          }
+          if (P.mb == 2) {  // M block 1: rows 128..255 x columns 128..np-1 (128 rows = 16 groups)
+            const uint32_t off = koff + 16u * TC_SBO;
+            const uint64_t a_hi = make_smem_desc(hi + off, lbo, sbo);
+            const uint64_t a_lo = make_smem_desc(lo + off, lbo, sbo);
+            const uint32_t d = tmem_base + (uint32_t)P.np;
+            tc_mma_tf32(d, a_hi, a_hi, idesc1, acc);
+            tc_mma_tf32(d, a_hi, a_lo, idesc1, 1u);
+            tc_mma_tf32(d, a_lo, a_hi, idesc1, 1u);
           }
         }
         tc_commit(smem_u32(&empty_op[st]));  // implies fence::before_thread_sync
+        if ((s % P.seg_steps) == P.seg_steps - 1 || s == my_steps - 1) tc_commit(smem_u32(acc_full));
       }
-      tc_commit(smem_u32(acc_full));
     }
-  } else {
+  } else if (warp < 6) {
     // ===================================================================== transform warps
     const int t = threadIdx.x - 64;  // 0..127
     const int np4 = P.np >> 2;
@@ -280,38 +306,59 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
         mbar_arrive(smem_u32(&empty_raw[rs]));
       }
     }
-    // ===================================================================== epilogue
+  } else {
+    // ===================================================================== epilogue warps
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    float* out = P.part + (size_t)blockIdx.x * P.n * P.np;
     if (my_steps > 0) {
-      mbar_wait(smem_u32(acc_full), 0);
-      tc_fence_after();
-      const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
-      float* out = P.part + (size_t)blockIdx.x * P.n * P.np;
-      for (int m = 0; m < P.mb; ++m) {
-        const int row = m * 128 + quarter * 32 + lane;
-        for (int c0 = 0; c0 < P.np; c0 += 16) {
-          uint32_t v[16];
-          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(m * P.np + c0);
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-                "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-                "=r"(v[14]), "=r"(v[15])
-              : "r"(taddr));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (row < P.n) {
+      const int64_t n_seg = (my_steps + P.seg_steps - 1) / P.seg_steps;
+      for (int64_t seg = 0; seg < n_seg; ++seg) {
+        mbar_wait(smem_u32(acc_full), (uint32_t)(seg & 1));
+        tc_fence_after();
+        for (int m = 0; m < P.mb; ++m) {
+          const int row = m * 128 + quarter * 32 + lane;
+          const int col_beg = m * 128;                       // block 1 starts at column 128
+          const uint32_t tcol0 = m == 0 ? 0u : (uint32_t)P.np;
+          for (int c0 = col_beg; c0 < P.np; c0 += 16) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + tcol0 + (uint32_t)(c0 - col_beg);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                  "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                  "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr));
+            float4 old[4];
             float4* dst = reinterpret_cast<float4*>(out + (size_t)row * P.np + c0);
+            const bool live = row < P.n;
+            if (live && seg > 0) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-              dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                   __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+              for (int q = 0; q < 4; ++q) old[q] = dst[q];
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) old[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            // pin the uses of v[] behind the wait (volatile asms keep their order)
+            asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),
+                              "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]),
+                              "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
+            if (live) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                dst[q] = make_float4(old[q].x + __uint_as_float(v[4 * q]), old[q].y + __uint_as_float(v[4 * q + 1]),
+                                     old[q].z + __uint_as_float(v[4 * q + 2]), old[q].w + __uint_as_float(v[4 * q + 3]));
+            }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(acc_empty));
       }
     } else {
       // idle CTA (more CTAs than steps): contribute zeros
-      float* out = P.part + (size_t)blockIdx.x * P.n * P.np;
-      for (int i = t; i < P.n * P.np; i += TC_TRANSFORM_THREADS) out[i] = 0.f;
+      for (int i = threadIdx.x - 192; i < P.n * P.np; i += TC_EPILOGUE_WARPS * 32) out[i] = 0.f;
     }
   }
   tc_fence_before();
@@ -391,8 +438,11 @@ int syrk_tcgen05_launch(const float* x, int64_t ldx, int64_t k_rows, int n, floa
   TcParams P;
   P.n = n; P.np = g.np; P.mb = g.mb; P.lbo = g.lbo; P.op_bytes = g.op_bytes; P.raw_bytes = g.raw_bytes;
   P.tmem_cols = g.tmem_cols;
-  const char* sw = getenv("LGNN_SYRK_SWAP_LBO_SBO");
-  P.swap_lbo_sbo = (sw && sw[0] == '1') ? 1 : 0;
+  P.seg_steps = TC_SEG_STEPS_DEFAULT;
+  if (const char* sg = getenv("LGNN_SYRK_SEG_STEPS")) {  // accuracy / speed experiments
+    int v = atoi(sg);
+    if (v >= 1 && v <= (1 << 20)) P.seg_steps = v;
+  }
   P.steps_total = (k_rows + TC_BK - 1) / TC_BK;
   int grid = tc_grid(P.steps_total);
   P.steps_per_cta = (P.steps_total + grid - 1) / grid;

@@ -74,6 +74,39 @@ def _kron_class():
     return Kron
 
 
+class _Whole:
+    """Backward layout: every graph row is local (single device, or the column-parallel backward)."""
+
+    def __init__(self, graph):
+        self.csr_t = graph.ahat_t
+        self.n_local = self.total_rows = graph.n
+        self.slot0 = 0
+
+    def gather(self, slab):
+        pass
+
+    def agree_min(self, value: int) -> int:
+        return value
+
+
+class _Rows:
+    """Backward layout: this rank's row block; SpMM inputs are all-gathered padded slabs."""
+
+    def __init__(self, part):
+        self.part = part
+        self.csr_t = part.ahat_t
+        self.n_local, self.total_rows, self.slot0 = part.n_local, part.total_rows, part.slot0
+
+    def gather(self, slab):
+        self.part.all_gather_slab(slab)
+
+    def agree_min(self, value: int) -> int:
+        """Collectives need the same column grouping on every rank."""
+        t = torch.tensor([value], dtype=torch.int64, device=self.part.ahat.rowptr.device)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=self.part.pg)
+        return int(t.item())
+
+
 class _B200KFAC:
     """kron()/diag() on the B200 kernels; mixed into a CurvatureInterface subclass."""
 
@@ -81,6 +114,8 @@ class _B200KFAC:
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows"):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
+        if backward_parallel not in ("rows", "columns"):
+            raise ValueError(f"backward_parallel must be 'rows' or 'columns', got {backward_parallel!r}")
         if differentiable:
             raise NotImplementedError(
                 "differentiable=True (gradients of the factors w.r.t. the adjacency) is outside the "
@@ -110,23 +145,40 @@ class _B200KFAC:
             bs.append(None if conv.lin.bias is None else conv.lin.bias.detach().contiguous())
         return Ws, bs
 
-    def _forward(self, Ws, bs):
-        """Eval-mode forward.  Returns Hs = [X, H_1, ..., H_{L-1}] and the logits P_L [n, C]."""
+    def _forward(self, Ws, bs, part=None):
+        """Eval-mode forward.  Returns Hs = [X, H_1, ..., H_{L-1}] and the logits P_L — all graph
+        rows on one device, this rank's row block when ``part`` is given (each layer then
+        all-gathers Z_l, the slab its SpMM reads, over the process group)."""
         g = self.model.graph
         h = self.model.X
         if h.dtype != torch.float32 or not h.is_contiguous():
             h = h.float().contiguous()
+        if part is not None:
+            h = h[part.lo:part.hi]
         Hs = [h]
         L = len(Ws)
         for l in range(L):
-            with ops.timed("gemm_fwd", Ws[l].shape[0], 2.0 * h.shape[0] * Ws[l].numel()):
-                z = torch.mm(h, Ws[l].t()) if bs[l] is None else torch.addmm(bs[l], h, Ws[l].t())
-            h = ops.spmm(g.ahat, z, relu=(l < L - 1))
+            d_out = Ws[l].shape[0]
+            if part is None:
+                with ops.timed("gemm_fwd", d_out, 2.0 * h.shape[0] * Ws[l].numel()):
+                    z = torch.mm(h, Ws[l].t()) if bs[l] is None else torch.addmm(bs[l], h, Ws[l].t())
+                h = ops.spmm(g.ahat, z, relu=(l < L - 1))
+            else:
+                slab = torch.empty(part.total_rows, d_out, dtype=torch.float32, device=h.device)
+                z = slab[part.slot0:part.slot0 + part.n_local]
+                with ops.timed("gemm_fwd", d_out, 2.0 * h.shape[0] * Ws[l].numel()):
+                    if bs[l] is None:
+                        torch.mm(h, Ws[l].t(), out=z)
+                    else:
+                        torch.addmm(bs[l], h, Ws[l].t(), out=z)
+                with ops.timed("allgather", d_out, 4.0 * part.total_rows * d_out):
+                    part.all_gather_slab(slab)
+                h = ops.spmm(part.ahat, slab, relu=(l < L - 1))
             if l < L - 1:
                 Hs.append(h)
         return Hs, h
 
-    def _group_size(self, n: int, dmax: int, C: int, device) -> int:
+    def _group_size(self, rows_in: int, rows_out: int, dmax: int, C: int, device) -> int:
         budget = self.rhs_tile_bytes
         if budget is None:
             if device.type == "cuda":
@@ -134,19 +186,69 @@ class _B200KFAC:
                 budget = min(int(0.6 * free), int(0.4 * total))
             else:
                 budget = 1 << 30
-        g = int(budget // (2 * n * dmax * 4))
+        g = int(budget // (max(rows_in + rows_out, 1) * dmax * 4))
         return max(1, min(C, g))
+
+    def _partition(self):
+        """RowPartition of the model's graph for this backend's process group (built once)."""
+        if self.process_group is None:
+            return None
+        part = getattr(self, "_part", None)
+        if part is None or part.pg is not self.process_group:
+            from .dist import RowPartition
+            part = RowPartition.build(self.model.graph, self.process_group)
+            self._part = part
+        return part
+
+    def _backward_columns(self, lay, logits, idx, Hs, Ws, cols, G):
+        """Multi-RHS KFAC backward for the Hessian-sqrt columns ``cols = (first, count)`` on the
+        rows ``lay`` describes: G[l] += sum_c gZ_{l,c}^T gZ_{l,c}  (kfac.py:653-661, 777-817)."""
+        L = len(Ws)
+        C = logits.shape[1]
+        dims = [w.shape[0] for w in Ws]                 # d_1 .. d_L (d_L = C)
+        c_pad = (C + 3) // 4 * 4
+        dmax = max([c_pad] + dims[:-1])
+        c_first, c_count = cols
+        if c_count <= 0:
+            return 0, 0
+        dev = logits.device
+        n_loc, n_in, slot0 = lay.n_local, lay.total_rows, lay.slot0
+        grp = lay.agree_min(min(self._group_size(n_in, n_loc, dmax, C, dev), c_count))
+        buf_a = torch.empty(n_in * grp * dmax, dtype=torch.float32, device=dev)    # SpMM inputs (slabs)
+        buf_b = torch.empty(max(n_loc, 1) * grp * dmax, dtype=torch.float32, device=dev)  # SpMM outputs
+        for c0 in range(c_first, c_first + c_count, grp):
+            gc = min(grp, c_first + c_count - c0)
+            slab = buf_a[: n_in * gc * c_pad].view(n_in, gc * c_pad)
+            delta = slab[slot0:slot0 + n_loc]
+            with ops.timed("hess_rhs", gc):
+                delta.zero_()
+                ops.hess_rhs(logits, idx, c0, gc, delta, c_pad, self.hess_sqrt)
+            width, ld = C, c_pad
+            for l in range(L - 1, -1, -1):
+                with ops.timed("allgather", gc * ld, 4.0 * n_in * gc * ld):
+                    lay.gather(slab)
+                gz = buf_b[: n_loc * gc * ld].view(n_loc, gc * ld)
+                ops.spmm(lay.csr_t, slab, out=gz)
+                gz_rows = gz.view(n_loc * gc, ld)
+                ops.syrk(gz_rows, n=width, alpha=1.0, beta=1.0, out=G[l], impl=self._impl(width))
+                if l > 0:
+                    d_prev = dims[l - 1]
+                    slab = buf_a[: n_in * gc * d_prev].view(n_in, gc * d_prev)
+                    nxt = slab[slot0:slot0 + n_loc].view(n_loc * gc, d_prev)
+                    with ops.timed("gemm_bwd", d_prev, 2.0 * n_loc * gc * width * d_prev):
+                        torch.mm(gz_rows[:, :width], Ws[l], out=nxt)
+                    with ops.timed("relu_mask", d_prev, 2.0 * n_loc * gc * d_prev * 4):
+                        ops.relu_mask_mul(nxt, Hs[l], gc)
+                    width, ld = d_prev, d_prev
+        return grp, (c_count + grp - 1) // grp
 
     # ------------------------------------------------------------------ kron
     def kron(self, x: torch.Tensor, y: torch.Tensor, N: int, **kwargs):
         """(loss, Kron) for the batch of train-node indices ``x`` with labels ``y``; ``N`` is the
-        size of the whole training set (curvature.py:236-265)."""
-        if self.process_group is not None:
-            from .dist import kron_partitioned
-            return kron_partitioned(self, x, y, N)
+        size of the whole training set (curvature.py:236-265).  With a ``process_group`` every rank
+        passes the same (x, y) and receives the same (all-reduced) result."""
         model = self.model
         g = model.graph
-        n = g.n
         Ws, bs = self._layers()
         L = len(Ws)
         M = int(y.shape[0])
@@ -154,47 +256,54 @@ class _B200KFAC:
             raise ValueError("x (node indices) and y (labels) must have the same length")
         idx = x.to(torch.int64).contiguous()
         yy = y.to(torch.int64).contiguous()
-        Hs, logits = self._forward(Ws, bs)
+        part = self._partition()
+        Hs, logits = self._forward(Ws, bs, part)
         C = logits.shape[1]
-        loss, _hits = ops.softmax_ce_sum(logits, idx, yy)
+        dev = logits.device
+        if part is not None:                                   # this rank's train nodes, local row ids
+            mine = (idx >= part.lo) & (idx < part.hi)
+            idx_loc, y_loc = (idx[mine] - part.lo).contiguous(), yy[mine].contiguous()
+        else:
+            idx_loc, y_loc = idx, yy
+        loss, _hits = ops.softmax_ce_sum(logits, idx_loc, y_loc)
 
-        # input-side factors A_l over ALL n nodes (kfac.py:870), then the M/N rescale (curvlinops.py:46-53)
+        # input-side factors A_l over ALL graph nodes (kfac.py:870), then the M/N rescale
+        # (curvlinops.py:46-53); with a partition: this rank's rows, summed by the all-reduce below
         A = []
         for l in range(L):
             a = ops.syrk(Hs[l], alpha=1.0 / M, impl=self._impl(Hs[l].shape[1]))
             a *= M / N
             A.append(a)
 
-        # output-side factors G_l, multi-RHS backward in groups of Hessian-sqrt columns
-        dims = [w.shape[0] for w in Ws]                 # d_1 .. d_L (d_L = C)
-        c_pad = (C + 3) // 4 * 4
-        dmax = max([c_pad] + dims[:-1])
-        grp = self._group_size(n, dmax, C, logits.device)
-        buf_a = torch.empty(n * grp * dmax, dtype=torch.float32, device=logits.device)
-        buf_b = torch.empty(n * grp * dmax, dtype=torch.float32, device=logits.device)
-        G = [torch.zeros(d, d, dtype=torch.float32, device=logits.device) for d in dims]
-        for c0 in range(0, C, grp):
-            gc = min(grp, C - c0)
-            delta = buf_a[: n * gc * c_pad].view(n, gc * c_pad)
-            with ops.timed("hess_rhs", gc):
-                delta.zero_()
-                ops.hess_rhs(logits, idx, c0, gc, delta, c_pad, self.hess_sqrt)
-            width, ld = C, c_pad
-            for l in range(L - 1, -1, -1):
-                gz = buf_b[: n * gc * ld].view(n, gc * ld)
-                ops.spmm(g.ahat_t, delta, out=gz)
-                gz_rows = gz.view(n * gc, ld)
-                ops.syrk(gz_rows, n=width, alpha=1.0, beta=1.0, out=G[l], impl=self._impl(width))
-                if l > 0:
-                    d_prev = dims[l - 1]
-                    nxt = buf_a[: n * gc * d_prev].view(n * gc, d_prev)
-                    with ops.timed("gemm_bwd", d_prev, 2.0 * n * gc * width * d_prev):
-                        torch.mm(gz_rows[:, :width], Ws[l], out=nxt)
-                    with ops.timed("relu_mask", d_prev, 2.0 * n * gc * d_prev * 4):
-                        ops.relu_mask_mul(nxt, Hs[l], gc)
-                    delta = nxt.view(n, gc * d_prev)
-                    width, ld = d_prev, d_prev
-        self.last_stats = {"group": grp, "n_groups": (C + grp - 1) // grp, "M": M, "C": C}
+        # output-side factors G_l: multi-RHS backward in groups of Hessian-sqrt columns
+        G = [torch.zeros(w.shape[0], w.shape[0], dtype=torch.float32, device=dev) for w in Ws]
+        if part is None:
+            grp, n_groups = self._backward_columns(_Whole(g), logits, idx, Hs, Ws, (0, C), G)
+        elif self.backward_parallel == "rows":
+            grp, n_groups = self._backward_columns(_Rows(part), logits, idx_loc, Hs, Ws, (0, C), G)
+        else:                                                  # "columns": full graph, own columns
+            from .dist import column_share
+            full_H, full_logits = [self.model.X.float().contiguous()], None
+            for t_loc in Hs[1:] + [logits]:
+                w = t_loc.shape[1]
+                slab = torch.empty(part.total_rows, w, dtype=torch.float32, device=dev)
+                slab[part.slot0:part.slot0 + part.n_local] = t_loc
+                with ops.timed("allgather", w, 4.0 * part.total_rows * w):
+                    part.all_gather_slab(slab)
+                full = part.compact(slab, w)
+                if t_loc is logits:
+                    full_logits = full
+                else:
+                    full_H.append(full)
+            grp, n_groups = self._backward_columns(_Whole(g), full_logits, idx, full_H, Ws,
+                                                   column_share(C, part.rank, part.world), G)
+        if part is not None:
+            with ops.timed("allreduce", 0, 4.0 * sum(t.numel() for t in G + A)):
+                part.all_reduce_sum(G + A)
+                part.all_reduce_sum([loss])
+        self.last_stats = {"group": grp, "n_groups": n_groups, "M": M, "C": C,
+                           "world": 1 if part is None else part.world,
+                           "halo_fraction": None if part is None else part.halo_fraction}
 
         Kron = _kron_class()
         kfacs = []

@@ -1,0 +1,112 @@
+"""Row-partitioned multi-GPU execution of the GCN KFAC-GGN pass (one process per GPU,
+``torch.distributed`` / NCCL over NVLink).  The reference is single-device; this is
+the B200 design of BASELINE.json's north star:
+
+* the graph is split into ``world`` contiguous row blocks balanced by nnz (``lgnn_row_partition``,
+  bit-exact against ``oracle.row_partition``); rank r owns rows [bounds[r], bounds[r+1]) of every
+  activation / gradient slab and the matching CSR row slices of Â and Â^T;
+* before each local SpMM the ranks all-gather the slab the SpMM reads (the halo of a uniformly
+  random graph with average degree >= 15 is > 85 % of all rows, so the whole slab is exchanged;
+  ``halo_fraction`` reports the exact figure).  Slabs live in a padded layout
+  [world, pad, width] so the all-gather is in place and the local CSR slices carry column indices
+  remapped to that layout (``lgnn_csr_slice_remap``);
+* the small d x d Kronecker factors are summed with ONE all-reduce at the end of the pass, the loss
+  with a second (double precision); the factor eigendecompositions / marglik then run replicated.
+
+``backward_parallel`` selects how the C Hessian-sqrt columns of the backward are spread:
+
+  "rows"     every rank processes all C columns on its row block; each layer step all-gathers the
+             N x (g*d) right-hand-side slab (communication ~ compute at 8 GPUs; hidden behind
+             the SpMM of the other in-flight column group when ``overlap`` is on);
+  "columns"  the forward stays row-partitioned (halo all-gather of Z_l, all-gather of H_l), then
+             rank r back-propagates its own C/world columns on the full graph: no data-path
+             collective in the backward at all.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .ops import CSR
+
+
+@dataclass
+class RowPartition:
+    """State of one rank for a given (graph, process group)."""
+    pg: object
+    rank: int
+    world: int
+    bounds: list            # world+1 python ints
+    pad: int                # rows per slot of the padded all-gather layout
+    ahat: CSR               # rows [lo, hi) of Â,   columns in padded layout
+    ahat_t: CSR             # rows [lo, hi) of Â^T, columns in padded layout
+    halo_fraction: float    # fraction of the other ranks' rows this rank's SpMM reads
+
+    @property
+    def lo(self) -> int:
+        return self.bounds[self.rank]
+
+    @property
+    def hi(self) -> int:
+        return self.bounds[self.rank + 1]
+
+    @property
+    def n_local(self) -> int:
+        return self.hi - self.lo
+
+    @property
+    def total_rows(self) -> int:
+        return self.world * self.pad
+
+    @property
+    def slot0(self) -> int:
+        return self.rank * self.pad
+
+    @classmethod
+    def build(cls, graph, pg) -> "RowPartition":
+        rank, world = dist.get_rank(pg), dist.get_world_size(pg)
+        bounds_t = graph.partition_bounds(world)
+        bounds = [int(v) for v in bounds_t.tolist()]
+        pad = max(max(bounds[r + 1] - bounds[r] for r in range(world)), 1)
+        lo, hi = bounds[rank], bounds[rank + 1]
+        a = ops.csr_slice_remap(graph.ahat, lo, hi, bounds_t, pad)
+        at = a if graph.ahat_t is graph.ahat else ops.csr_slice_remap(graph.ahat_t, lo, hi, bounds_t, pad)
+        n_other = graph.n - (hi - lo)
+        halo = ops.halo_columns(graph.ahat_t, lo, hi)
+        frac = float(halo.numel()) / n_other if n_other > 0 else 0.0
+        return cls(pg, rank, world, bounds, pad, a, at, frac)
+
+    # ---- collectives -------------------------------------------------------------------
+    def all_gather_slab(self, slab: torch.Tensor, async_op: bool = False):
+        """In-place all-gather of a padded slab [world*pad, width]: every rank has filled its own
+        slot rows [rank*pad, rank*pad + n_local)."""
+        flat = slab.view(self.world, -1)
+        mine = flat[self.rank]
+        if not slab.is_cuda:           # gloo (CPU tests): no in-place guarantee
+            mine = mine.clone()
+        return dist.all_gather_into_tensor(flat.view(-1), mine.reshape(-1), group=self.pg, async_op=async_op)
+
+    def compact(self, slab: torch.Tensor, width: int) -> torch.Tensor:
+        """Padded [world*pad, width] -> natural node order [N, width]."""
+        v = slab.view(self.world, self.pad, width)
+        return torch.cat([v[r, : self.bounds[r + 1] - self.bounds[r]] for r in range(self.world)], dim=0)
+
+    def all_reduce_sum(self, tensors) -> None:
+        """One all-reduce over the concatenation of same-dtype tensors (written back in place)."""
+        flat = torch.cat([t.reshape(-1) for t in tensors])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+        off = 0
+        for t in tensors:
+            n = t.numel()
+            t.copy_(flat[off:off + n].view_as(t))
+            off += n
+
+
+def column_share(C: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous block of Hessian-sqrt columns owned by ``rank``: sizes differ by at most one."""
+    base, rem = divmod(C, world)
+    start = rank * base + min(rank, rem)
+    return start, base + (1 if rank < rem else 0)

@@ -168,8 +168,11 @@ def csr_slice_remap(a: CSR, lo: int, hi: int, bounds: torch.Tensor, pad: int) ->
 
 
 # ------------------------------------------------------------------------------ SpMM
+_SPMM_IMPL = {"auto": 0, "ldg": _lib.SPMM_FORCE_LDG, "bulk": _lib.SPMM_FORCE_BULK}
+
+
 def spmm(a: CSR, x: torch.Tensor, relu: bool = False, out: torch.Tensor | None = None,
-         d: int | None = None) -> torch.Tensor:
+         d: int | None = None, impl: str = "auto") -> torch.Tensor:
     """Y = A @ X[:, :d]  (optionally relu'd).  x: [>= n_cols, ld] row-major fp32."""
     lib = _lib.load()
     _f32c(x, "x")
@@ -182,8 +185,9 @@ def spmm(a: CSR, x: torch.Tensor, relu: bool = False, out: torch.Tensor | None =
     if out.shape[0] < a.n_rows or out.shape[1] < d:
         raise ValueError("spmm: out too small")
     with _Timed("spmm", d, spmm_algorithmic_bytes(a.n_rows, a.nnz, d)):
-        check(lib.lgnn_spmm_f32(a.n_rows, ptr(a.rowptr), ptr(a.col), ptr(a.val), ptr(x), x.stride(0),
-                                ptr(out), out.stride(0), d, _lib.SPMM_RELU if relu else _lib.SPMM_NONE,
+        check(lib.lgnn_spmm_f32(a.n_rows, a.nnz, ptr(a.rowptr), ptr(a.col), ptr(a.val), ptr(x), x.stride(0),
+                                ptr(out), out.stride(0), d,
+                                (_lib.SPMM_RELU if relu else _lib.SPMM_NONE) | _SPMM_IMPL[impl],
                                 stream()), "lgnn_spmm_f32")
     _lib.count_launches(1)
     return out

@@ -57,7 +57,7 @@ def csr_slice_remap(a, lo, hi, bounds, pad):
     return CSR(hi - lo, (len(b) - 1) * pad, torch.from_numpy(rp[lo:hi + 1] - s), torch.from_numpy(new_col), val)
 
 
-def spmm(a, x, relu=False, out=None, d=None):
+def spmm(a, x, relu=False, out=None, d=None, impl="auto"):
     d = x.shape[1] if d is None else d
     m = torch.sparse_csr_tensor(a.rowptr, a.col.to(torch.int64), a.val, size=(a.n_rows, x.shape[0]))
     y = m @ x[:, :d].contiguous()

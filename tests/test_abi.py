@@ -36,7 +36,7 @@ def test_abi_version_and_host_only_queries():
 
 def test_bad_arguments_are_rejected_before_any_launch():
     lib = _lib.load()
-    rc = lib.lgnn_spmm_f32(-1, None, None, None, None, 4, None, 4, 4, 0, None)
+    rc = lib.lgnn_spmm_f32(-1, 0, None, None, None, None, 4, None, 4, 4, 0, None)
     assert rc == -1 and b"spmm" in lib.lgnn_last_error()
     rc = lib.lgnn_hess_rhs_f32(None, 4, 4, None, 1, 0, 4, 4, 7, None, None)
     assert rc == -1

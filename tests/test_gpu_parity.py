@@ -119,6 +119,55 @@ def test_spmm_matches_oracle(d, relu):
         assert max_rel_err(y.cpu().numpy(), ref.numpy()) <= 1e-5
 
 
+@pytest.mark.parametrize("d", [512, 516, 960, 1024, 3072, 3076, 4096, 7000])
+@pytest.mark.parametrize("relu", [False, True])
+def test_spmm_bulk_kernel_matches_oracle_and_ldg_kernel(d, relu):
+    """Wide (multi-RHS) SpMM: the bulk-async ring kernel vs the oracle and vs the warp-per-row kernel
+    (summation order over a row's neighbours is the same in both, so they agree to the bit)."""
+    ops = _ops()
+    n = 2000
+    ei = O.synthetic_edges(n, 9000, seed=d, directed=True, rmat=(d % 8 == 0))
+    G, R = _dev_graph(ei, n), O.build_graph(ei, n)
+    rng = np.random.Generator(np.random.PCG64(d))
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    xd = torch.from_numpy(x).to(DEV)
+    for transpose, csr in ((False, G.ahat), (True, G.ahat_t)):
+        ref = O.spmm(R, x, transpose=transpose, dtype=torch.float64)
+        if relu:
+            ref = torch.relu(ref)
+        y = ops.spmm(csr, xd, relu=relu, impl="bulk")
+        assert max_rel_err(y.cpu().numpy(), ref.numpy()) <= 1e-5
+        assert torch.equal(y, ops.spmm(csr, xd, relu=relu, impl="ldg"))
+        assert torch.equal(y, ops.spmm(csr, xd, relu=relu))          # auto picks bulk for d >= 512
+
+
+def test_spmm_bulk_kernel_empty_rows_hub_rows_and_leading_dimensions():
+    """Rectangular CSR with empty rows (leading, interior, trailing), one hub row longer than a CTA's
+    nnz budget, and ldx / ldy larger than d."""
+    ops = _ops()
+    from laplace_gnn_b200.ops import CSR
+    rng = np.random.Generator(np.random.PCG64(7))
+    n_rows, n_cols, d, ld = 300, 500, 640, 700
+    counts = rng.integers(0, 12, n_rows)
+    counts[[0, 1, 57, 58, 298, 299]] = 0
+    counts[100] = 9000                                    # > BULK_NNZ_PER_CTA: spans several CTA budgets
+    rowptr = np.zeros(n_rows + 1, np.int64)
+    np.cumsum(counts, out=rowptr[1:])
+    col = rng.integers(0, n_cols, rowptr[-1]).astype(np.int32)
+    val = rng.standard_normal(rowptr[-1]).astype(np.float32)
+    x = rng.standard_normal((n_cols, ld)).astype(np.float32)
+    a = CSR(n_rows, n_cols, torch.from_numpy(rowptr).to(DEV), torch.from_numpy(col).to(DEV),
+            torch.from_numpy(val).to(DEV))
+    import scipy.sparse as sp
+    ref = sp.csr_matrix((val.astype(np.float64), col, rowptr), shape=(n_rows, n_cols)) @ x[:, :d].astype(np.float64)
+    out = torch.full((n_rows, ld), 7.0, device=DEV)
+    ops.spmm(a, torch.from_numpy(x).to(DEV), out=out, d=d, impl="bulk")
+    assert max_rel_err(out[:, :d].cpu().numpy(), ref) <= 1e-5
+    assert float((out[:, d:] - 7.0).abs().max()) == 0.0   # columns beyond d untouched
+    assert float(out[[0, 1, 57, 58, 298, 299], :d].abs().max()) == 0.0
+    assert torch.equal(out[:, :d], ops.spmm(a, torch.from_numpy(x).to(DEV), d=d, impl="ldg"))
+
+
 def test_spmm_strided_and_unaligned_operands():
     ops = _ops()
     n, d = 1000, 24
