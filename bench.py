@@ -45,6 +45,8 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink nodes and edges by this factor (debug)")
     ap.add_argument("--hess-sqrt", default="reference", choices=["reference", "ggn"])
     ap.add_argument("--syrk", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--backward-parallel", default="rows", choices=["rows", "columns"],
+                    help="multi-GPU layout of the KFAC backward (laplace_gnn_b200/dist.py)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-div", type=int, default=64)
@@ -222,6 +224,7 @@ def main():
     bk = {"hess_sqrt": args.hess_sqrt, "syrk_impl": args.syrk}
     if pg is not None:
         bk["process_group"] = pg
+        bk["backward_parallel"] = args.backward_parallel
     loader = L.TensorBatchLoader(idx, y)      # one full batch, no per-sample collation
 
     def step(mdl, ldr):
@@ -344,7 +347,8 @@ def main():
                    "nodes": n, "nnz": nnz, "features": f, "classes": c, "train_nodes": int(idx.numel()),
                    "hess_sqrt": args.hess_sqrt, "syrk": args.syrk, "scale": args.scale,
                    "l2": "inputs (>= 10 GB per SpMM) far exceed the 126 MB L2; no explicit flush",
-                   "parallelism": "single GPU" if world == 1 else f"row-partitioned x{world}"},
+                   "parallelism": "single GPU" if world == 1 else
+                   f"row-partitioned x{world} (halo all-gather), backward over {args.backward_parallel}"},
         "marglik": marglik, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roof,
         "cpu_baseline": cpu,
     }

@@ -348,7 +348,9 @@ extern "C" int lgnn_spmm_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr,
                       ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
   const int warps_per_block = SPMM_THREADS / 32;
   const int epi = flags & LGNN_SPMM_RELU;
-  bool bulk = vec_ok && d >= 512;
+  // measured on B200 (profiles/): with >= 10 KB ring stages the bulk kernel sits at the HBM roofline;
+  // with smaller stages its per-stage hand-off dominates and the warp-per-row kernel is faster
+  bool bulk = vec_ok && d >= 2560 && ((d / 4 + ((d / 4 + 767) / 768) - 1) / ((d / 4 + 767) / 768)) > 640;
   if (flags & LGNN_SPMM_FORCE_LDG) bulk = false;
   if (flags & LGNN_SPMM_FORCE_BULK) {
     if (!vec_ok) return fail(LGNN_E_ALIGN, "spmm: the bulk path needs 16-byte aligned x / y and d, ldx, ldy %% 4 == 0");

@@ -17,7 +17,7 @@
 // Only the upper block-triangle is computed: M block 0 (rows 0..127) against all np columns, M block
 // 1 (rows 128..255) against columns 128..np-1 only — 25 % fewer MMAs and TMEM columns at n = 256.
 //
-// Pipeline per CTA (10 warps):
+// Pipeline per CTA (14 warps):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes [BK rows x NP cols] of raw fp32 into a
 //               4-deep shared-memory ring (out-of-bounds rows / columns arrive as zeros, which makes
 //               every edge case — row tail, n not a multiple of 16 — free);
@@ -27,9 +27,12 @@
 //   warp 1      one elected lane issues, per 8-wide k-step and per M block, three tcgen05.mma
 //               (hi.hi, hi.lo, lo.hi; A and B descriptors point into the SAME operand buffers because
 //               both operands are X), then tcgen05.commit frees the operand stage;
-//   warps 6..9  epilogue, once per segment: tcgen05.ld the accumulator (each warp its own 32-lane
-//               TMEM quarter), add into this CTA's partial n x NP block; a second kernel reduces the
-//               <=148 partials in fixed order (deterministic) and writes both triangles of C.
+//   warps 6..13 epilogue, once per segment: tcgen05.ld the accumulator (two warps per 32-lane TMEM
+//               quarter, alternating 16-column chunks) and add it into this CTA's zero-initialised
+//               partial n x NP block with fire-and-forget red.global.add.v4.f32 (RN adds in L2; every
+//               address is only ever touched by one thread, so the order of adds — and the result —
+//               is the same on every run); a second kernel reduces the <=148 partials in fixed
+//               order and writes both triangles of C.
 //
 // Tensor roofline accounting: useful flops = k_rows * n * (n+1); the 3x issue factor
 // of the split is not counted as useful work.
@@ -45,9 +48,9 @@ constexpr int TC_BK = 16;          // rows of X per pipeline stage (two k=8 UMMA
 constexpr int TC_RAW_STAGES = 4;
 constexpr int TC_OP_STAGES = 3;
 constexpr int TC_SBO = 144;        // byte stride between 8-row core-matrix groups (128 + 16 pad)
-constexpr int TC_THREADS = 320;
+constexpr int TC_THREADS = 448;
 constexpr int TC_TRANSFORM_THREADS = 128;
-constexpr int TC_EPILOGUE_WARPS = 4;
+constexpr int TC_EPILOGUE_WARPS = 8;
 constexpr int TC_SEG_STEPS_DEFAULT = 32;  // 32 steps x 2 k-steps x 3 products = 192 accumulates per chain
 
 struct TcGeom {
@@ -308,57 +311,46 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
     }
   } else {
     // ===================================================================== epilogue warps
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    const int half = (warp - 6) >> 2;      // the two warps of a quarter take alternate 16-column chunks
     float* out = P.part + (size_t)blockIdx.x * P.n * P.np;
-    if (my_steps > 0) {
-      const int64_t n_seg = (my_steps + P.seg_steps - 1) / P.seg_steps;
-      for (int64_t seg = 0; seg < n_seg; ++seg) {
-        mbar_wait(smem_u32(acc_full), (uint32_t)(seg & 1));
-        tc_fence_after();
-        for (int m = 0; m < P.mb; ++m) {
-          const int row = m * 128 + quarter * 32 + lane;
-          const int col_beg = m * 128;                       // block 1 starts at column 128
-          const uint32_t tcol0 = m == 0 ? 0u : (uint32_t)P.np;
-          for (int c0 = col_beg; c0 < P.np; c0 += 16) {
-            uint32_t v[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + tcol0 + (uint32_t)(c0 - col_beg);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
-                  "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
-                  "=r"(v[14]), "=r"(v[15])
-                : "r"(taddr));
-            float4 old[4];
-            float4* dst = reinterpret_cast<float4*>(out + (size_t)row * P.np + c0);
-            const bool live = row < P.n;
-            if (live && seg > 0) {
+    const int64_t n_seg = (my_steps + P.seg_steps - 1) / P.seg_steps;
+    for (int64_t seg = 0; seg < n_seg; ++seg) {
+      mbar_wait(smem_u32(acc_full), (uint32_t)(seg & 1));
+      tc_fence_after();
+      for (int m = 0; m < P.mb; ++m) {
+        const int row = m * 128 + quarter * 32 + lane;
+        const int col_beg = m * 128;                       // block 1 starts at column 128
+        const uint32_t tcol0 = m == 0 ? 0u : (uint32_t)P.np;
+        const bool live = row < P.n;
+        for (int c0 = col_beg + 16 * half; c0 < P.np; c0 += 32) {
+          uint32_t v[16];
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + tcol0 + (uint32_t)(c0 - col_beg);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+              : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+                "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+                "=r"(v[14]), "=r"(v[15])
+              : "r"(taddr));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          // pin the uses of v[] behind the wait (volatile asms keep their order)
+          asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),
+                            "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]),
+                            "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
+          if (live) {
+            float* dst = out + (size_t)row * P.np + c0;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) old[q] = dst[q];
-            } else {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) old[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            // pin the uses of v[] behind the wait (volatile asms keep their order)
-            asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),
-                              "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]),
-                              "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
-            if (live) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q)
-                dst[q] = make_float4(old[q].x + __uint_as_float(v[4 * q]), old[q].y + __uint_as_float(v[4 * q + 1]),
-                                     old[q].z + __uint_as_float(v[4 * q + 2]), old[q].w + __uint_as_float(v[4 * q + 3]));
-            }
+            for (int q = 0; q < 4; ++q)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * q), "r"(v[4 * q]),
+                           "r"(v[4 * q + 1]), "r"(v[4 * q + 2]), "r"(v[4 * q + 3])
+                           : "memory");
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(acc_empty));
       }
-    } else {
-      // idle CTA (more CTAs than steps): contribute zeros
-      for (int i = threadIdx.x - 192; i < P.n * P.np; i += TC_EPILOGUE_WARPS * 32) out[i] = 0.f;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(acc_empty));
     }
   }
   tc_fence_before();
@@ -449,6 +441,7 @@ int syrk_tcgen05_launch(const float* x, int64_t ldx, int64_t k_rows, int n, floa
   P.part = reinterpret_cast<float*>(ws);
   LGNN_CUDA_TRY(cudaFuncSetAttribute(syrk_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)g.smem_bytes));
+  LGNN_CUDA_TRY(cudaMemsetAsync(P.part, 0, (size_t)grid * n * g.np * sizeof(float), st));
   syrk_tcgen05_kernel<<<grid, TC_THREADS, g.smem_bytes, st>>>(tmap, P);
   LGNN_LAUNCH_CHECK("syrk_tcgen05_kernel");
   int elems = n * g.np;

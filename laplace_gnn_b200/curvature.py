@@ -81,6 +81,7 @@ class _Whole:
         self.csr_t = graph.ahat_t
         self.n_local = self.total_rows = graph.n
         self.slot0 = 0
+        self.communicates = False
 
     def gather(self, slab):
         pass
@@ -96,6 +97,7 @@ class _Rows:
         self.part = part
         self.csr_t = part.ahat_t
         self.n_local, self.total_rows, self.slot0 = part.n_local, part.total_rows, part.slot0
+        self.communicates = True
 
     def gather(self, slab):
         self.part.all_gather_slab(slab)
@@ -111,7 +113,7 @@ class _B200KFAC:
     """kron()/diag() on the B200 kernels; mixed into a CurvatureInterface subclass."""
 
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
-                    rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows"):
+                    rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if backward_parallel not in ("rows", "columns"):
@@ -131,6 +133,7 @@ class _B200KFAC:
         self.rhs_tile_bytes = rhs_tile_bytes
         self.syrk_impl = syrk_impl
         self.backward_parallel = backward_parallel
+        self.overlap = bool(overlap)
         self.n_outputs = self.model.out_channels
         self.last_stats: dict[str, Any] = {}
 
@@ -200,47 +203,90 @@ class _B200KFAC:
             self._part = part
         return part
 
-    def _backward_columns(self, lay, logits, idx, Hs, Ws, cols, G):
-        """Multi-RHS KFAC backward for the Hessian-sqrt columns ``cols = (first, count)`` on the
-        rows ``lay`` describes: G[l] += sum_c gZ_{l,c}^T gZ_{l,c}  (kfac.py:653-661, 777-817)."""
+    def _chain(self, lay, logits, idx, Hs, Ws, c0, gc, buf_a, buf_b, G):
+        """One group of ``gc`` Hessian-sqrt columns pushed down all layers; a generator that yields
+        after each layer so that two groups can be interleaved on two streams (their all-gathers
+        then overlap the other group's SpMM)."""
         L = len(Ws)
         C = logits.shape[1]
         dims = [w.shape[0] for w in Ws]                 # d_1 .. d_L (d_L = C)
         c_pad = (C + 3) // 4 * 4
+        n_loc, n_in, slot0 = lay.n_local, lay.total_rows, lay.slot0
+        slab = buf_a[: n_in * gc * c_pad].view(n_in, gc * c_pad)
+        delta = slab[slot0:slot0 + n_loc]
+        with ops.timed("hess_rhs", gc):
+            delta.zero_()
+            ops.hess_rhs(logits, idx, c0, gc, delta, c_pad, self.hess_sqrt)
+        width, ld = C, c_pad
+        for l in range(L - 1, -1, -1):
+            with ops.timed("allgather", gc * ld, 4.0 * n_in * gc * ld):
+                lay.gather(slab)
+            gz = buf_b[: n_loc * gc * ld].view(n_loc, gc * ld)
+            ops.spmm(lay.csr_t, slab, out=gz)
+            gz_rows = gz.view(n_loc * gc, ld)
+            ops.syrk(gz_rows, n=width, alpha=1.0, beta=1.0, out=G[l], impl=self._impl(width))
+            if l > 0:
+                d_prev = dims[l - 1]
+                slab = buf_a[: n_in * gc * d_prev].view(n_in, gc * d_prev)
+                nxt = slab[slot0:slot0 + n_loc].view(n_loc * gc, d_prev)
+                with ops.timed("gemm_bwd", d_prev, 2.0 * n_loc * gc * width * d_prev):
+                    torch.mm(gz_rows[:, :width], Ws[l], out=nxt)
+                with ops.timed("relu_mask", d_prev, 2.0 * n_loc * gc * d_prev * 4):
+                    ops.relu_mask_mul(nxt, Hs[l], gc)
+                width, ld = d_prev, d_prev
+            yield
+
+    def _backward_columns(self, lay, logits, idx, Hs, Ws, cols, G):
+        """Multi-RHS KFAC backward for the Hessian-sqrt columns ``cols = (first, count)`` on the
+        rows ``lay`` describes: G[l] += sum_c gZ_{l,c}^T gZ_{l,c}  (kfac.py:653-661, 777-817)."""
+        C = logits.shape[1]
+        dims = [w.shape[0] for w in Ws]
+        c_pad = (C + 3) // 4 * 4
         dmax = max([c_pad] + dims[:-1])
         c_first, c_count = cols
-        if c_count <= 0:
-            return 0, 0
         dev = logits.device
-        n_loc, n_in, slot0 = lay.n_local, lay.total_rows, lay.slot0
-        grp = lay.agree_min(min(self._group_size(n_in, n_loc, dmax, C, dev), c_count))
-        buf_a = torch.empty(n_in * grp * dmax, dtype=torch.float32, device=dev)    # SpMM inputs (slabs)
-        buf_b = torch.empty(max(n_loc, 1) * grp * dmax, dtype=torch.float32, device=dev)  # SpMM outputs
-        for c0 in range(c_first, c_first + c_count, grp):
-            gc = min(grp, c_first + c_count - c0)
-            slab = buf_a[: n_in * gc * c_pad].view(n_in, gc * c_pad)
-            delta = slab[slot0:slot0 + n_loc]
-            with ops.timed("hess_rhs", gc):
-                delta.zero_()
-                ops.hess_rhs(logits, idx, c0, gc, delta, c_pad, self.hess_sqrt)
-            width, ld = C, c_pad
-            for l in range(L - 1, -1, -1):
-                with ops.timed("allgather", gc * ld, 4.0 * n_in * gc * ld):
-                    lay.gather(slab)
-                gz = buf_b[: n_loc * gc * ld].view(n_loc, gc * ld)
-                ops.spmm(lay.csr_t, slab, out=gz)
-                gz_rows = gz.view(n_loc * gc, ld)
-                ops.syrk(gz_rows, n=width, alpha=1.0, beta=1.0, out=G[l], impl=self._impl(width))
-                if l > 0:
-                    d_prev = dims[l - 1]
-                    slab = buf_a[: n_in * gc * d_prev].view(n_in, gc * d_prev)
-                    nxt = slab[slot0:slot0 + n_loc].view(n_loc * gc, d_prev)
-                    with ops.timed("gemm_bwd", d_prev, 2.0 * n_loc * gc * width * d_prev):
-                        torch.mm(gz_rows[:, :width], Ws[l], out=nxt)
-                    with ops.timed("relu_mask", d_prev, 2.0 * n_loc * gc * d_prev * 4):
-                        ops.relu_mask_mul(nxt, Hs[l], gc)
-                    width, ld = d_prev, d_prev
-        return grp, (c_count + grp - 1) // grp
+        n_loc, n_in = lay.n_local, lay.total_rows
+        lanes = 2 if (self.overlap and lay.communicates and dev.type == "cuda") else 1
+        grp = self._group_size(lanes * n_in, lanes * n_loc, dmax, C, dev)
+        grp = lay.agree_min(max(1, min(grp, (c_count + lanes - 1) // lanes)))
+        if c_count <= 0:
+            return grp, 0
+        groups = [(c0, min(grp, c_first + c_count - c0)) for c0 in range(c_first, c_first + c_count, grp)]
+        lanes = min(lanes, len(groups))
+        bufs = [(torch.empty(n_in * grp * dmax, dtype=torch.float32, device=dev),          # SpMM inputs (slabs)
+                 torch.empty(max(n_loc, 1) * grp * dmax, dtype=torch.float32, device=dev))  # SpMM outputs
+                for _ in range(lanes)]
+        if lanes == 1:
+            for c0, gc in groups:
+                for _ in self._chain(lay, logits, idx, Hs, Ws, c0, gc, bufs[0][0], bufs[0][1], G):
+                    pass
+            return grp, len(groups)
+        # two column groups in flight, each on its own stream with its own buffers and factor
+        # accumulators: while one waits for its all-gather the other runs its SpMM / SYRK / GEMM
+        main = torch.cuda.current_stream(dev)
+        streams = [torch.cuda.Stream(dev) for _ in range(lanes)]
+        G_lane = [G] + [[torch.zeros_like(t) for t in G] for _ in range(lanes - 1)]
+        for st in streams:
+            st.wait_stream(main)
+        pending = list(groups)
+        active = [None] * lanes
+        while pending or any(a is not None for a in active):
+            for i in range(lanes):
+                with torch.cuda.stream(streams[i]):
+                    if active[i] is None and pending:
+                        c0, gc = pending.pop(0)
+                        active[i] = self._chain(lay, logits, idx, Hs, Ws, c0, gc, bufs[i][0], bufs[i][1], G_lane[i])
+                    if active[i] is not None:
+                        try:
+                            next(active[i])
+                        except StopIteration:
+                            active[i] = None
+        for st in streams:
+            main.wait_stream(st)
+        for extra in G_lane[1:]:
+            for t, e in zip(G, extra):
+                t += e
+        return grp, len(groups)
 
     # ------------------------------------------------------------------ kron
     def kron(self, x: torch.Tensor, y: torch.Tensor, N: int, **kwargs):
@@ -335,7 +381,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
     def __init__(self, model, likelihood, last_layer=False, subnetwork_indices=None,
                  dict_key_x="input_ids", dict_key_y="labels", stochastic=False,
                  hess_sqrt="reference", differentiable=False, process_group=None,
-                 rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows"):
+                 rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -345,7 +391,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                           dict_key_y, stochastic)
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
-                         backward_parallel)
+                         backward_parallel, overlap)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

@@ -249,7 +249,9 @@ _ws_cache: dict = {}
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
-    key = (device.type, device.index)
+    """Scratch for split-K partials, one buffer per (device, stream): two streams may run SYRKs
+    concurrently (overlapped column groups of the multi-GPU backward)."""
+    key = (device.type, device.index, torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)

@@ -1,0 +1,70 @@
+"""GPU, needs >= 2 devices (skipped on a 1-GPU box): the NCCL row-partitioned pass against the
+single-GPU pass on the same arxiv-like graph — both backward layouts, with and without the
+two-lane overlap.  One process per GPU; never more ranks than GPUs."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import laplace_gnn_b200 as L
+        n, u, f, c, h, layers = 40_000, 300_000, 64, 10, 128, 3
+        gen = torch.Generator(device=dev).manual_seed(0)
+        src = torch.randint(0, n, (u,), device=dev, generator=gen)
+        dst = torch.randint(0, n, (u,), device=dev, generator=gen)
+        ei = torch.stack([torch.cat([src, dst]), torch.cat([dst, src])])
+        X = torch.randn(n, f, device=dev, generator=gen)
+        idx = torch.randperm(n, device=dev, generator=gen)[: int(0.6 * n)].sort().values
+        y = torch.randint(0, c, (idx.numel(),), device=dev, generator=gen)
+        torch.manual_seed(0)
+        model = L.SparseGCN(f, h, c, layers, X, L.Graph.from_edge_index(ei, n)).to(dev)
+
+        def fit(**kw):
+            la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs=kw)
+            la.fit(L.TensorBatchLoader(idx, y))
+            return la, float(la.log_marginal_likelihood())
+
+        ref, ref_ml = fit()
+        for kw in ({"backward_parallel": "rows", "overlap": False},
+                   {"backward_parallel": "rows", "overlap": True, "rhs_tile_bytes": 64 << 20},
+                   {"backward_parallel": "columns"}):
+            la, ml = fit(process_group=dist.group.WORLD, **kw)
+            for blk, rblk in zip(la.H_facs.kfacs, ref.H_facs.kfacs):
+                for a, b in zip(blk, rblk):
+                    err = float((a - b).abs().max() / b.abs().max())
+                    assert err <= 2e-5, (kw, err)
+            assert abs(ml - ref_ml) <= 1e-5 * abs(ref_ml), (kw, ml, ref_ml)
+            assert abs(float(la.loss) - float(ref.loss)) <= 1e-6 * abs(float(ref.loss))
+        out[rank] = ref_ml
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
+def test_nccl_partitioned_fit_matches_single_gpu():
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert len(out) == world

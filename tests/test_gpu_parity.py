@@ -138,7 +138,7 @@ def test_spmm_bulk_kernel_matches_oracle_and_ldg_kernel(d, relu):
         y = ops.spmm(csr, xd, relu=relu, impl="bulk")
         assert max_rel_err(y.cpu().numpy(), ref.numpy()) <= 1e-5
         assert torch.equal(y, ops.spmm(csr, xd, relu=relu, impl="ldg"))
-        assert torch.equal(y, ops.spmm(csr, xd, relu=relu))          # auto picks bulk for d >= 512
+        assert torch.equal(y, ops.spmm(csr, xd, relu=relu))          # auto: whichever kernel the width selects
 
 
 def test_spmm_bulk_kernel_empty_rows_hub_rows_and_leading_dimensions():
@@ -342,3 +342,26 @@ def test_arxiv_shape_properties():
     A0 = (X.double().T @ X.double() / idx.numel()).float()
     assert max_rel_err(kron.kfacs[0][1].cpu().numpy(), A0.cpu().numpy()) <= 1e-4
     assert torch.isfinite(loss)
+
+
+# ---------------------------------------------------------------------------------- exact diag GGN
+@pytest.mark.parametrize("name", ["tiny_undirected_2l", "tiny_directed_3l", "tiny_directed_dups_2l",
+                                  "tiny_symmetrised_2l"])
+def test_diag_laplace_matches_reference_golden(name):
+    """hessian_structure="diag": backend.diag() vs the reference's DiagLaplace (GGNInterface.diag,
+    curvature.py:412-432) stored by oracle/make_golden.py.  diag GGN <= 1e-4 rel, marglik <= 1e-3 rel."""
+    import laplace_gnn_b200 as L
+    from laplace_gnn_b200.diag import diag_ggn_exact
+    g = Golden(name)
+    if "diag_H" not in g.z.files:
+        pytest.skip("fixture has no diag reference")
+    model = build_model(g, DEV)
+    la = L.Laplace(model, "classification", hessian_structure="diag", backend=L.B200GGN)
+    la.fit(loader_for(g, DEV))
+    assert max_rel_err(la.H.cpu().numpy(), g.z["diag_H"]) <= 1e-4
+    ref_ml = float(g.z["diag_marglik"])
+    assert abs(float(la.log_marginal_likelihood()) - ref_ml) <= 1e-3 * abs(ref_ml)
+    idx, y = torch.from_numpy(g.idx).to(DEV), torch.from_numpy(g.y).to(DEV)
+    _, d1 = diag_ggn_exact(la.backend, idx, y, tile_bytes=1)             # one train node per tile
+    if g.batch_size == len(g.idx):
+        assert max_rel_err(d1.cpu().numpy(), g.z["diag_H"]) <= 1e-4

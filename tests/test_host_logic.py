@@ -62,6 +62,29 @@ def test_ggn_mode_switch(fake_ops):
         L.B200GGN(model, "classification", hess_sqrt="nope")
 
 
+def test_exact_diag_ggn_matches_oracle_and_kron_diag(fake_ops):
+    """diag() vs the brute-force Jacobian oracle (curvature.py:412-432), in several tiles, and the
+    reference's own kron-vs-diag consistency property (tests/test_curv_backends_curvlinops.py:241-247)."""
+    import laplace_gnn_b200 as L
+    from laplace_gnn_b200.diag import diag_ggn_exact
+    from oracle import gcn_kfac_oracle as O
+    for name in ("tiny_undirected_2l", "tiny_directed_3l"):
+        g = Golden(name)
+        model = build_model(g)
+        idx, y = torch.from_numpy(g.idx), torch.from_numpy(g.y)
+        be = L.B200GGN(model, "classification", hess_sqrt="ggn")
+        loss, d = be.diag(idx, y, N=len(y))
+        G = O.build_graph(g.edge_index, g.n, g.symmetric)
+        ref_loss, ref = O.diag_ggn(G, g.x, g.Ws, g.bs, g.idx, g.y)
+        assert max_rel_err(d.numpy(), ref.numpy()) <= 1e-4
+        assert abs(float(loss) - float(ref_loss)) <= 1e-5 * abs(float(ref_loss))
+        _, d2 = diag_ggn_exact(be, idx, y, tile_bytes=1)                  # one train node per tile
+        assert max_rel_err(d2.numpy(), d.numpy()) <= 1e-5
+        la = L.Laplace(model, "classification", hessian_structure="diag", backend=L.B200GGN)
+        la.fit(loader_for(g))
+        assert torch.isfinite(la.log_marginal_likelihood())
+
+
 def test_backend_rejects_what_is_outside_the_path(fake_ops):
     import laplace_gnn_b200 as L
     g = Golden("tiny_undirected_2l")
