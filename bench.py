@@ -45,8 +45,9 @@ def parse_args():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink nodes and edges by this factor (debug)")
     ap.add_argument("--hess-sqrt", default="reference", choices=["reference", "ggn"])
     ap.add_argument("--syrk", default="auto", choices=["auto", "simt", "tcgen05"])
-    ap.add_argument("--backward-parallel", default="rows", choices=["rows", "columns"],
+    ap.add_argument("--backward-parallel", default="columns", choices=["rows", "columns"],
                     help="multi-GPU layout of the KFAC backward (laplace_gnn_b200/dist.py)")
+    ap.add_argument("--no-overlap", action="store_true", help="rows layout: one column group in flight instead of two")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-div", type=int, default=64)
@@ -225,6 +226,7 @@ def main():
     if pg is not None:
         bk["process_group"] = pg
         bk["backward_parallel"] = args.backward_parallel
+        bk["overlap"] = not args.no_overlap
     loader = L.TensorBatchLoader(idx, y)      # one full batch, no per-sample collation
 
     def step(mdl, ldr):

@@ -31,7 +31,7 @@ def test_syrk_tcgen05_matches_fp64(k, n):
     assert torch.equal(c, c.T)
     assert torch.equal(ops.syrk(x, impl="tcgen05"), c)                # deterministic reduction
     simt = ops.syrk(x, impl="simt")
-    assert max_rel_err(c.cpu().numpy(), simt.cpu().numpy()) <= 1e-5
+    assert max_rel_err(c.cpu().numpy(), simt.cpu().numpy()) <= 4e-5   # each is ~1e-5 from fp64
 
 
 def test_syrk_tcgen05_alpha_beta_and_leading_dimension():
