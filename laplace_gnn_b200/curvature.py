@@ -356,7 +356,9 @@ class _B200KFAC:
         for l in range(L):
             kfacs.append([G[l], A[l]])
             if bs[l] is not None:
-                kfacs.append([G[l].clone()])
+                dup = G[l].clone()
+                dup._dup_of = G[l]          # lets the stand-in Kron.decompose skip the repeated eigh
+                kfacs.append([dup])
         kron = Kron(kfacs)
         return (self.factor * loss).to(torch.float32), kron
 
