@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--backward-parallel", default="columns", choices=["rows", "columns"],
                     help="multi-GPU layout of the KFAC backward (laplace_gnn_b200/dist.py)")
     ap.add_argument("--no-overlap", action="store_true", help="rows layout: one column group in flight instead of two")
+    ap.add_argument("--no-fused-gemm", action="store_true", help="cuBLAS fp32 GEMM + mask kernel instead of the fused tcgen05 kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-div", type=int, default=64)
@@ -222,7 +223,7 @@ def main():
     nnz = model.graph.nnz
     if args.no_e2e:
         del edge_index
-    bk = {"hess_sqrt": args.hess_sqrt, "syrk_impl": args.syrk}
+    bk = {"hess_sqrt": args.hess_sqrt, "syrk_impl": args.syrk, "fused_gemm": not args.no_fused_gemm}
     if pg is not None:
         bk["process_group"] = pg
         bk["backward_parallel"] = args.backward_parallel

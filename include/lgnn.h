@@ -175,6 +175,26 @@ int lgnn_syrk_f32(const float* x, int64_t ldx, int64_t k_rows, int64_t n, float 
                   float* c, int64_t ldc, void* ws, size_t ws_bytes, int impl,
                   lgnn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * fused back-propagation step between two SpMMs — tensor-core / HBM balanced
+ * ---------------------------------------------------------------------------------------- */
+
+/* out[r, 0:n] = (A[r, 0:k] . W[0:k, 0:n]) * (act[r / group, 0:n] > 0),  r in [0, m_rows).
+ * The relu-masked product delta_{l-1} = (gZ_l W_l) ⊙ 1[H_{l-1} > 0] that autograd computes between
+ * the aggregation backward passes of curvlinops/kfac.py:653-661 (gnn/models/base_gnn.py:150,
+ * gnn/models/layers.py:45).  A = gZ viewed as [nodes*group, k] (pitch lda), W = conv.lin.weight
+ * [k = d_l, n = d_{l-1}] row-major (pitch ldw); act = H_{l-1} [nodes, n]; act == NULL skips the mask.
+ * 3xTF32 on tcgen05 tensor cores; supported for k <= 256 and n in {64, 128, 256}
+ * (lgnn_gemm_mask_supported); all pointers 16-byte aligned, pitches multiples of 4 floats.
+ * The weights are prepared once per W into two [n, kpad] arrays (kpad = lgnn_gemm_mask_kpad(k)). */
+int lgnn_gemm_mask_supported(int64_t k, int64_t n);
+int64_t lgnn_gemm_mask_kpad(int64_t k);
+int lgnn_gemm_mask_prepare_f32(const float* w, int64_t ldw, int64_t k, int64_t n, float* wt_hi,
+                               float* wt_lo, lgnn_stream_t stream);
+int lgnn_gemm_mask_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, const float* wt_hi,
+                       const float* wt_lo, int64_t n, const float* act, int64_t ld_act, int32_t group,
+                       float* out, int64_t ldo, lgnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,6 +40,10 @@ PROTOTYPES = {
     "lgnn_softmax_ce_sum": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
     "lgnn_hess_rhs_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, C.c_int, _vp, _vp]),
     "lgnn_relu_mask_mul_f32": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i64, _vp]),
+    "lgnn_gemm_mask_supported": (C.c_int, [_i64, _i64]),
+    "lgnn_gemm_mask_kpad": (_i64, [_i64]),
+    "lgnn_gemm_mask_prepare_f32": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "lgnn_gemm_mask_f32": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
     "lgnn_syrk_workspace_bytes": (_sz, [_i64, _i64, C.c_int]),
     "lgnn_syrk_f32": (C.c_int, [_vp, _i64, _i64, _i64, _f32, _f32, _vp, _i64, _vp, _sz, C.c_int, _vp]),
 }

@@ -113,7 +113,8 @@ class _B200KFAC:
     """kron()/diag() on the B200 kernels; mixed into a CurvatureInterface subclass."""
 
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
-                    rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True):
+                    rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
+                    fused_gemm=True):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if backward_parallel not in ("rows", "columns"):
@@ -134,6 +135,7 @@ class _B200KFAC:
         self.syrk_impl = syrk_impl
         self.backward_parallel = backward_parallel
         self.overlap = bool(overlap)
+        self.fused_gemm = bool(fused_gemm)
         self.n_outputs = self.model.out_channels
         self.last_stats: dict[str, Any] = {}
 
@@ -203,7 +205,7 @@ class _B200KFAC:
             self._part = part
         return part
 
-    def _chain(self, lay, logits, idx, Hs, Ws, c0, gc, buf_a, buf_b, G):
+    def _chain(self, lay, logits, idx, Hs, Ws, Wp, c0, gc, buf_a, buf_b, G):
         """One group of ``gc`` Hessian-sqrt columns pushed down all layers; a generator that yields
         after each layer so that two groups can be interleaved on two streams (their all-gathers
         then overlap the other group's SpMM)."""
@@ -229,10 +231,13 @@ class _B200KFAC:
                 d_prev = dims[l - 1]
                 slab = buf_a[: n_in * gc * d_prev].view(n_in, gc * d_prev)
                 nxt = slab[slot0:slot0 + n_loc].view(n_loc * gc, d_prev)
-                with ops.timed("gemm_bwd", d_prev, 2.0 * n_loc * gc * width * d_prev):
-                    torch.mm(gz_rows[:, :width], Ws[l], out=nxt)
-                with ops.timed("relu_mask", d_prev, 2.0 * n_loc * gc * d_prev * 4):
-                    ops.relu_mask_mul(nxt, Hs[l], gc)
+                if Wp[l] is not None:      # fused 3xTF32 tensor-core GEMM + relu' mask
+                    ops.gemm_mask(gz_rows, Wp[l], Hs[l], gc, out=nxt, m_rows=n_loc * gc)
+                else:                      # shapes the fused kernel does not take: cuBLAS + mask kernel
+                    with ops.timed("gemm_bwd", d_prev, 2.0 * n_loc * gc * width * d_prev):
+                        torch.mm(gz_rows[:, :width], Ws[l], out=nxt)
+                    with ops.timed("relu_mask", d_prev, 2.0 * n_loc * gc * d_prev * 4):
+                        ops.relu_mask_mul(nxt, Hs[l], gc)
                 width, ld = d_prev, d_prev
             yield
 
@@ -252,13 +257,17 @@ class _B200KFAC:
         if c_count <= 0:
             return grp, 0
         groups = [(c0, min(grp, c_first + c_count - c0)) for c0 in range(c_first, c_first + c_count, grp)]
+        # W_l [d_l, d_{l-1}] as resident tensor-core operands, once per pass
+        Wp = [None] + [ops.gemm_mask_prepare(Ws[l]) if self.fused_gemm and dev.type == "cuda" and
+                       ops.gemm_mask_supported(Ws[l].shape[0], Ws[l].shape[1]) else None
+                       for l in range(1, len(Ws))]
         lanes = min(lanes, len(groups))
         bufs = [(torch.empty(n_in * grp * dmax, dtype=torch.float32, device=dev),          # SpMM inputs (slabs)
                  torch.empty(max(n_loc, 1) * grp * dmax, dtype=torch.float32, device=dev))  # SpMM outputs
                 for _ in range(lanes)]
         if lanes == 1:
             for c0, gc in groups:
-                for _ in self._chain(lay, logits, idx, Hs, Ws, c0, gc, bufs[0][0], bufs[0][1], G):
+                for _ in self._chain(lay, logits, idx, Hs, Ws, Wp, c0, gc, bufs[0][0], bufs[0][1], G):
                     pass
             return grp, len(groups)
         # two column groups in flight, each on its own stream with its own buffers and factor
@@ -275,7 +284,7 @@ class _B200KFAC:
                 with torch.cuda.stream(streams[i]):
                     if active[i] is None and pending:
                         c0, gc = pending.pop(0)
-                        active[i] = self._chain(lay, logits, idx, Hs, Ws, c0, gc, bufs[i][0], bufs[i][1], G_lane[i])
+                        active[i] = self._chain(lay, logits, idx, Hs, Ws, Wp, c0, gc, bufs[i][0], bufs[i][1], G_lane[i])
                     if active[i] is not None:
                         try:
                             next(active[i])
@@ -383,7 +392,8 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
     def __init__(self, model, likelihood, last_layer=False, subnetwork_indices=None,
                  dict_key_x="input_ids", dict_key_y="labels", stochastic=False,
                  hess_sqrt="reference", differentiable=False, process_group=None,
-                 rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True):
+                 rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
+                 fused_gemm=True):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -393,7 +403,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                           dict_key_y, stochastic)
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
-                         backward_parallel, overlap)
+                         backward_parallel, overlap, fused_gemm)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

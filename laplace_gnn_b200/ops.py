@@ -243,6 +243,57 @@ def relu_mask_mul(inp: torch.Tensor, act: torch.Tensor, group: int, out: torch.T
     return out
 
 
+# ------------------------------------------------------------------------------ fused (gZ W) ⊙ relu'
+@dataclass
+class PreparedWeight:
+    """W [k, n] as the two K-major tensor-core operands of the fused GEMM: wt_hi = W^T (the tensor
+    core truncates it to tf32), wt_lo = W^T - trunc_tf32(W^T); both [n, kpad], zero padded."""
+    k: int
+    n: int
+    wt_hi: torch.Tensor
+    wt_lo: torch.Tensor
+
+
+def gemm_mask_supported(k: int, n: int) -> bool:
+    return bool(_lib.load().lgnn_gemm_mask_supported(int(k), int(n)))
+
+
+def gemm_mask_prepare(w: torch.Tensor) -> PreparedWeight:
+    lib = _lib.load()
+    _f32c(w, "w")
+    k, n = int(w.shape[0]), int(w.shape[1])
+    kpad = int(lib.lgnn_gemm_mask_kpad(k))
+    hi = torch.empty(n, kpad, dtype=torch.float32, device=w.device)
+    lo = torch.empty(n, kpad, dtype=torch.float32, device=w.device)
+    check(lib.lgnn_gemm_mask_prepare_f32(ptr(w), w.stride(0), k, n, ptr(hi), ptr(lo), stream()),
+          "lgnn_gemm_mask_prepare_f32")
+    _lib.count_launches(1)
+    return PreparedWeight(k, n, hi, lo)
+
+
+def gemm_mask(a: torch.Tensor, w: PreparedWeight, act: torch.Tensor | None, group: int,
+              out: torch.Tensor | None = None, m_rows: int | None = None) -> torch.Tensor:
+    """out[r, :] = (a[r, :k] @ W) * (act[r // group, :] > 0)   (act=None: plain product)."""
+    lib = _lib.load()
+    _f32c(a, "a")
+    m_rows = int(a.shape[0]) if m_rows is None else int(m_rows)
+    if a.shape[1] < w.k:
+        raise ValueError("gemm_mask: a has fewer columns than W has rows")
+    if out is None:
+        out = torch.empty(m_rows, w.n, dtype=torch.float32, device=a.device)
+    _f32c(out, "out")
+    if act is not None:
+        _f32c(act, "act")
+        if act.shape[0] * group < m_rows or act.shape[1] < w.n:
+            raise ValueError("gemm_mask: act too small")
+    with _Timed("gemm_mask", w.n, 2.0 * m_rows * w.k * w.n):
+        check(lib.lgnn_gemm_mask_f32(ptr(a), a.stride(0), m_rows, w.k, ptr(w.wt_hi), ptr(w.wt_lo), w.n,
+                                     ptr(act), 0 if act is None else act.stride(0), int(group),
+                                     ptr(out), out.stride(0), stream()), "lgnn_gemm_mask_f32")
+    _lib.count_launches(1)
+    return out
+
+
 # ------------------------------------------------------------------------------ SYRK
 _SYRK_IMPL = {"auto": _lib.SYRK_AUTO, "simt": _lib.SYRK_SIMT, "tcgen05": _lib.SYRK_TCGEN05}
 _ws_cache: dict = {}

@@ -106,5 +106,9 @@ def syrk(x, n=None, alpha=1.0, beta=0.0, out=None, impl="auto", k_rows=None):
     return out
 
 
-ALL = ["csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
+def gemm_mask_supported(k, n):
+    return False          # the CPU double keeps the two-step path (torch.mm + relu_mask_mul)
+
+
+ALL = ["gemm_mask_supported", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
        "halo_columns", "csr_slice_remap", "spmm", "softmax_ce_sum", "hess_rhs", "relu_mask_mul", "syrk"]

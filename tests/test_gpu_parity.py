@@ -365,3 +365,44 @@ def test_diag_laplace_matches_reference_golden(name):
     _, d1 = diag_ggn_exact(la.backend, idx, y, tile_bytes=1)             # one train node per tile
     if g.batch_size == len(g.idx):
         assert max_rel_err(d1.cpu().numpy(), g.z["diag_H"]) <= 1e-4
+
+
+# ---------------------------------------------------------------------------------- fused (gZ W) ⊙ relu'
+@pytest.mark.parametrize("m,k,n,group", [(1000, 47, 256, 3), (129, 256, 256, 1), (5000, 64, 64, 5),
+                                           (70_001, 256, 128, 7), (128 * 32 * 3 + 5, 200, 256, 4),
+                                           (1, 8, 64, 1), (300_000, 256, 256, 12)])
+def test_gemm_mask_fused_kernel_matches_fp64(m, k, n, group):
+    """out = (A W) ⊙ (act > 0) on tcgen05 (3xTF32, cluster multicast) vs fp64, and vs the two-step
+    cuBLAS + mask-kernel path it replaces."""
+    ops = _ops()
+    gen = torch.Generator(device=DEV).manual_seed(m + k + n)
+    ld = (k + 3) // 4 * 4
+    a = torch.randn(m, ld, device=DEV, generator=gen)[:, :k]
+    w = torch.randn(k, n, device=DEV, generator=gen) / k ** 0.5
+    nodes = (m + group - 1) // group
+    act = torch.randn(nodes, n, device=DEV, generator=gen)
+    assert ops.gemm_mask_supported(k, n)
+    wp = ops.gemm_mask_prepare(w)
+    out = ops.gemm_mask(a, wp, act, group)
+    mask = (act > 0).repeat_interleave(group, dim=0)[:m]
+    ref = (a.double() @ w.double()) * mask
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    assert err <= 5e-6, err                              # fp32-faithful (plain TF32 would be ~5e-4)
+    two_step = ops.relu_mask_mul(torch.mm(a, w), act, group) if m == nodes * group else None
+    if two_step is not None:
+        assert float((out - two_step).abs().max() / ref.abs().max()) <= 5e-6
+    plain = ops.gemm_mask(a, wp, None, group)           # no mask
+    assert float((plain.double() - a.double() @ w.double()).abs().max() / ref.abs().max()) <= 5e-6
+    assert torch.equal(out, ops.gemm_mask(a, wp, act, group))   # deterministic
+
+
+def test_fused_and_two_step_backends_agree():
+    import laplace_gnn_b200 as L
+    g = Golden("pubmed_shape")
+    model = build_model(g, DEV)
+    idx, y = torch.from_numpy(g.idx).to(DEV), torch.from_numpy(g.y).to(DEV)
+    _, k1 = L.B200GGN(model, "classification", fused_gemm=True).kron(idx, y, N=len(y))
+    _, k2 = L.B200GGN(model, "classification", fused_gemm=False).kron(idx, y, N=len(y))
+    for fa, fb in zip(k1.kfacs, k2.kfacs):
+        for a, b in zip(fa, fb):
+            assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 2e-5
