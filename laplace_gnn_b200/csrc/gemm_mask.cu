@@ -12,19 +12,30 @@
 // shared memory for its whole life, and the cluster shares ONE read of each A tile: every CTA
 // TMA-loads 128/cluster rows of the tile and multicasts them into all CTAs' shared memory.
 //
-// Shared memory operands are K-major with the 128-byte swizzle exactly as TMA writes them, so the
-// raw fp32 tile IS the "hi" operand (kind::tf32 ignores the low 13 mantissa bits); only "lo" =
-// x - trunc_tf32(x) is materialised by the transform warps, chunk for chunk at the same swizzled
-// address — no transposition, no bank conflicts.
+// The A operand lives in TENSOR MEMORY: TMA writes the raw fp32 tile into a 5-deep shared-memory
+// ring (128-byte swizzle), four transform warps — one thread per tile row, which is also one TMEM
+// lane — read their row, split it into hi = x (kind::tf32 ignores the low 13 mantissa bits) and
+// lo = x - trunc_tf32(x), and tcgen05.st both into a 4-deep ring of TMEM operand stages.  The MMAs
+// then take A from TMEM and only the resident weight slice from shared memory (K-major, 128-byte
+// swizzle, as TMA wrote it).  With M=128 N=64 an all-shared-memory operand path needs 192 B/clk
+// of shared-memory bandwidth (more than the 128 B/clk an SM has) — measured 9.5 us per tile in v1;
+// with A in TMEM the tensor path reads 64 B/clk.
 //
-// Per CTA (10 warps): warp 0 TMA producer; warp 1 MMA issuer (one thread; 12 MMAs M=128 N=64 K=8 per
-// 32-wide k-block; accumulator double-buffered in TMEM); warps 2-5 lo transform; warps 6-9 epilogue
-// (tcgen05.ld -> mask -> 128-bit stores).  A ring stage is recycled when the MMAs of ALL CTAs of the
-// cluster have consumed it (tcgen05.commit multicast onto every CTA's "empty" barrier), because the
-// next multicast overwrites it everywhere.
+// Per CTA (14 warps): warp 0 TMA producer; warp 1 MMA issuer (one thread; 12 MMAs M=128 N=64 K=8 per
+// 32-wide k-block; accumulator double-buffered in TMEM); warps 2-9 transform (two sets of four
+// alternate k-blocks: the wait -> ld.shared -> split -> tcgen05.st -> wait::st -> arrive chain of one
+// k-block is longer than the 384 cycles its MMAs take); warps 10-13 epilogue (tcgen05.ld ->
+// shared-memory staging -> 128-bit stores of 64 contiguous bytes per row; the relu' mask words of the
+// NEXT tile are prefetched while the current one is stored).  A raw ring
+// stage is recycled when the transform warps of ALL CTAs of the cluster have read it (remote
+// mbarrier arrives), because the next multicast overwrites it everywhere.
 //
 // Roofline: useful flops 2·M·K·N; HBM bytes M·(K + N)·4 + mask; at K = N = 256 both
-// bounds are ~40 ms per 115 M rows — the kernel is balanced between the tensor pipe and HBM.
+// bounds are ~40 ms per 115 M rows.  Measured (profiles/r1c_gemm_lab.txt): 97 useful TFLOP/s at
+// K = N = 256 (291 issued, 25 % of the TF32 peak) — with N = 64 per CTA every MMA still reads a
+// full 4 KB A operand, so the operand path, not the MMA floor, paces the k-loop (~90 cycles per
+// MMA instead of 32).  An L2 prefetch ahead of the ring and doubling the transform warps changed
+// nothing, which rules out HBM latency and the transform chain.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -35,12 +46,17 @@ namespace lgnn {
 constexpr int GM_BM = 128;            // rows per tile
 constexpr int GM_BN = 64;             // output columns per CTA
 constexpr int GM_BK = 32;             // floats per k-block = 128 bytes = one swizzle row
-constexpr int GM_STAGES = 3;
-constexpr int GM_THREADS = 320;
+constexpr int GM_RAW_STAGES = 5;      // shared-memory ring of raw A k-blocks
+constexpr int GM_TM_STAGES = 4;       // TMEM ring of (hi, lo) A operand k-blocks, 64 columns each
+constexpr int GM_THREADS = 448;            // 1 TMA + 1 MMA + 8 transform + 4 epilogue warps
 constexpr int GM_A_TILE = GM_BM * GM_BK * 4;   // 16 KB
 constexpr int GM_B_TILE = GM_BN * GM_BK * 4;   // 8 KB
 constexpr int GM_TILES_PER_CLUSTER = 32;
 constexpr int GM_MAX_KB = 8;                   // K <= 256
+constexpr int GM_STG_PITCH = 80;               // epilogue staging: 16 floats per row + 16 bytes pad
+constexpr int GM_STG_WARP = 32 * GM_STG_PITCH; // per epilogue warp
+constexpr uint32_t GM_TMEM_COLS = 512;         // D: 2 x 64, A: 4 x 64
+constexpr uint32_t GM_TMEM_A0 = 128;
 
 struct GmParams {
   int64_t m_rows;
@@ -55,6 +71,37 @@ struct GmParams {
   int64_t ldo;
 };
 
+__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
+        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
+        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_bar), "r"(cta));
+  // default semantics (release at CTA scope), like cutlass::arch::ClusterBarrier::arrive(cta_id): a
+  // cluster-scope release costs a MEMBAR.ALL.GPU + ERRBAR per call (26 % of all stall samples in the
+  // first ncu capture); the data this arrive orders (shared-memory reads) is already in registers.
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_bhi,
                  const __grid_constant__ CUtensorMap tm_blo, const GmParams P) {
@@ -62,14 +109,16 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gm_smem_) + 1023) & ~(uintptr_t)1023);
   uint8_t* b_hi = smem;
   uint8_t* b_lo = b_hi + (size_t)P.n_kb * GM_B_TILE;
-  uint8_t* a_base = b_lo + (size_t)P.n_kb * GM_B_TILE;   // stage s: raw at +s*32 KB, lo 16 KB behind it
-  uint64_t* bars = reinterpret_cast<uint64_t*>(a_base + (size_t)GM_STAGES * 2 * GM_A_TILE);
-  uint64_t* full_raw = bars;                    // [STAGES] TMA bytes of all cluster slices landed
-  uint64_t* lo_ready = full_raw + GM_STAGES;    // [STAGES] transform warps wrote lo
-  uint64_t* empty = lo_ready + GM_STAGES;       // [STAGES] MMAs of every CTA of the cluster consumed it
-  uint64_t* b_full = empty + GM_STAGES;         // [1]
-  uint64_t* acc_full = b_full + 1;              // [2]
-  uint64_t* acc_empty = acc_full + 2;           // [2]
+  uint8_t* a_raw = b_lo + (size_t)P.n_kb * GM_B_TILE;                    // [RAW_STAGES][16 KB]
+  uint8_t* stg = a_raw + (size_t)GM_RAW_STAGES * GM_A_TILE;               // [4 warps][32 rows][80 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 4 * GM_STG_WARP);
+  uint64_t* full_raw = bars;                       // [RAW] TMA bytes of all cluster slices landed
+  uint64_t* empty_raw = full_raw + GM_RAW_STAGES;  // [RAW] transform warps of every CTA have read it
+  uint64_t* ta_full = empty_raw + GM_RAW_STAGES;   // [TM]  hi / lo operand stage written to TMEM
+  uint64_t* ta_empty = ta_full + GM_TM_STAGES;     // [TM]  MMAs that read it completed
+  uint64_t* b_full = ta_empty + GM_TM_STAGES;      // [1]
+  uint64_t* acc_full = b_full + 1;                 // [2]
+  uint64_t* acc_empty = acc_full + 2;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -85,10 +134,13 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int n0 = (int)rank * GM_BN;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < GM_STAGES; ++i) {
+    for (int i = 0; i < GM_RAW_STAGES; ++i) {
       mbar_init(smem_u32(&full_raw[i]), 1);
-      mbar_init(smem_u32(&lo_ready[i]), 4);
-      mbar_init(smem_u32(&empty[i]), (uint32_t)cl);
+      mbar_init(smem_u32(&empty_raw[i]), (uint32_t)(4 * cl));
+    }
+    for (int i = 0; i < GM_TM_STAGES; ++i) {
+      mbar_init(smem_u32(&ta_full[i]), 4);
+      mbar_init(smem_u32(&ta_empty[i]), 1);
     }
     mbar_init(smem_u32(b_full), 1);
     for (int i = 0; i < 2; ++i) {
@@ -99,7 +151,7 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(128u)
+                 "r"(GM_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -121,23 +173,17 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
       const int rows_per_cta = GM_BM / cl;
       for (int64_t it = 0; it < total_it; ++it) {
-        const int s = (int)(it % GM_STAGES);
-        const uint32_t ph = (uint32_t)((it / GM_STAGES) & 1);
+        const int s = (int)(it % GM_RAW_STAGES);
+        const uint32_t ph = (uint32_t)((it / GM_RAW_STAGES) & 1);
         const int64_t tile = tile_beg + it / P.n_kb;
         const int kb = (int)(it % P.n_kb);
-        mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
+        mbar_wait(smem_u32(&empty_raw[s]), ph ^ 1u);
         const uint32_t bar = smem_u32(&full_raw[s]);
         mbar_arrive_expect_tx(bar, (uint32_t)GM_A_TILE);
-        const uint32_t dst = smem_u32(a_base + (size_t)s * 2 * GM_A_TILE + (size_t)rank * rows_per_cta * GM_BK * 4);
+        const uint32_t dst = smem_u32(a_raw + (size_t)s * GM_A_TILE + (size_t)rank * rows_per_cta * GM_BK * 4);
         const int row0 = (int)(tile * GM_BM + (int64_t)rank * rows_per_cta);
         if (cl > 1) tma_load_2d_multicast(dst, &tm_a, kb * GM_BK, row0, bar, cta_mask);
         else tma_load_2d(dst, &tm_a, kb * GM_BK, row0, bar);
-      }
-      // tail: the last uses of every stage have been released by ALL CTAs, i.e. no remote arrive is
-      // still heading for this CTA's barriers when it leaves
-      for (int64_t it = total_it; it < total_it + GM_STAGES; ++it) {
-        if (it < GM_STAGES) continue;   // stage never used
-        mbar_wait(smem_u32(&empty[it % GM_STAGES]), (uint32_t)((it / GM_STAGES) & 1) ^ 1u);
       }
     }
   } else if (warp == 1) {
@@ -153,122 +199,171 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const uint32_t d = tmem_base + (uint32_t)(as * GM_BN);
         for (int kb = 0; kb < P.n_kb; ++kb) {
           const int64_t it = t * P.n_kb + kb;
-          const int s = (int)(it % GM_STAGES);
-          const uint32_t ph = (uint32_t)((it / GM_STAGES) & 1);
-          mbar_wait(smem_u32(&full_raw[s]), ph);
-          mbar_wait(smem_u32(&lo_ready[s]), ph);
+          const int s = (int)(it % GM_TM_STAGES);
+          const uint32_t ph = (uint32_t)((it / GM_TM_STAGES) & 1);
+          mbar_wait(smem_u32(&ta_full[s]), ph);
           tc_fence_after();
-          const uint32_t a_hi = smem_u32(a_base + (size_t)s * 2 * GM_A_TILE);
-          const uint32_t a_lo = a_hi + GM_A_TILE;
+          const uint32_t a_hi = tmem_base + GM_TMEM_A0 + (uint32_t)(s * 64);   // 32 columns hi, 32 columns lo
+          const uint32_t a_lo = a_hi + 32;
           const uint32_t bh = smem_u32(b_hi + (size_t)kb * GM_B_TILE);
           const uint32_t bl = smem_u32(b_lo + (size_t)kb * GM_B_TILE);
           const int ksteps = (kb == P.n_kb - 1) ? P.last_ksteps : GM_BK / 8;
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint32_t off = (uint32_t)ks * 32u;   // 8 tf32 = 32 bytes inside the 128-byte swizzle row
-            const uint64_t da_hi = make_smem_desc(a_hi + off, 0, 1024, 2);
-            const uint64_t da_lo = make_smem_desc(a_lo + off, 0, 1024, 2);
             const uint64_t db_hi = make_smem_desc(bh + off, 0, 1024, 2);
             const uint64_t db_lo = make_smem_desc(bl + off, 0, 1024, 2);
-            tc_mma_tf32(d, da_hi, db_hi, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
-            tc_mma_tf32(d, da_hi, db_lo, idesc, 1u);
-            tc_mma_tf32(d, da_lo, db_hi, idesc, 1u);
+            const uint32_t ca = (uint32_t)(ks * 8);    // 8 tf32 = 8 TMEM columns
+            tc_mma_tf32_ts(d, a_hi + ca, db_hi, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
+            tc_mma_tf32_ts(d, a_hi + ca, db_lo, idesc, 1u);
+            tc_mma_tf32_ts(d, a_lo + ca, db_hi, idesc, 1u);
           }
-          if (cl > 1) tc_commit_multicast(smem_u32(&empty[s]), cta_mask);
-          else tc_commit(smem_u32(&empty[s]));
+          tc_commit(smem_u32(&ta_empty[s]));
         }
         tc_commit(smem_u32(&acc_full[as]));
       }
     }
-  } else if (warp < 6) {
-    // ===================================================================== lo transform warps
-    const int t = threadIdx.x - 64;  // 0..127
-    for (int64_t it = 0; it < total_it; ++it) {
-      const int s = (int)(it % GM_STAGES);
-      const uint32_t ph = (uint32_t)((it / GM_STAGES) & 1);
-      mbar_wait(smem_u32(&full_raw[s]), ph);
-      const float4* raw = reinterpret_cast<const float4*>(a_base + (size_t)s * 2 * GM_A_TILE);
-      float4* lo = reinterpret_cast<float4*>(a_base + (size_t)s * 2 * GM_A_TILE + GM_A_TILE);
+  } else if (warp < 10) {
+    // ===================================================================== transform warps
+    // thread = tile row = TMEM lane (a warp may only touch its own quarter of the lanes);
+    // warps 2-5 take the even k-blocks, warps 6-9 the odd ones
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    for (int64_t it = (warp - 2) >> 2; it < total_it; it += 2) {
+      const int rs = (int)(it % GM_RAW_STAGES);
+      const uint32_t rph = (uint32_t)((it / GM_RAW_STAGES) & 1);
+      const int ts = (int)(it % GM_TM_STAGES);
+      const uint32_t tph = (uint32_t)((it / GM_TM_STAGES) & 1);
+      mbar_wait(smem_u32(&full_raw[rs]), rph);
+      const uint8_t* row = a_raw + (size_t)rs * GM_A_TILE + (size_t)r * 128;
+      uint32_t hi[32], lo[32];
 #pragma unroll
-      for (int c = 0; c < GM_A_TILE / 16 / 128; ++c) {
-        const float4 x = raw[t + 128 * c];
-        float4 l;
-        l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xffffe000u);
-        l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
-        l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xffffe000u);
-        l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
-        lo[t + 128 * c] = l;
+      for (int c = 0; c < 8; ++c) {   // 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
+        const float4 x = *reinterpret_cast<const float4*>(row + ((c ^ (r & 7)) << 4));
+        hi[4 * c + 0] = __float_as_uint(x.x);
+        hi[4 * c + 1] = __float_as_uint(x.y);
+        hi[4 * c + 2] = __float_as_uint(x.z);
+        hi[4 * c + 3] = __float_as_uint(x.w);
       }
-      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor-core (async) proxy
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        lo[j] = __float_as_uint(__uint_as_float(hi[j]) - __uint_as_float(hi[j] & 0xffffe000u));
+      // the raw stage is in registers: hand it back to every producer of the cluster
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&lo_ready[s]));
+      if (lane < cl) {
+        if (cl > 1) mbar_arrive_remote(smem_u32(&empty_raw[rs]), (uint32_t)lane);
+        else mbar_arrive(smem_u32(&empty_raw[rs]));
+      }
+      mbar_wait(smem_u32(&ta_empty[ts]), tph ^ 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + lane_addr + GM_TMEM_A0 + (uint32_t)(ts * 64);
+      tmem_st_x32(taddr, hi);
+      tmem_st_x32(taddr + 32, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ta_full[ts]));
     }
   } else {
     // ===================================================================== epilogue warps
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    uint8_t* my_stg = stg + (size_t)(warp - 10) * GM_STG_WARP;
+    const int sub_r = lane >> 2, sub_c = lane & 3;
+    const bool masked = P.act != nullptr;
+    // relu' mask words of one tile for this thread: mk[4*p + i] covers pass p (columns 16p + 4*sub_c ..),
+    // row i*8 + sub_r.  They do not depend on the MMAs, so tile t+1's are fetched while tile t is stored.
+    float4 mk[16];
+    auto fetch_mask = [&](int64_t t) {
+      const int64_t row_base = (tile_beg + t) * GM_BM + quarter * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int64_t row = row_base + i * 8 + sub_r;
+        const bool ok = t < n_tiles && row < P.m_rows;
+        const float* src = P.act + (int64_t)((uint32_t)row / (uint32_t)P.group) * P.ld_act + n0 + 4 * sub_c;
+#pragma unroll
+        for (int p = 0; p < 4; ++p)
+          mk[4 * p + i] = ok ? __ldg(reinterpret_cast<const float4*>(src + 16 * p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    if (masked) fetch_mask(0);
     for (int64_t t = 0; t < n_tiles; ++t) {
       const int as = (int)(t & 1);
       const uint32_t aph = (uint32_t)((t >> 1) & 1);
+      const int64_t row_base = (tile_beg + t) * GM_BM + quarter * 32;
+      unsigned long long keep = ~0ull;   // bit 4*(4*p + i) + e
+      if (masked) {
+        keep = 0ull;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          const unsigned long long b = (mk[q].x > 0.f ? 1ull : 0ull) | (mk[q].y > 0.f ? 2ull : 0ull) |
+                                       (mk[q].z > 0.f ? 4ull : 0ull) | (mk[q].w > 0.f ? 8ull : 0ull);
+          keep |= b << (4 * q);
+        }
+        fetch_mask(t + 1);               // in flight during this tile's TMEM drain and stores
+      }
       mbar_wait(smem_u32(&acc_full[as]), aph);
       tc_fence_after();
-      uint32_t v[64];
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * GM_BN);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[32 * h + 0]), "=r"(v[32 * h + 1]), "=r"(v[32 * h + 2]), "=r"(v[32 * h + 3]),
-              "=r"(v[32 * h + 4]), "=r"(v[32 * h + 5]), "=r"(v[32 * h + 6]), "=r"(v[32 * h + 7]),
-              "=r"(v[32 * h + 8]), "=r"(v[32 * h + 9]), "=r"(v[32 * h + 10]), "=r"(v[32 * h + 11]),
-              "=r"(v[32 * h + 12]), "=r"(v[32 * h + 13]), "=r"(v[32 * h + 14]), "=r"(v[32 * h + 15]),
-              "=r"(v[32 * h + 16]), "=r"(v[32 * h + 17]), "=r"(v[32 * h + 18]), "=r"(v[32 * h + 19]),
-              "=r"(v[32 * h + 20]), "=r"(v[32 * h + 21]), "=r"(v[32 * h + 22]), "=r"(v[32 * h + 23]),
-              "=r"(v[32 * h + 24]), "=r"(v[32 * h + 25]), "=r"(v[32 * h + 26]), "=r"(v[32 * h + 27]),
-              "=r"(v[32 * h + 28]), "=r"(v[32 * h + 29]), "=r"(v[32 * h + 30]), "=r"(v[32 * h + 31])
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
             : "r"(taddr + (uint32_t)(32 * h)));
-      }
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int q = 0; q < 4; ++q)   // pin the uses of v[] behind the wait (volatile asms keep their order)
-        asm volatile("" : "+r"(v[16 * q + 0]), "+r"(v[16 * q + 1]), "+r"(v[16 * q + 2]), "+r"(v[16 * q + 3]),
-                          "+r"(v[16 * q + 4]), "+r"(v[16 * q + 5]), "+r"(v[16 * q + 6]), "+r"(v[16 * q + 7]),
-                          "+r"(v[16 * q + 8]), "+r"(v[16 * q + 9]), "+r"(v[16 * q + 10]), "+r"(v[16 * q + 11]),
-                          "+r"(v[16 * q + 12]), "+r"(v[16 * q + 13]), "+r"(v[16 * q + 14]), "+r"(v[16 * q + 15]));
-      // the accumulator is in registers: hand the TMEM buffer back before touching global memory
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
-      const int64_t row = (tile_beg + t) * GM_BM + quarter * 32 + lane;
-      if (row < P.m_rows) {
-        float4* dst = reinterpret_cast<float4*>(P.out + row * P.ldo + n0);
-        if (P.act != nullptr) {
-          const float4* m = reinterpret_cast<const float4*>(P.act + (row / P.group) * P.ld_act + n0);
+        for (int q = 0; q < 2; ++q)   // pin the uses of v[] behind the wait (volatile asms keep their order)
+          asm volatile("" : "+r"(v[16 * q + 0]), "+r"(v[16 * q + 1]), "+r"(v[16 * q + 2]), "+r"(v[16 * q + 3]),
+                            "+r"(v[16 * q + 4]), "+r"(v[16 * q + 5]), "+r"(v[16 * q + 6]), "+r"(v[16 * q + 7]),
+                            "+r"(v[16 * q + 8]), "+r"(v[16 * q + 9]), "+r"(v[16 * q + 10]), "+r"(v[16 * q + 11]),
+                            "+r"(v[16 * q + 12]), "+r"(v[16 * q + 13]), "+r"(v[16 * q + 14]), "+r"(v[16 * q + 15]));
+        if (h == 1) {   // the whole accumulator has left TMEM: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
+        }
+        // thread = row in TMEM; global memory wants lanes along a row.  Passes of 16 columns through a
+        // padded staging tile: 128-bit stores by row (conflict-free at an 80-byte pitch), then every
+        // instruction writes 8 rows x 64 contiguous bytes.
 #pragma unroll
-          for (int j = 0; j < GM_BN / 4; ++j) {
-            const float4 a = __ldg(m + j);
-            float4 o;
-            o.x = a.x > 0.f ? __uint_as_float(v[4 * j + 0]) : 0.f;
-            o.y = a.y > 0.f ? __uint_as_float(v[4 * j + 1]) : 0.f;
-            o.z = a.z > 0.f ? __uint_as_float(v[4 * j + 2]) : 0.f;
-            o.w = a.w > 0.f ? __uint_as_float(v[4 * j + 3]) : 0.f;
-            dst[j] = o;
+        for (int pp = 0; pp < 2; ++pp) {
+          const int p = 2 * h + pp;
+          float4* mine = reinterpret_cast<float4*>(my_stg + (size_t)lane * GM_STG_PITCH);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            mine[j] = make_float4(__uint_as_float(v[16 * pp + 4 * j + 0]), __uint_as_float(v[16 * pp + 4 * j + 1]),
+                                  __uint_as_float(v[16 * pp + 4 * j + 2]), __uint_as_float(v[16 * pp + 4 * j + 3]));
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rl = i * 8 + sub_r;
+            const int64_t row = row_base + rl;
+            float4 o = *reinterpret_cast<const float4*>(my_stg + (size_t)rl * GM_STG_PITCH + sub_c * 16);
+            const unsigned kb4 = (unsigned)(keep >> (4 * (4 * p + i))) & 15u;
+            o.x = (kb4 & 1u) ? o.x : 0.f;
+            o.y = (kb4 & 2u) ? o.y : 0.f;
+            o.z = (kb4 & 4u) ? o.z : 0.f;
+            o.w = (kb4 & 8u) ? o.w : 0.f;
+            if (row < P.m_rows) *reinterpret_cast<float4*>(P.out + row * P.ldo + n0 + 16 * p + 4 * sub_c) = o;
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < GM_BN / 4; ++j)
-            dst[j] = make_float4(__uint_as_float(v[4 * j + 0]), __uint_as_float(v[4 * j + 1]),
-                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          __syncwarp();
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (cl > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into it
+  if (cl > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into it / arrive on it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(GM_TMEM_COLS)
+                 : "memory");
   }
 }
 
@@ -354,7 +449,7 @@ int lgnn_gemm_mask_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, c
   if ((rc = encode_2d(&tm_a, a, (uint64_t)k, (uint64_t)m_rows, (uint64_t)lda * 4, GM_BK, GM_BM / P.cl))) return rc;
   if ((rc = encode_2d(&tm_bhi, wt_hi, (uint64_t)k_pad, (uint64_t)n, (uint64_t)k_pad * 4, GM_BK, GM_BN))) return rc;
   if ((rc = encode_2d(&tm_blo, wt_lo, (uint64_t)k_pad, (uint64_t)n, (uint64_t)k_pad * 4, GM_BK, GM_BN))) return rc;
-  const size_t smem = 1024 + (size_t)2 * P.n_kb * GM_B_TILE + (size_t)GM_STAGES * 2 * GM_A_TILE + 256;
+  const size_t smem = 1024 + (size_t)2 * P.n_kb * GM_B_TILE + (size_t)GM_RAW_STAGES * GM_A_TILE + 4 * GM_STG_WARP + 256;
   LGNN_CUDA_TRY(cudaFuncSetAttribute(gemm_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_clusters = (P.tiles_total + GM_TILES_PER_CLUSTER - 1) / GM_TILES_PER_CLUSTER;
   cudaLaunchConfig_t cfg = {};

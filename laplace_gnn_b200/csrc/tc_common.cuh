@@ -50,6 +50,10 @@ __device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtens
       ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(cta_mask)
       : "memory");
 }
+// bring the box into L2 only (no shared memory, no barrier): latency hiding beyond the ring depth
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
