@@ -199,11 +199,29 @@ __device__ __forceinline__ int64_t row_lower_bound(const int64_t* __restrict__ r
   return lo;
 }
 
+// Rows longer than BULK_HUB_FACTOR CTA budgets ("hubs" of power-law graphs) are split at the CTA
+// budget boundaries: every CTA adds its piece of the row with red.global.add.v4.f32 onto a row that
+// spmm_zero_hub_rows_kernel cleared beforehand.  All other rows belong entirely to the CTA in whose
+// budget they start and are written with plain stores in a fixed summation order (bit-reproducible,
+// bit-equal to the warp-per-row kernel).  With a fused relu the split is off (relu needs the full sum).
+constexpr int BULK_HUB_FACTOR = 4;
+
+__global__ void spmm_zero_hub_rows_kernel(int64_t n_rows, const int64_t* __restrict__ rowptr, int64_t hub_len,
+                                          float* __restrict__ y, int64_t ldy, int d4) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_rows) return;
+  if (__ldg(rowptr + row + 1) - __ldg(rowptr + row) <= hub_len) return;
+  float4* dst = reinterpret_cast<float4*>(y + row * ldy);
+  for (int c = lane; c < d4; c += 32) dst[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 template <int VPT>  // float4 accumulators per consumer thread; column range <= VPT*256 float4
 __global__ void __launch_bounds__(BULK_THREADS, 1) spmm_bulk_kernel(
     int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     const float* __restrict__ val, const float* __restrict__ x, int64_t ldx, float* __restrict__ y,
-    int64_t ldy, int d4, int range4, int stages, int stage_bytes, int64_t nnz_per_cta, int flags) {
+    int64_t ldy, int d4, int range4, int stages, int stage_bytes, int64_t nnz_per_cta, int64_t hub_len,
+    int flags) {
   extern __shared__ uint8_t bulk_smem_[];
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bulk_smem_) + 127) & ~(uintptr_t)127);
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)stages * stage_bytes);
@@ -216,13 +234,26 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) spmm_bulk_kernel(
   const uint32_t bytes = (uint32_t)w4 * 16u;
 
   const int64_t nnz = __ldg(rowptr + n_rows);
+  const bool last_cta = blockIdx.y == gridDim.y - 1;
   const int64_t t_beg = (int64_t)blockIdx.y * nnz_per_cta;
   if (blockIdx.y > 0 && t_beg >= nnz) return;
+  const int64_t t_end = (last_cta || t_beg + nnz_per_cta >= nnz) ? nnz : t_beg + nnz_per_cta;
   const int64_t row_beg = blockIdx.y == 0 ? 0 : row_lower_bound(rowptr, n_rows, t_beg);
-  const int64_t row_end = (blockIdx.y == gridDim.y - 1 || t_beg + nnz_per_cta >= nnz)
-                              ? n_rows
-                              : row_lower_bound(rowptr, n_rows, t_beg + nnz_per_cta);
-  if (row_beg >= row_end) return;
+  const int64_t row_end = (last_cta || t_end >= nnz) ? n_rows : row_lower_bound(rowptr, n_rows, t_end);
+  // piece of a hub row that started in an earlier CTA's budget and reaches into this one
+  const int64_t main_beg = __ldg(rowptr + row_beg);
+  const bool has_prefix = blockIdx.y > 0 && row_beg > 0 && main_beg > t_beg &&
+                          (main_beg - __ldg(rowptr + row_beg - 1)) > hub_len;
+  const int64_t pre_end = main_beg < t_end ? main_beg : t_end;
+  // a hub row that starts in this budget (necessarily its last row) stops at the budget boundary
+  int64_t s_end = has_prefix ? pre_end : main_beg;
+  if (row_end > row_beg) {
+    s_end = __ldg(rowptr + row_end);
+    const int64_t last_beg = __ldg(rowptr + row_end - 1);
+    if (s_end - last_beg > hub_len && s_end > t_end) s_end = t_end;
+  }
+  const int64_t s_beg = has_prefix ? t_beg : main_beg;
+  if (row_beg >= row_end && !has_prefix) return;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < stages; ++i) {
@@ -233,21 +264,19 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) spmm_bulk_kernel(
   }
   __syncthreads();
 
-  const int64_t k_beg = __ldg(rowptr + row_beg), k_end = __ldg(rowptr + row_end);
-
   if (warp == BULK_CONSUMERS / 32) {
     // ===================================================================== producer warp
     const float* xb = x + (int64_t)c4_0 * 4;
-    for (int64_t k0 = k_beg; k0 < k_end; k0 += 32) {
+    for (int64_t k0 = s_beg; k0 < s_end; k0 += 32) {
       const int64_t k = k0 + lane;
-      const bool valid = k < k_end;
+      const bool valid = k < s_end;
       int32_t c = 0;
       float v = 0.f;
       if (valid) {
         c = __ldg(col + k);
         v = __ldg(val + k);
       }
-      const int64_t it = k - k_beg;
+      const int64_t it = k - s_beg;
       const int st = (int)(it % stages);
       const uint32_t ph = (uint32_t)((it / stages) & 1);
       // lanes whose stages coincide (stages < 32) go in successive sub-batches
@@ -269,13 +298,12 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) spmm_bulk_kernel(
 #pragma unroll
     for (int j = 0; j < VPT; ++j) act[j] = (t + j * BULK_CONSUMERS) < w4;
     int64_t it = 0;
-    int64_t k_row = k_beg;
-    for (int64_t row = row_beg; row < row_end; ++row) {
-      const int64_t k_next = __ldg(rowptr + row + 1);
+    // one segment = `cnt` consecutive ring stages accumulated into row `row`
+    auto segment = [&](int64_t row, int64_t cnt, bool atomic) {
       float4 acc[VPT];
 #pragma unroll
       for (int j = 0; j < VPT; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int64_t k = k_row; k < k_next; ++k, ++it) {
+      for (int64_t e = 0; e < cnt; ++e, ++it) {
         const int st = (int)(it % stages);
         const uint32_t ph = (uint32_t)((it / stages) & 1);
         bulk_mbar_wait(smem_addr(&full[st]), ph);
@@ -291,17 +319,31 @@ __global__ void __launch_bounds__(BULK_THREADS, 1) spmm_bulk_kernel(
         __syncwarp();
         if (lane == 0) bulk_mbar_arrive(smem_addr(&empty[st]));
       }
-      k_row = k_next;
       float4* dst = reinterpret_cast<float4*>(y + row * ldy) + c4_0 + t;
 #pragma unroll
       for (int j = 0; j < VPT; ++j) {
         if (!act[j]) continue;
         float4 a = acc[j];
+        if (atomic) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j * BULK_CONSUMERS), "f"(a.x),
+                       "f"(a.y), "f"(a.z), "f"(a.w)
+                       : "memory");
+          continue;
+        }
         if (flags & LGNN_SPMM_RELU) {
           a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
         }
         dst[j * BULK_CONSUMERS] = a;
       }
+    };
+    if (has_prefix) segment(row_beg - 1, pre_end - t_beg, true);
+    int64_t k_row = main_beg;
+    for (int64_t row = row_beg; row < row_end; ++row) {
+      const int64_t k_next = __ldg(rowptr + row + 1);
+      const bool hub = (k_next - k_row) > hub_len;
+      const int64_t k_stop = (hub && k_next > s_end) ? s_end : k_next;
+      segment(row, k_stop - k_row, hub);
+      k_row = k_next;
     }
   }
 }
@@ -324,8 +366,17 @@ static int launch_bulk(int64_t n_rows, const int64_t* rowptr, const int32_t* col
     blocks_y = (nnz_hint + per_cta - 1) / per_cta;
   }
   dim3 grid((unsigned)n_ranges, (unsigned)blocks_y);
+  int64_t hub_len = per_cta * BULK_HUB_FACTOR;
+  if (flags & LGNN_SPMM_RELU) {
+    hub_len = INT64_MAX;   // relu needs the complete row sum: no split
+  } else {
+    const int64_t zb = (n_rows * 32 + 255) / 256;
+    if (zb > 0x7fffffffLL) return fail(LGNN_E_UNSUPPORTED, "spmm: grid too large");
+    spmm_zero_hub_rows_kernel<<<(unsigned)zb, 256, 0, st>>>(n_rows, rowptr, hub_len, y, ldy, d4);
+    LGNN_LAUNCH_CHECK("spmm_zero_hub_rows_kernel");
+  }
   spmm_bulk_kernel<VPT><<<grid, BULK_THREADS, smem, st>>>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4,
-                                                         range4, stages, stage_bytes, per_cta, flags);
+                                                         range4, stages, stage_bytes, per_cta, hub_len, flags);
   LGNN_LAUNCH_CHECK("spmm_bulk_kernel");
   return LGNN_OK;
 }
@@ -350,7 +401,7 @@ extern "C" int lgnn_spmm_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr,
   const int epi = flags & LGNN_SPMM_RELU;
   // measured on B200 (profiles/): with >= 10 KB ring stages the bulk kernel sits at the HBM roofline;
   // with smaller stages its per-stage hand-off dominates and the warp-per-row kernel is faster
-  bool bulk = vec_ok && d >= 2560 && ((d / 4 + ((d / 4 + 767) / 768) - 1) / ((d / 4 + 767) / 768)) > 640;
+  bool bulk = vec_ok && d >= 2560 && ((d / 4 + ((d / 4 + 767) / 768) - 1) / ((d / 4 + 767) / 768)) >= 640;
   if (flags & LGNN_SPMM_FORCE_LDG) bulk = false;
   if (flags & LGNN_SPMM_FORCE_BULK) {
     if (!vec_ok) return fail(LGNN_E_ALIGN, "spmm: the bulk path needs 16-byte aligned x / y and d, ldx, ldy %% 4 == 0");

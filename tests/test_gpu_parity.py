@@ -142,15 +142,18 @@ def test_spmm_bulk_kernel_matches_oracle_and_ldg_kernel(d, relu):
 
 
 def test_spmm_bulk_kernel_empty_rows_hub_rows_and_leading_dimensions():
-    """Rectangular CSR with empty rows (leading, interior, trailing), one hub row longer than a CTA's
-    nnz budget, and ldx / ldy larger than d."""
+    """Rectangular CSR with empty rows (leading, interior, trailing), a row longer than one CTA's nnz
+    budget (kept whole), two hub rows long enough to be split across CTAs (added with red.global —
+    one of them starting a budget, one ending the matrix), and ldx / ldy larger than d."""
     ops = _ops()
     from laplace_gnn_b200.ops import CSR
     rng = np.random.Generator(np.random.PCG64(7))
-    n_rows, n_cols, d, ld = 300, 500, 640, 700
+    n_rows, n_cols, d, ld = 300, 500, 2560, 2600
     counts = rng.integers(0, 12, n_rows)
     counts[[0, 1, 57, 58, 298, 299]] = 0
-    counts[100] = 9000                                    # > BULK_NNZ_PER_CTA: spans several CTA budgets
+    counts[100] = 9000                                    # > BULK_NNZ_PER_CTA, below the hub threshold
+    counts[200] = 50_000                                  # hub: split over ~12 CTA budgets
+    counts[297] = 20_000                                  # hub that is the last non-empty row
     rowptr = np.zeros(n_rows + 1, np.int64)
     np.cumsum(counts, out=rowptr[1:])
     col = rng.integers(0, n_cols, rowptr[-1]).astype(np.int32)
@@ -160,12 +163,18 @@ def test_spmm_bulk_kernel_empty_rows_hub_rows_and_leading_dimensions():
             torch.from_numpy(val).to(DEV))
     import scipy.sparse as sp
     ref = sp.csr_matrix((val.astype(np.float64), col, rowptr), shape=(n_rows, n_cols)) @ x[:, :d].astype(np.float64)
-    out = torch.full((n_rows, ld), 7.0, device=DEV)
-    ops.spmm(a, torch.from_numpy(x).to(DEV), out=out, d=d, impl="bulk")
-    assert max_rel_err(out[:, :d].cpu().numpy(), ref) <= 1e-5
-    assert float((out[:, d:] - 7.0).abs().max()) == 0.0   # columns beyond d untouched
-    assert float(out[[0, 1, 57, 58, 298, 299], :d].abs().max()) == 0.0
-    assert torch.equal(out[:, :d], ops.spmm(a, torch.from_numpy(x).to(DEV), d=d, impl="ldg"))
+    xd = torch.from_numpy(x).to(DEV)
+    for impl in ("bulk", "auto"):                         # d = 2560 is a width "auto" gives to the bulk kernel
+        out = torch.full((n_rows, ld), 7.0, device=DEV)
+        ops.spmm(a, xd, out=out, d=d, impl=impl)
+        assert max_rel_err(out[:, :d].cpu().numpy(), ref) <= 1e-5
+        assert float((out[:, d:] - 7.0).abs().max()) == 0.0   # columns beyond d untouched
+        assert float(out[[0, 1, 57, 58, 298, 299], :d].abs().max()) == 0.0
+        whole = np.setdiff1d(np.arange(n_rows), [200, 297])   # rows written with plain stores: bit-equal
+        ldg = ops.spmm(a, xd, d=d, impl="ldg")
+        assert torch.equal(out[whole, :d], ldg[whole])
+    relu = ops.spmm(a, xd, d=d, relu=True, impl="bulk")   # fused relu: hub rows are not split
+    assert max_rel_err(relu.cpu().numpy(), np.maximum(ref, 0)) <= 1e-5
 
 
 def test_spmm_strided_and_unaligned_operands():

@@ -2,5 +2,4 @@
 set -u
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -q > gpurun_out/t1.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/t1.log | cut -c1-300
-timeout 300 python tools/gemm_lab.py 2>&1 | tee gpurun_out/gemm_lab.log
-timeout 600 python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/b1_fused.log 2>gpurun_out/b1_fused.err; echo "fused rc=$?"; tail -c 700 gpurun_out/b1_fused.log; tail -3 gpurun_out/b1_fused.err
+timeout 900 python tools/rmat_sweep.py 2>&1 | tee gpurun_out/rmat_sweep.log
