@@ -13,6 +13,7 @@ from .gcn import GCNConvFunction, SparseGCN, SparseGCNConv  # noqa: F401
 from .curvature import B200GGN, make_backend  # noqa: F401
 from .data import TensorBatchLoader  # noqa: F401
 from .kron import DiagLaplace, Kron, KronDecomposed, KronLaplace, Laplace  # noqa: F401
+from .training import MarglikTrainingResult, marglik_training  # noqa: F401
 
 __all__ = ["Graph", "SparseGCN", "SparseGCNConv", "GCNConvFunction", "B200GGN", "make_backend",
-           "TensorBatchLoader", "Laplace", "KronLaplace", "DiagLaplace", "Kron", "KronDecomposed", "ops"]
+           "TensorBatchLoader", "marglik_training", "MarglikTrainingResult", "Laplace", "KronLaplace", "DiagLaplace", "Kron", "KronDecomposed", "ops"]

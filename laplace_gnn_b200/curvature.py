@@ -114,7 +114,7 @@ class _B200KFAC:
 
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
-                    fused_gemm=True):
+                    fused_gemm=True, cache_input_factor=False, _shared_cache=None):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if backward_parallel not in ("rows", "columns"):
@@ -136,6 +136,11 @@ class _B200KFAC:
         self.backward_parallel = backward_parallel
         self.overlap = bool(overlap)
         self.fused_gemm = bool(fused_gemm)
+        # A_0 = X^T X does not depend on the weights: with cache_input_factor the raw Gram matrix of
+        # this rank's feature rows is kept (per backend, or in a dict shared across backends by the
+        # epoch loop) and only rescaled per call
+        self.cache_input_factor = bool(cache_input_factor)
+        self._cache = _shared_cache if _shared_cache is not None else {}
         self.n_outputs = self.model.out_channels
         self.last_stats: dict[str, Any] = {}
 
@@ -326,7 +331,14 @@ class _B200KFAC:
         # (curvlinops.py:46-53); with a partition: this rank's rows, summed by the all-reduce below
         A = []
         for l in range(L):
-            a = ops.syrk(Hs[l], alpha=1.0 / M, impl=self._impl(Hs[l].shape[1]))
+            if l == 0 and self.cache_input_factor:
+                key = ("xtx", Hs[0].data_ptr(), tuple(Hs[0].shape), Hs[0]._version)
+                if key not in self._cache:
+                    self._cache.clear()
+                    self._cache[key] = ops.syrk(Hs[0], impl=self._impl(Hs[0].shape[1]))
+                a = self._cache[key] * (1.0 / M)
+            else:
+                a = ops.syrk(Hs[l], alpha=1.0 / M, impl=self._impl(Hs[l].shape[1]))
             a *= M / N
             A.append(a)
 
@@ -393,7 +405,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  dict_key_x="input_ids", dict_key_y="labels", stochastic=False,
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
-                 fused_gemm=True):
+                 fused_gemm=True, cache_input_factor=False, _shared_cache=None):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -403,7 +415,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                           dict_key_y, stochastic)
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
-                         backward_parallel, overlap, fused_gemm)
+                         backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

@@ -197,3 +197,30 @@ print('DROPIN_OK')
 """ % (ROOT, ROOT)
     out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, timeout=600)
     assert "DROPIN_OK" in out.stdout, out.stderr[-3000:]
+
+
+def test_marglik_training_epoch_loop(fake_ops):
+    """the reference's per-epoch train step + fit + marglik + validation forward
+    (gnn/marglik_training.py:159-329) on the sparse model; A_0 is cached across epochs."""
+    import laplace_gnn_b200 as L
+    g = Golden("tiny_undirected_2l")
+    model = build_model(g)
+    idx, y = torch.from_numpy(g.idx), torch.from_numpy(g.y)
+    rest = np.setdiff1d(np.arange(g.n), g.idx)
+    val_idx = torch.from_numpy(rest[: max(2, len(rest) // 2)])
+    val_y = torch.randint(0, g.C, (val_idx.numel(),), generator=torch.Generator().manual_seed(1))
+    res = L.marglik_training(model, idx, y, val_idx, val_y, n_epochs=6, lr=0.05, weight_decay=0.0,
+                             patience=2, early_stop=False)
+    assert len(res.neg_margliks) == len(res.losses) == len(res.val_losses) == 6
+    assert all(np.isfinite(res.neg_margliks)) and res.losses[-1] < res.losses[0]     # Adam makes progress
+    assert 1 <= res.best_marglik_epoch <= 6 and res.best_marglik_state is not None
+    # the cached input factor gives the same factors as a fresh backend
+    la_c = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs={"cache_input_factor": True})
+    la_c.fit(loader_for(g)); la_c.fit(loader_for(g))
+    la_f = L.Laplace(model, "classification", backend=L.B200GGN)
+    la_f.fit(loader_for(g))
+    for fa, fb in zip(la_c.H_facs.kfacs, la_f.H_facs.kfacs):
+        for a, b in zip(fa, fb):
+            assert max_rel_err(a.numpy(), b.numpy()) <= 1e-6
+    stopped = L.marglik_training(model, idx, y, val_idx, val_y, n_epochs=50, lr=0.0, patience=2, early_stop=True)
+    assert stopped.stopped_epoch < 50                                               # lr = 0: no improvement, patience ends it
