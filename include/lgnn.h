@@ -45,7 +45,9 @@ enum {
   LGNN_SPMM_NONE = 0,
   LGNN_SPMM_RELU = 1,       /* y = max(y, 0) fused into the store */
   LGNN_SPMM_FORCE_LDG = 2,  /* kernel selection override (tests / profiling): warp-per-row LDG.128 kernel */
-  LGNN_SPMM_FORCE_BULK = 4  /* kernel selection override: bulk-async (TMA 1-D copy) shared-memory ring kernel */
+  LGNN_SPMM_FORCE_BULK = 4, /* kernel selection override: bulk-async (TMA 1-D copy) shared-memory ring kernel */
+  LGNN_SPMM_NO_HUB_ROWS = 8 /* caller guarantees that no row has more than 4096 non-zeros: the passes that
+                               split hub rows of power-law graphs across warps / CTAs are skipped */
 };
 
 /* SYRK implementation selector */

@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_HERE, "liblgnn.so")
 
 OK = 0
 HESS_REFERENCE, HESS_GGN = 0, 1
-SPMM_NONE, SPMM_RELU, SPMM_FORCE_LDG, SPMM_FORCE_BULK = 0, 1, 2, 4
+SPMM_NONE, SPMM_RELU, SPMM_FORCE_LDG, SPMM_FORCE_BULK, SPMM_NO_HUB_ROWS = 0, 1, 2, 4, 8
 SYRK_AUTO, SYRK_SIMT, SYRK_TCGEN05 = 0, 1, 2
 
 _i64, _i32, _f32, _vp, _sz = C.c_int64, C.c_int32, C.c_float, C.c_void_p, C.c_size_t

@@ -16,6 +16,9 @@ namespace lgnn {
 
 constexpr int SPMM_THREADS = 256;
 
+__global__ void spmm_zero_hub_rows_kernel(int64_t n_rows, const int64_t* __restrict__ rowptr, int64_t hub_len,
+                                          float* __restrict__ y, int64_t ldy, int d4);
+
 __device__ __forceinline__ float4 ldg_f4(const float* p) {
   return __ldg(reinterpret_cast<const float4*>(p));
 }
@@ -27,29 +30,12 @@ __device__ __forceinline__ void fma4(float4& a, float v, const float4& x) {
   a.w = fmaf(v, x.w, a.w);
 }
 
-// VEC float4 per lane per chunk (chunk = VEC*128 floats); d4 = d/4.
+// acc[t] += sum_{k in [beg, end)} val[k] * X[col[k], chunk columns]  — the warp-wide gather loop shared by
+// the row kernel and the hub-segment kernel.
 template <int VEC, int UNROLL>
-__global__ void __launch_bounds__(SPMM_THREADS, 2) spmm_vec_kernel(
-    int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
-    const float* __restrict__ val, const float* __restrict__ x, int64_t ldx, float* __restrict__ y,
-    int64_t ldy, int d4, int n_chunks, int flags) {
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * SPMM_THREADS + threadIdx.x) >> 5;
-  const int64_t row = warp / n_chunks;
-  if (row >= n_rows) return;
-  const int chunk = (int)(warp - row * n_chunks);
-  const int c4 = chunk * (VEC * 32) + lane;  // first float4 column of this lane
-
-  bool act[VEC];
-#pragma unroll
-  for (int t = 0; t < VEC; ++t) act[t] = (c4 + 32 * t) < d4;
-
-  float4 acc[VEC];
-#pragma unroll
-  for (int t = 0; t < VEC; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  const float* xb = x + (int64_t)c4 * 4;
-  const int64_t beg = rowptr[row], end = rowptr[row + 1];
+__device__ __forceinline__ void gather_range(int64_t beg, int64_t end, const int32_t* __restrict__ col,
+                                             const float* __restrict__ val, const float* __restrict__ xb,
+                                             int64_t ldx, const bool (&act)[VEC], float4 (&acc)[VEC], int lane) {
   for (int64_t k0 = beg; k0 < end; k0 += 32) {
     int cnt = (int)((end - k0) < 32 ? (end - k0) : 32);
     int32_t my_c = 0;
@@ -86,6 +72,38 @@ __global__ void __launch_bounds__(SPMM_THREADS, 2) spmm_vec_kernel(
         if (act[t]) fma4(acc[t], v, ldg_f4(src + 128 * t));
     }
   }
+}
+
+// Rows longer than LDG_HUB_LEN non-zeros are left to spmm_hub_kernel: one warp walking a 100 k-entry
+// hub row of a power-law graph is a 10 ms tail (measured 29-54 % of the HBM roofline on R-MAT).
+constexpr int64_t LDG_HUB_LEN = 4096;
+constexpr int LDG_HUB_SEG = 2048;   // non-zeros per block of the hub kernel (8 warps x 256)
+
+// VEC float4 per lane per chunk (chunk = VEC*128 floats); d4 = d/4.
+template <int VEC, int UNROLL>
+__global__ void __launch_bounds__(SPMM_THREADS, 2) spmm_vec_kernel(
+    int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+    const float* __restrict__ val, const float* __restrict__ x, int64_t ldx, float* __restrict__ y,
+    int64_t ldy, int d4, int n_chunks, int64_t hub_len, int flags) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * SPMM_THREADS + threadIdx.x) >> 5;
+  const int64_t row = warp / n_chunks;
+  if (row >= n_rows) return;
+  const int chunk = (int)(warp - row * n_chunks);
+  const int c4 = chunk * (VEC * 32) + lane;  // first float4 column of this lane
+
+  bool act[VEC];
+#pragma unroll
+  for (int t = 0; t < VEC; ++t) act[t] = (c4 + 32 * t) < d4;
+
+  float4 acc[VEC];
+#pragma unroll
+  for (int t = 0; t < VEC; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const float* xb = x + (int64_t)c4 * 4;
+  const int64_t beg = rowptr[row], end = rowptr[row + 1];
+  if (end - beg > hub_len) return;   // hub row: spmm_hub_kernel adds it up in segments
+  gather_range<VEC, UNROLL>(beg, end, col, val, xb, ldx, act, acc, lane);
   float* yb = y + row * ldy + (int64_t)c4 * 4;
 #pragma unroll
   for (int t = 0; t < VEC; ++t) {
@@ -95,6 +113,72 @@ __global__ void __launch_bounds__(SPMM_THREADS, 2) spmm_vec_kernel(
       a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
     }
     *reinterpret_cast<float4*>(yb + 128 * t) = a;
+  }
+}
+
+// Hub rows of the warp-per-row path.  Block b owns the non-zeros [b*SEG, (b+1)*SEG); for every hub row
+// intersecting that range its 8 warps split the intersection evenly and add their partial sums onto
+// the row (cleared beforehand by spmm_zero_hub_rows_kernel) with red.global.add.v4.f32.  Blocks
+// whose range touches no hub row — all of them on a uniform graph — leave after one ballot.
+template <int VEC, int UNROLL>
+__global__ void __launch_bounds__(SPMM_THREADS, 2) spmm_hub_kernel(
+    int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+    const float* __restrict__ val, const float* __restrict__ x, int64_t ldx, float* __restrict__ y,
+    int64_t ldy, int d4) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t nnz = __ldg(rowptr + n_rows);
+  const int64_t t_beg = (int64_t)blockIdx.x * LDG_HUB_SEG;
+  if (t_beg >= nnz) return;
+  const int64_t t_end = (t_beg + LDG_HUB_SEG < nnz) ? t_beg + LDG_HUB_SEG : nnz;
+  // last row whose first non-zero is at or before t_beg
+  int64_t lo = 0, hi = n_rows;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (__ldg(rowptr + mid) <= t_beg) lo = mid + 1; else hi = mid;
+  }
+  const int c4 = blockIdx.y * (VEC * 32) + lane;
+  bool act[VEC];
+#pragma unroll
+  for (int t = 0; t < VEC; ++t) act[t] = (c4 + 32 * t) < d4;
+  const float* xb = x + (int64_t)c4 * 4;
+  for (int64_t row = lo - 1; row < n_rows; ++row) {
+    const int64_t r_beg = __ldg(rowptr + row);
+    if (r_beg >= t_end) break;
+    const int64_t r_end = __ldg(rowptr + row + 1);
+    if (r_end - r_beg <= LDG_HUB_LEN) continue;
+    const int64_t s_beg = r_beg > t_beg ? r_beg : t_beg;
+    const int64_t s_end = r_end < t_end ? r_end : t_end;
+    const int64_t per_warp = (s_end - s_beg + SPMM_THREADS / 32 - 1) / (SPMM_THREADS / 32);
+    const int64_t my_beg = s_beg + w * per_warp;
+    int64_t my_end = my_beg + per_warp;
+    if (my_end > s_end) my_end = s_end;
+    if (my_beg >= my_end) continue;
+    float4 acc[VEC];
+#pragma unroll
+    for (int t = 0; t < VEC; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    gather_range<VEC, UNROLL>(my_beg, my_end, col, val, xb, ldx, act, acc, lane);
+    float* yb = y + row * ldy + (int64_t)c4 * 4;
+#pragma unroll
+    for (int t = 0; t < VEC; ++t)
+      if (act[t])
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yb + 128 * t), "f"(acc[t].x),
+                     "f"(acc[t].y), "f"(acc[t].z), "f"(acc[t].w)
+                     : "memory");
+  }
+}
+
+// y[row, :] = max(y[row, :], 0) for hub rows (their relu cannot be fused: the sum arrives in pieces)
+__global__ void spmm_relu_hub_rows_kernel(int64_t n_rows, const int64_t* __restrict__ rowptr, int64_t hub_len,
+                                          float* __restrict__ y, int64_t ldy, int d4) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n_rows) return;
+  if (__ldg(rowptr + row + 1) - __ldg(rowptr + row) <= hub_len) return;
+  float4* dst = reinterpret_cast<float4*>(y + row * ldy);
+  for (int c = lane; c < d4; c += 32) {
+    float4 a = dst[c];
+    a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+    dst[c] = a;
   }
 }
 
@@ -367,8 +451,8 @@ static int launch_bulk(int64_t n_rows, const int64_t* rowptr, const int32_t* col
   }
   dim3 grid((unsigned)n_ranges, (unsigned)blocks_y);
   int64_t hub_len = per_cta * BULK_HUB_FACTOR;
-  if (flags & LGNN_SPMM_RELU) {
-    hub_len = INT64_MAX;   // relu needs the complete row sum: no split
+  if (flags & (LGNN_SPMM_RELU | LGNN_SPMM_NO_HUB_ROWS)) {
+    hub_len = INT64_MAX;   // relu needs the complete row sum / the caller vouches for short rows: no split
   } else {
     const int64_t zb = (n_rows * 32 + 255) / 256;
     if (zb > 0x7fffffffLL) return fail(LGNN_E_UNSUPPORTED, "spmm: grid too large");
@@ -413,28 +497,48 @@ extern "C" int lgnn_spmm_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr,
     const int range4 = (d4 + n_ranges - 1) / n_ranges;
     const int vpt = (range4 + BULK_CONSUMERS - 1) / BULK_CONSUMERS;
     switch (vpt) {
-      case 1: return launch_bulk<1>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_ranges, range4, nnz, epi, st);
-      case 2: return launch_bulk<2>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_ranges, range4, nnz, epi, st);
-      default: return launch_bulk<3>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_ranges, range4, nnz, epi, st);
+      case 1: return launch_bulk<1>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_ranges, range4, nnz, epi | (flags & LGNN_SPMM_NO_HUB_ROWS), st);
+      case 2: return launch_bulk<2>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_ranges, range4, nnz, epi | (flags & LGNN_SPMM_NO_HUB_ROWS), st);
+      default: return launch_bulk<3>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_ranges, range4, nnz, epi | (flags & LGNN_SPMM_NO_HUB_ROWS), st);
     }
   }
   if (vec_ok) {
     int d4 = (int)(d / 4);
+    const int64_t zb = (n_rows * 32 + 255) / 256;                      // one warp per row
+    // hub kernel: one block per 2048 non-zeros; skipped when the caller vouches for short rows
+    const int64_t hub_blocks = (flags & LGNN_SPMM_NO_HUB_ROWS) ? 0 : (nnz + LDG_HUB_SEG - 1) / LDG_HUB_SEG;
+    const int64_t hub_len = hub_blocks > 0 ? LDG_HUB_LEN : INT64_MAX;
+    if (zb > 0x7fffffffLL || hub_blocks > 0x7fffffffLL) return fail(LGNN_E_UNSUPPORTED, "spmm: grid too large");
+    if (hub_blocks > 0) {
+      spmm_zero_hub_rows_kernel<<<(unsigned)zb, 256, 0, st>>>(n_rows, rowptr, LDG_HUB_LEN, y, ldy, d4);
+      LGNN_LAUNCH_CHECK("spmm_zero_hub_rows_kernel");
+    }
     if (d4 <= 32) {
       int64_t warps = n_rows;
       spmm_vec_kernel<1, 8><<<(unsigned)((warps + warps_per_block - 1) / warps_per_block), SPMM_THREADS, 0, st>>>(
-          n_rows, rowptr, col, val, x, ldx, y, ldy, d4, 1, epi);
+          n_rows, rowptr, col, val, x, ldx, y, ldy, d4, 1, hub_len, epi);
+      if (hub_blocks > 0)
+        spmm_hub_kernel<1, 8><<<dim3((unsigned)hub_blocks, 1), SPMM_THREADS, 0, st>>>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4);
     } else if (d4 <= 64) {
       int64_t warps = n_rows;
       spmm_vec_kernel<2, 4><<<(unsigned)((warps + warps_per_block - 1) / warps_per_block), SPMM_THREADS, 0, st>>>(
-          n_rows, rowptr, col, val, x, ldx, y, ldy, d4, 1, epi);
+          n_rows, rowptr, col, val, x, ldx, y, ldy, d4, 1, hub_len, epi);
+      if (hub_blocks > 0)
+        spmm_hub_kernel<2, 4><<<dim3((unsigned)hub_blocks, 1), SPMM_THREADS, 0, st>>>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4);
     } else {
       int n_chunks = (d4 + 127) / 128;
       int64_t warps = n_rows * n_chunks;
       int64_t blocks = (warps + warps_per_block - 1) / warps_per_block;
       if (blocks > 0x7fffffffLL) return fail(LGNN_E_UNSUPPORTED, "spmm: grid too large");
+      if (n_chunks > 65535) return fail(LGNN_E_UNSUPPORTED, "spmm: d too large");
       spmm_vec_kernel<4, 2><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(
-          n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_chunks, epi);
+          n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_chunks, hub_len, epi);
+      if (hub_blocks > 0)
+        spmm_hub_kernel<4, 2><<<dim3((unsigned)hub_blocks, (unsigned)n_chunks), SPMM_THREADS, 0, st>>>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4);
+    }
+    if (hub_blocks > 0 && epi) {
+      spmm_relu_hub_rows_kernel<<<(unsigned)zb, 256, 0, st>>>(n_rows, rowptr, LDG_HUB_LEN, y, ldy, d4);
+      LGNN_LAUNCH_CHECK("spmm_relu_hub_rows_kernel");
     }
     LGNN_LAUNCH_CHECK("spmm_vec_kernel");
   } else {

@@ -51,6 +51,10 @@ class Graph:
         else:
             at = ops.csr_transpose(a)                                         # pattern of A^T == Â
             at.val = ops.edge_values(at, dis)
+        # longest rows (one host read at graph build): SpMM skips its hub-row passes on graphs without hubs
+        a.max_row_nnz = int(deg.max()) if num_nodes > 0 else 0
+        if at is not a:
+            at.max_row_nnz = int((at.rowptr[1:] - at.rowptr[:-1]).max()) if num_nodes > 0 else 0
         return cls(int(num_nodes), deg, dis, at, a, symmetric or assume_undirected)
 
     def partition_bounds(self, nparts: int) -> torch.Tensor:

@@ -21,6 +21,7 @@ class CSR:
     rowptr: torch.Tensor
     col: torch.Tensor
     val: torch.Tensor | None = None
+    max_row_nnz: int | None = None     # longest row, if known (graph build): lets SpMM skip its hub passes
 
     @property
     def nnz(self) -> int:
@@ -164,7 +165,7 @@ def csr_slice_remap(a: CSR, lo: int, hi: int, bounds: torch.Tensor, pad: int) ->
                                    pad, ptr(out_rowptr), ptr(out_col), ptr(out_val), stream()),
           "lgnn_csr_slice_remap")
     _lib.count_launches(1)
-    return CSR(hi - lo, nparts * pad, out_rowptr, out_col, out_val)
+    return CSR(hi - lo, nparts * pad, out_rowptr, out_col, out_val, a.max_row_nnz)   # rows are kept whole
 
 
 # ------------------------------------------------------------------------------ SpMM
@@ -187,7 +188,8 @@ def spmm(a: CSR, x: torch.Tensor, relu: bool = False, out: torch.Tensor | None =
     with _Timed("spmm", d, spmm_algorithmic_bytes(a.n_rows, a.nnz, d)):
         check(lib.lgnn_spmm_f32(a.n_rows, a.nnz, ptr(a.rowptr), ptr(a.col), ptr(a.val), ptr(x), x.stride(0),
                                 ptr(out), out.stride(0), d,
-                                (_lib.SPMM_RELU if relu else _lib.SPMM_NONE) | _SPMM_IMPL[impl],
+                                (_lib.SPMM_RELU if relu else _lib.SPMM_NONE) | _SPMM_IMPL[impl] |
+                                (_lib.SPMM_NO_HUB_ROWS if a.max_row_nnz is not None and a.max_row_nnz <= 4096 else 0),
                                 stream()), "lgnn_spmm_f32")
     _lib.count_launches(1)
     return out

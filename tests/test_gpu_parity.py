@@ -170,11 +170,38 @@ def test_spmm_bulk_kernel_empty_rows_hub_rows_and_leading_dimensions():
         assert max_rel_err(out[:, :d].cpu().numpy(), ref) <= 1e-5
         assert float((out[:, d:] - 7.0).abs().max()) == 0.0   # columns beyond d untouched
         assert float(out[[0, 1, 57, 58, 298, 299], :d].abs().max()) == 0.0
-        whole = np.setdiff1d(np.arange(n_rows), [200, 297])   # rows written with plain stores: bit-equal
+        whole = np.setdiff1d(np.arange(n_rows), [100, 200, 297])   # rows neither kernel splits: bit-equal
         ldg = ops.spmm(a, xd, d=d, impl="ldg")
         assert torch.equal(out[whole, :d], ldg[whole])
     relu = ops.spmm(a, xd, d=d, relu=True, impl="bulk")   # fused relu: hub rows are not split
     assert max_rel_err(relu.cpu().numpy(), np.maximum(ref, 0)) <= 1e-5
+
+
+@pytest.mark.parametrize("d", [16, 64, 256, 1024, 2256])
+@pytest.mark.parametrize("relu", [False, True])
+def test_spmm_hub_rows_of_power_law_graphs(d, relu):
+    """A star on top of a random graph: rows of 30 k and 9 k non-zeros are split into 2048-entry
+    segments (warp-per-row path) and summed with red.global; relu is applied after the full sum."""
+    ops = _ops()
+    n = 40_000
+    rng = np.random.Generator(np.random.PCG64(d))
+    base = O.synthetic_edges(n, 60_000, seed=d)
+    star0 = np.stack([np.zeros(30_000, np.int64), rng.permutation(n)[:30_000]])
+    star1 = np.stack([np.full(9_000, 17, np.int64), rng.permutation(n)[:9_000]])
+    stars = np.concatenate([star0, star1], axis=1)
+    ei = np.concatenate([base, stars, stars[::-1]], axis=1)
+    G, R = _dev_graph(ei, n), O.build_graph(ei, n)
+    assert int(np.diff(R.rowptr).max()) > 30_000
+    x = rng.standard_normal((n, d)).astype(np.float32)
+    xd = torch.from_numpy(x).to(DEV)
+    ref = O.spmm(R, x, dtype=torch.float64)
+    if relu:
+        ref = torch.relu(ref)
+    y = ops.spmm(G.ahat, xd, relu=relu, impl="ldg")
+    assert max_rel_err(y.cpu().numpy(), ref.numpy()) <= 1e-5
+    # rows below the hub threshold are bit-reproducible
+    small = torch.from_numpy(np.flatnonzero(np.diff(R.rowptr) <= 4096)).to(DEV)
+    assert torch.equal(y[small], ops.spmm(G.ahat, xd, relu=relu, impl="ldg")[small])
 
 
 def test_spmm_strided_and_unaligned_operands():
