@@ -158,6 +158,13 @@ int lgnn_hess_rhs_f32(const float* logits, int64_t ld, int32_t C, const int64_t*
                       int32_t c0, int32_t ncols, int32_t ldc, int mode, float* delta,
                       lgnn_stream_t stream);
 
+/* out[k] = keep[col[k]] ? val[k] : 0 for the nnz entries of a CSR.  The right-hand sides injected at
+ * the logits are zero outside the batch's train nodes (curvlinops/kfac.py:653-661 back-propagates
+ * through model(X)[idx]); with the edges into those rows zeroed, the output-layer SpMM of the KFAC
+ * backward skips their gathers (a zero edge value costs no load in lgnn_spmm_f32's row kernel). */
+int lgnn_mask_edge_values(int64_t nnz, const int32_t* col, const float* val, const uint8_t* keep,
+                          float* out, lgnn_stream_t stream);
+
 /* out[r, j] = in[r, j] * (act[(r / group), j] > 0)   (relu' mask of the layer below;
  * autograd of base_gnn.py:150 inside kfac.py:653-661).  in/out: [n_rows*group, d], act: [n_rows, d]. */
 int lgnn_relu_mask_mul_f32(const float* in, int64_t ldi, const float* act, int64_t lda, float* out,

@@ -39,6 +39,7 @@ PROTOTYPES = {
     "lgnn_spmm_f32": (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, C.c_int, _vp]),
     "lgnn_softmax_ce_sum": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
     "lgnn_hess_rhs_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, C.c_int, _vp, _vp]),
+    "lgnn_mask_edge_values": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "lgnn_relu_mask_mul_f32": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i64, _vp]),
     "lgnn_gemm_mask_supported": (C.c_int, [_i64, _i64]),
     "lgnn_gemm_mask_kpad": (_i64, [_i64]),

@@ -140,6 +140,15 @@ __global__ void __launch_bounds__(HESS_THREADS) relu_mask_mul_kernel(
   }
 }
 
+// out[k] = keep[col[k]] ? val[k] : 0
+__global__ void __launch_bounds__(HESS_THREADS) mask_edge_values_kernel(
+    int64_t nnz, const int32_t* __restrict__ col, const float* __restrict__ val,
+    const uint8_t* __restrict__ keep, float* __restrict__ out) {
+  int64_t k = (int64_t)blockIdx.x * HESS_THREADS + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * HESS_THREADS;
+  for (; k < nnz; k += stride) out[k] = keep[__ldg(col + k)] ? __ldg(val + k) : 0.f;
+}
+
 }  // namespace lgnn
 
 using namespace lgnn;
@@ -179,6 +188,18 @@ int lgnn_hess_rhs_f32(const float* logits, int64_t ld, int32_t C, const int64_t*
   hess_rhs_kernel<<<(unsigned)blocks, HESS_THREADS, smem, as_stream(stream)>>>(
       logits, ld, C, idx, m, c0, ncols, ldc, mode, delta);
   LGNN_LAUNCH_CHECK("hess_rhs_kernel");
+  return LGNN_OK;
+}
+
+int lgnn_mask_edge_values(int64_t nnz, const int32_t* col, const float* val, const uint8_t* keep,
+                          float* out, lgnn_stream_t stream) {
+  if (nnz < 0 || (nnz > 0 && (!col || !val || !keep || !out))) return fail(LGNN_E_BADARG, "mask_edge_values: bad argument");
+  if (nnz == 0) return LGNN_OK;
+  int64_t blocks = (nnz + HESS_THREADS - 1) / HESS_THREADS;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  mask_edge_values_kernel<<<(unsigned)blocks, HESS_THREADS, 0, as_stream(stream)>>>(nnz, col, val, keep, out);
+  LGNN_LAUNCH_CHECK("mask_edge_values_kernel");
   return LGNN_OK;
 }
 

@@ -53,9 +53,11 @@ __device__ __forceinline__ void gather_range(int64_t beg, int64_t end, const int
         int32_t c = __shfl_sync(0xffffffffu, my_c, j + u);
         vv[u] = __shfl_sync(0xffffffffu, my_v, j + u);
         const float* src = xb + (int64_t)c * ldx;
+        // an explicit zero (lgnn_mask_edge_values: source row known to be all zero) costs no gather;
+        // (c, v) are warp-uniform, so is the branch
 #pragma unroll
         for (int t = 0; t < VEC; ++t)
-          if (act[t]) buf[u][t] = ldg_f4(src + 128 * t);
+          if (act[t]) buf[u][t] = vv[u] != 0.f ? ldg_f4(src + 128 * t) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < UNROLL; ++u)
@@ -67,9 +69,11 @@ __device__ __forceinline__ void gather_range(int64_t beg, int64_t end, const int
       int32_t c = __shfl_sync(0xffffffffu, my_c, j);
       float v = __shfl_sync(0xffffffffu, my_v, j);
       const float* src = xb + (int64_t)c * ldx;
+      if (v != 0.f) {
 #pragma unroll
-      for (int t = 0; t < VEC; ++t)
-        if (act[t]) fma4(acc[t], v, ldg_f4(src + 128 * t));
+        for (int t = 0; t < VEC; ++t)
+          if (act[t]) fma4(acc[t], v, ldg_f4(src + 128 * t));
+      }
     }
   }
 }

@@ -82,6 +82,7 @@ class _Whole:
         self.n_local = self.total_rows = graph.n
         self.slot0 = 0
         self.communicates = False
+        self.csr_t_top = None        # Â^T with the edges from non-train rows zeroed (set per kron call)
 
     def gather(self, slab):
         pass
@@ -98,6 +99,7 @@ class _Rows:
         self.csr_t = part.ahat_t
         self.n_local, self.total_rows, self.slot0 = part.n_local, part.total_rows, part.slot0
         self.communicates = True
+        self.csr_t_top = None
 
     def gather(self, slab):
         self.part.all_gather_slab(slab)
@@ -136,6 +138,7 @@ class _B200KFAC:
         self.backward_parallel = backward_parallel
         self.overlap = bool(overlap)
         self.fused_gemm = bool(fused_gemm)
+        self.skip_zero_rows = True
         # A_0 = X^T X does not depend on the weights: with cache_input_factor the raw Gram matrix of
         # this rank's feature rows is kept (per backend, or in a dict shared across backends by the
         # epoch loop) and only rescaled per call
@@ -229,7 +232,8 @@ class _B200KFAC:
             with ops.timed("allgather", gc * ld, 4.0 * n_in * gc * ld):
                 lay.gather(slab)
             gz = buf_b[: n_loc * gc * ld].view(n_loc, gc * ld)
-            ops.spmm(lay.csr_t, slab, out=gz)
+            # output layer: the slab is zero outside the batch's train rows -> no gather for those edges
+            ops.spmm(lay.csr_t_top if (l == L - 1 and lay.csr_t_top is not None) else lay.csr_t, slab, out=gz)
             gz_rows = gz.view(n_loc * gc, ld)
             ops.syrk(gz_rows, n=width, alpha=1.0, beta=1.0, out=G[l], impl=self._impl(width))
             if l > 0:
@@ -344,8 +348,13 @@ class _B200KFAC:
 
         # output-side factors G_l: multi-RHS backward in groups of Hessian-sqrt columns
         G = [torch.zeros(w.shape[0], w.shape[0], dtype=torch.float32, device=dev) for w in Ws]
+        whole = _Whole(g)
+        if self.skip_zero_rows and (part is None or self.backward_parallel == "columns") and M < g.n:
+            keep = torch.zeros(g.n, dtype=torch.uint8, device=dev)
+            keep[idx] = 1
+            whole.csr_t_top = ops.csr_with_masked_sources(g.ahat_t, keep)
         if part is None:
-            grp, n_groups = self._backward_columns(_Whole(g), logits, idx, Hs, Ws, (0, C), G)
+            grp, n_groups = self._backward_columns(whole, logits, idx, Hs, Ws, (0, C), G)
         elif self.backward_parallel == "rows":
             grp, n_groups = self._backward_columns(_Rows(part), logits, idx_loc, Hs, Ws, (0, C), G)
         else:                                                  # "columns": full graph, own columns
@@ -362,7 +371,7 @@ class _B200KFAC:
                     full_logits = full
                 else:
                     full_H.append(full)
-            grp, n_groups = self._backward_columns(_Whole(g), full_logits, idx, full_H, Ws,
+            grp, n_groups = self._backward_columns(whole, full_logits, idx, full_H, Ws,
                                                    column_share(C, part.rank, part.world), G)
         if part is not None:
             with ops.timed("allreduce", 0, 4.0 * sum(t.numel() for t in G + A)):

@@ -229,6 +229,19 @@ def hess_rhs(logits: torch.Tensor, idx: torch.Tensor, c0: int, ncols: int, delta
     return delta
 
 
+def csr_with_masked_sources(a: CSR, keep: torch.Tensor) -> CSR:
+    """Same pattern, edge values zeroed where the source row (column index) is not flagged in
+    ``keep`` (uint8 [n_cols]): SpMM then skips the gathers of rows known to be all zero."""
+    lib = _lib.load()
+    if keep.dtype != torch.uint8 or keep.numel() < a.n_cols:
+        raise TypeError("keep must be a uint8 tensor with one flag per column")
+    val = torch.empty_like(a.val)
+    check(lib.lgnn_mask_edge_values(a.nnz, ptr(a.col), ptr(a.val), ptr(keep), ptr(val), stream()),
+          "lgnn_mask_edge_values")
+    _lib.count_launches(1)
+    return CSR(a.n_rows, a.n_cols, a.rowptr, a.col, val, a.max_row_nnz)
+
+
 def relu_mask_mul(inp: torch.Tensor, act: torch.Tensor, group: int, out: torch.Tensor | None = None,
                   d: int | None = None) -> torch.Tensor:
     """out[r, :] = inp[r, :] * (act[r // group, :] > 0)."""

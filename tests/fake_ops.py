@@ -106,9 +106,14 @@ def syrk(x, n=None, alpha=1.0, beta=0.0, out=None, impl="auto", k_rows=None):
     return out
 
 
+def csr_with_masked_sources(a, keep):
+    val = a.val * keep[a.col.to(torch.int64)].to(a.val.dtype)
+    return CSR(a.n_rows, a.n_cols, a.rowptr, a.col, val, a.max_row_nnz)
+
+
 def gemm_mask_supported(k, n):
     return False          # the CPU double keeps the two-step path (torch.mm + relu_mask_mul)
 
 
-ALL = ["gemm_mask_supported", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
+ALL = ["gemm_mask_supported", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
        "halo_columns", "csr_slice_remap", "spmm", "softmax_ce_sum", "hess_rhs", "relu_mask_mul", "syrk"]

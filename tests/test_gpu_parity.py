@@ -462,3 +462,27 @@ def test_marglik_training_epoch_loop_on_device():
     la.fit(L.TensorBatchLoader(idx, y))
     ref = -float(la.log_marginal_likelihood())
     assert abs(res.neg_margliks[-1] - ref) <= 1e-5 * abs(ref)
+
+
+def test_masked_output_layer_spmm_changes_nothing():
+    """Zeroing the edges that read non-train rows of the output-layer slab only skips gathers of rows
+    that are zero anyway: identical loss and factors."""
+    import laplace_gnn_b200 as L
+    g = Golden("pubmed_shape")
+    model = build_model(g, DEV)
+    idx, y = torch.from_numpy(g.idx).to(DEV), torch.from_numpy(g.y).to(DEV)
+    be1 = L.B200GGN(model, "classification")
+    be2 = L.B200GGN(model, "classification")
+    be2.skip_zero_rows = False
+    l1, k1 = be1.kron(idx, y, N=len(y))
+    l2, k2 = be2.kron(idx, y, N=len(y))
+    assert float(l1) == float(l2)
+    for fa, fb in zip(k1.kfacs, k2.kfacs):
+        for a, b in zip(fa, fb):
+            assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-6
+    ops = _ops()
+    keep = torch.zeros(g.n, dtype=torch.uint8, device=DEV)
+    keep[idx] = 1
+    masked = ops.csr_with_masked_sources(model.graph.ahat_t, keep)
+    ref = model.graph.ahat_t.val * keep[model.graph.ahat_t.col.long()].float()
+    assert torch.equal(masked.val, ref)
