@@ -281,9 +281,10 @@ def main():
         for rec in prof:
             ms = rec["start"].elapsed_time(rec["end"])
             gk = (rec["kind"], rec["d"])
-            a = groups.setdefault(gk, {"ms": 0.0, "launches": 0, "bytes": rec["bytes"]})
+            a = groups.setdefault(gk, {"ms": 0.0, "launches": 0, "bytes": 0.0})
             a["ms"] += ms
             a["launches"] += 1
+            a["bytes"] += rec["bytes"]          # algorithmic bytes (SpMM) or useful flops (SYRK / GEMM), summed
         spmm_ms = sum(v["ms"] for (k, _), v in groups.items() if k == "spmm") / args.steps
         syrk_ms = sum(v["ms"] for (k, _), v in groups.items() if k == "syrk") / args.steps
         by_kind = {}
@@ -293,14 +294,27 @@ def main():
         spmm_groups = {kv[0]: kv[1] for kv in groups.items() if kv[0][0] == "spmm"}
         (kind, d), top = max(spmm_groups.items(), key=lambda kv: kv[1]["ms"])
         avg_ms = top["ms"] / top["launches"]
-        achieved = top["bytes"] / (avg_ms * 1e-3) / 1e9
+        achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None, "kernel": f"{kind} d={d}",
                 "avg_launch_ms": avg_ms, "launches_per_step": top["launches"] / args.steps,
                 "share_of_step": top["ms"] / args.steps / ms_step, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": top["bytes"],
+                "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
                 "spmm_ms_per_step": spmm_ms, "syrk_ms_per_step": syrk_ms,
                 "ms_per_step_by_kind": {k: round(v, 2) for k, v in sorted(by_kind.items())}}
+        # secondary, tensor-bound kernels: useful TFLOP/s (3xTF32 issues 3x that) against the TF32 dense
+        # peak taken as half the measured bf16 GEMM figure (MEASURED_PEAKS.json has no tf32 entry)
+        tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+        tens = []
+        for (k, dd), v in sorted(groups.items()):
+            if k in ("syrk", "gemm_mask") and v["ms"] > 0 and v["bytes"] > 0:
+                avg = v["ms"] / v["launches"]
+                ach = v["bytes"] / (v["ms"] * 1e-3) / 1e12
+                tens.append({"kernel": f"{k} n={dd}", "bound": "tensor", "achieved": ach, "peak": tf32_peak,
+                             "unit": "TFLOP/s", "frac": ach / tf32_peak, "avg_launch_ms": avg,
+                             "launches_per_step": v["launches"] / args.steps,
+                             "note": "useful flops; the 3xTF32 split issues 3x (SYRK: x2.25 with the block-triangle)"})
+        roof["tensor_kernels"] = tens
 
     # ---------------- end to end from pinned host buffers through the public API
     e2e = None

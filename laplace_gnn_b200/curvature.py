@@ -196,6 +196,8 @@ class _B200KFAC:
         if budget is None:
             if device.type == "cuda":
                 free, total = torch.cuda.mem_get_info(device)
+                # blocks torch's caching allocator holds but has not handed out are ours to reuse
+                free += torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device)
                 budget = min(int(0.6 * free), int(0.4 * total))
             else:
                 budget = 1 << 30

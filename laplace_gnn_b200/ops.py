@@ -22,6 +22,17 @@ class CSR:
     col: torch.Tensor
     val: torch.Tensor | None = None
     max_row_nnz: int | None = None     # longest row, if known (graph build): lets SpMM skip its hub passes
+    masked: bool = False               # some edge values were zeroed on purpose (their gathers are skipped)
+    _nnz_live: int | None = None
+
+    @property
+    def nnz_gathered(self) -> int:
+        """Non-zeros whose source row is actually read (profiling only: one host sync when masked)."""
+        if not self.masked:
+            return self.nnz
+        if self._nnz_live is None:
+            self._nnz_live = int(torch.count_nonzero(self.val))
+        return self._nnz_live
 
     @property
     def nnz(self) -> int:
@@ -185,7 +196,10 @@ def spmm(a: CSR, x: torch.Tensor, relu: bool = False, out: torch.Tensor | None =
     _f32c(out, "out")
     if out.shape[0] < a.n_rows or out.shape[1] < d:
         raise ValueError("spmm: out too small")
-    with _Timed("spmm", d, spmm_algorithmic_bytes(a.n_rows, a.nnz, d)):
+    work = 0.0
+    if PROFILE is not None:   # masked edges still stream their (col, val) but pull no source row
+        work = spmm_algorithmic_bytes(a.n_rows, a.nnz_gathered, d) + (a.nnz - a.nnz_gathered) * 8
+    with _Timed("spmm", d, work):
         check(lib.lgnn_spmm_f32(a.n_rows, a.nnz, ptr(a.rowptr), ptr(a.col), ptr(a.val), ptr(x), x.stride(0),
                                 ptr(out), out.stride(0), d,
                                 (_lib.SPMM_RELU if relu else _lib.SPMM_NONE) | _SPMM_IMPL[impl] |
@@ -239,7 +253,7 @@ def csr_with_masked_sources(a: CSR, keep: torch.Tensor) -> CSR:
     check(lib.lgnn_mask_edge_values(a.nnz, ptr(a.col), ptr(a.val), ptr(keep), ptr(val), stream()),
           "lgnn_mask_edge_values")
     _lib.count_launches(1)
-    return CSR(a.n_rows, a.n_cols, a.rowptr, a.col, val, a.max_row_nnz)
+    return CSR(a.n_rows, a.n_cols, a.rowptr, a.col, val, a.max_row_nnz, masked=True)
 
 
 def relu_mask_mul(inp: torch.Tensor, act: torch.Tensor, group: int, out: torch.Tensor | None = None,

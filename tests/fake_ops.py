@@ -108,7 +108,7 @@ def syrk(x, n=None, alpha=1.0, beta=0.0, out=None, impl="auto", k_rows=None):
 
 def csr_with_masked_sources(a, keep):
     val = a.val * keep[a.col.to(torch.int64)].to(a.val.dtype)
-    return CSR(a.n_rows, a.n_cols, a.rowptr, a.col, val, a.max_row_nnz)
+    return CSR(a.n_rows, a.n_cols, a.rowptr, a.col, val, a.max_row_nnz, masked=True)
 
 
 def gemm_mask_supported(k, n):
