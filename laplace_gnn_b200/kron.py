@@ -132,6 +132,34 @@ class KronDecomposed:
 
     __rmul__ = __mul__
 
+    def bmm(self, W: torch.Tensor, exponent: float = 1.0) -> torch.Tensor:
+        """``self ** exponent @ W`` row-wise for W [S, P] (matrix.py:396-475): weight blocks are
+        flattened [d_out, d_in] row-major with factors [G, A]."""
+        if W.ndim == 1:
+            return self.bmm(W.unsqueeze(0), exponent).squeeze(0)
+        if W.ndim != 2:
+            raise ValueError("W must be [P] or [S, P]")
+        out, cur = [], 0
+        for lams, Qs, delta in zip(self.eigenvalues, self.eigenvectors, self.deltas):
+            if len(lams) == 1:
+                p = lams[0].numel()
+                Wp = W[:, cur:cur + p].T
+                out.append((Qs[0] @ (torch.pow(lams[0] + delta, exponent).reshape(-1, 1) * (Qs[0].T @ Wp))).T)
+            else:
+                l1, l2 = lams
+                p = l1.numel() * l2.numel()
+                if self.damping:
+                    scale = torch.pow(torch.outer(l1 + delta.sqrt(), l2 + delta.sqrt()), exponent)
+                else:
+                    scale = torch.pow(torch.outer(l1, l2) + delta, exponent)
+                Wp = W[:, cur:cur + p].reshape(-1, l1.numel(), l2.numel())
+                Wp = (Qs[0].T @ Wp @ Qs[1]) * scale.unsqueeze(0)
+                out.append((Qs[0] @ Wp @ Qs[1].T).reshape(-1, p))
+            cur += p
+        if cur != W.shape[1]:
+            raise ValueError("W has the wrong number of parameters")
+        return torch.cat(out, dim=1)
+
     def logdet(self) -> torch.Tensor:
         total = 0.0
         for lams, delta in zip(self.eigenvalues, self.deltas):
@@ -293,6 +321,24 @@ class KronLaplace(_ParametricLaplaceLite):
     @property
     def log_det_posterior_precision(self) -> torch.Tensor:
         return self.posterior_precision.logdet()
+
+    def sample(self, n_samples: int = 100, generator: torch.Generator | None = None) -> torch.Tensor:
+        """Weight samples from N(mean, P^-1) (baselaplace.py:1646-1655)."""
+        eps = torch.randn(n_samples, self.n_params, device=self._device, generator=generator)
+        return self.mean.reshape(1, -1) + self.posterior_precision.bmm(eps, exponent=-0.5)
+
+    def __call__(self, x: torch.Tensor, pred_type: str = "nn", link_approx: str = "mc", n_samples: int = 100,
+                 generator: torch.Generator | None = None, samples: torch.Tensor | None = None) -> torch.Tensor:
+        """MC predictive ``la(idx, pred_type="nn", link_approx="mc", n_samples=...)`` — the call of
+        ``mc_eval`` (gnn/marglik_training.py:341-353; baselaplace.py:1183-1199): class probabilities
+        of the nodes ``x`` averaged over weight samples.  All samples of a tile go through the graph
+        together as extra right-hand-side columns of the SpMM."""
+        if pred_type != "nn" or link_approx != "mc":
+            raise NotImplementedError("only the sampling predictive (pred_type='nn', link_approx='mc') is built")
+        from .predictive import mc_predictive
+        if samples is None:
+            samples = self.sample(n_samples, generator)
+        return mc_predictive(self.model, samples, x)
 
 
 class DiagLaplace(_ParametricLaplaceLite):

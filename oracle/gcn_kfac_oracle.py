@@ -329,6 +329,59 @@ def fit_and_marglik(g: NormAdj, x, weights, biases, idx, y, prior_prec=1.0,
 
 
 # --------------------------------------------------------------------------------------
+# predictive path on the Kron posterior
+# --------------------------------------------------------------------------------------
+
+
+def kron_bmm(kfacs, W: torch.Tensor, exponent: float, delta: float = 1.0) -> torch.Tensor:
+    """(H + δI)^exponent @ W^T for the block-diagonal Kron H, row-wise on W [S, P]
+    (KronDecomposed._bmm, matrix.py:396-446; weight blocks are flattened [d_out, d_in] row-major
+    and their factors are [G (d_out), A (d_in)])."""
+    out, cur = [], 0
+    for F in kfacs:
+        if len(F) == 1:
+            lam, Q = symeig(F[0].to(W.dtype))
+            p = lam.numel()
+            Wp = W[:, cur:cur + p].T
+            out.append((Q @ (torch.pow(lam + delta, exponent).reshape(-1, 1) * (Q.T @ Wp))).T)
+        else:
+            (l1, Q1), (l2, Q2) = symeig(F[0].to(W.dtype)), symeig(F[1].to(W.dtype))
+            p = l1.numel() * l2.numel()
+            Wp = W[:, cur:cur + p].reshape(-1, l1.numel(), l2.numel())
+            Wp = (Q1.T @ Wp @ Q2) * torch.pow(torch.outer(l1, l2) + delta, exponent).unsqueeze(0)
+            out.append((Q1 @ Wp @ Q2.T).reshape(-1, p))
+        cur += p
+    return torch.cat(out, dim=1)
+
+
+def posterior_samples(mean, kfacs, eps, prior_prec: float = 1.0, dtype=torch.float32) -> torch.Tensor:
+    """KronLaplace.sample for given standard-normal draws eps [S, P] (baselaplace.py:1646-1655)."""
+    return _t(mean, dtype).reshape(1, -1) + kron_bmm(kfacs, _t(eps, dtype), -0.5, prior_prec)
+
+
+def unpack_params(theta, shapes):
+    """Parameter vector -> ([W_l], [b_l]) in named_parameters() order (weight then bias per layer)."""
+    Ws, bs, cur = [], [], 0
+    for (d_out, d_in) in shapes:
+        Ws.append(theta[cur:cur + d_out * d_in].reshape(d_out, d_in)); cur += d_out * d_in
+        bs.append(theta[cur:cur + d_out]); cur += d_out
+    return Ws, bs
+
+
+def mc_predictive(g: NormAdj, x, samples, shapes, idx, dtype=torch.float32) -> torch.Tensor:
+    """_nn_predictive_classification (baselaplace.py:1183-1199): mean over weight samples of
+    softmax(model_sample(idx)); one eval-mode full-graph forward per sample."""
+    idx_t = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
+    samples = _t(samples, dtype)
+    py = 0.0
+    for s in range(samples.shape[0]):
+        Ws, bs = unpack_params(samples[s], shapes)
+        _, ps = forward(g, x, Ws, bs, dtype)
+        py = py + torch.softmax(ps[-1][idx_t], dim=-1) / samples.shape[0]
+    return py
+
+
+# --------------------------------------------------------------------------------------
 # exact diag GGN (curvature.py:412-432) — small graphs only: builds the dense Jacobian
 # --------------------------------------------------------------------------------------
 
