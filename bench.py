@@ -295,8 +295,19 @@ def main():
         (kind, d), top = max(spmm_groups.items(), key=lambda kv: kv[1]["ms"])
         avg_ms = top["ms"] / top["launches"]
         achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
+        # DRAM bytes per launch of this kernel as ncu measured them on this workload (dram__bytes_read.sum +
+        # dram__bytes_write.sum; tools/ncu_traffic.py writes profiles/ncu_traffic.json), else null
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            ent = tj.get(f"{args.workload}:{args.scale}:{world}:spmm d={d}")
+            if ent and ent.get("nnz") == nnz:
+                traffic, traffic_src = ent["dram_bytes_per_launch"], ent.get("source")
+        except Exception:
+            pass
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "kernel": f"{kind} d={d}",
+                "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": f"{kind} d={d}",
                 "avg_launch_ms": avg_ms, "launches_per_step": top["launches"] / args.steps,
                 "share_of_step": top["ms"] / args.steps / ms_step, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],

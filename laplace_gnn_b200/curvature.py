@@ -175,7 +175,11 @@ class _B200KFAC:
             if part is None:
                 with ops.timed("gemm_fwd", d_out, 2.0 * h.shape[0] * Ws[l].numel()):
                     z = torch.mm(h, Ws[l].t()) if bs[l] is None else torch.addmm(bs[l], h, Ws[l].t())
-                h = ops.spmm(g.ahat, z, relu=(l < L - 1))
+                    if d_out % 4:      # odd class count: pad the pitch so the SpMM takes its 128-bit path
+                        zp = torch.zeros(z.shape[0], (d_out + 3) // 4 * 4, dtype=z.dtype, device=z.device)
+                        zp[:, :d_out] = z
+                        z = zp
+                h = ops.spmm(g.ahat, z, relu=(l < L - 1))[:, :d_out]
             else:
                 slab = torch.empty(part.total_rows, d_out, dtype=torch.float32, device=h.device)
                 z = slab[part.slot0:part.slot0 + part.n_local]
