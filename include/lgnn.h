@@ -131,8 +131,8 @@ int lgnn_csr_slice_remap(const int64_t* rowptr, const int32_t* col, const float*
  * backward passes of curvlinops/kfac.py:653-661 in ONE multi-RHS pass.
  * X: [*, ldx] row-major fp32; Y: [n_rows, ldy]; nnz = rowptr[n_rows] (host copy, sizes the grid).
  * The 128-bit paths need X, Y 16-byte aligned and d, ldx, ldy multiples of 4; anything else takes
- * the scalar path.  Wide slabs whose column ranges give >= 10 KB ring stages (d >= 2560) use the
- * bulk-async shared-memory ring kernel, everything else the warp-per-row kernel. */
+ * the scalar path.  Wide slabs whose column ranges (<= 4096 floats) give >= 14 KB ring stages
+ * (d >= 3584) use the bulk-async shared-memory ring kernel, everything else the warp-per-row kernel. */
 int lgnn_spmm_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr, const int32_t* col,
                   const float* val, const float* x, int64_t ldx, float* y, int64_t ldy, int64_t d,
                   int flags, lgnn_stream_t stream);

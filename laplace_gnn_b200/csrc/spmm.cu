@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(SPMM_THREADS) spmm_scalar_kernel(
 // Wide SpMM (d >= 512): bulk-async gather through a shared-memory ring.
 //
 // One CTA owns a block of consecutive rows holding ~BULK_NNZ_PER_CTA non-zeros (found by a binary
-// search in rowptr, so CTAs are nnz-balanced) and one column range of at most 4096 floats.  A
+// search in rowptr, so CTAs are nnz-balanced) and one column range of at most 4096 floats (16 KB stages).  A
 // producer warp walks the (col, val) stream of those rows; every lane issues, for its neighbour, ONE
 // cp.async.bulk (the TMA engine's 1-D copy) of the whole <= 16 KB piece of the source row into a
 // ring stage, completion signalled on the stage's mbarrier.  Up to ~190 KB of gathered rows are in
@@ -487,23 +487,27 @@ extern "C" int lgnn_spmm_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr,
                       ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
   const int warps_per_block = SPMM_THREADS / 32;
   const int epi = flags & LGNN_SPMM_RELU;
-  // measured on B200 (profiles/): with >= 10 KB ring stages the bulk kernel sits at the HBM roofline;
-  // with smaller stages its per-stage hand-off dominates and the warp-per-row kernel is faster
-  bool bulk = vec_ok && d >= 2560 && ((d / 4 + ((d / 4 + 767) / 768) - 1) / ((d / 4 + 767) / 768)) >= 640;
+  // measured on B200 (profiles/): both kernels sit at the HBM roofline for wide slabs; with small ring
+  // stages the bulk kernel's per-stage hand-off dominates and the warp-per-row kernel is faster
+  const int d4_all = (int)(d / 4);
+  const int bulk_ranges = (d4_all + 1023) / 1024;                       // column ranges of <= 4096 floats
+  const int bulk_range4 = bulk_ranges > 0 ? (d4_all + bulk_ranges - 1) / bulk_ranges : 0;
+  bool bulk = vec_ok && bulk_range4 >= 896;   // paired lab runs (profiles/r1f_spmm_lab.txt): the ring wins from ~14 KB stages up
   if (flags & LGNN_SPMM_FORCE_LDG) bulk = false;
   if (flags & LGNN_SPMM_FORCE_BULK) {
     if (!vec_ok) return fail(LGNN_E_ALIGN, "spmm: the bulk path needs 16-byte aligned x / y and d, ldx, ldy %% 4 == 0");
     bulk = true;
   }
   if (bulk) {
-    const int d4 = (int)(d / 4);
-    const int n_ranges = (d4 + 767) / 768;
+    const int d4 = d4_all;
+    const int n_ranges = bulk_ranges;
     const int range4 = (d4 + n_ranges - 1) / n_ranges;
     const int vpt = (range4 + BULK_CONSUMERS - 1) / BULK_CONSUMERS;
     switch (vpt) {
       case 1: return launch_bulk<1>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_ranges, range4, nnz, epi | (flags & LGNN_SPMM_NO_HUB_ROWS), st);
       case 2: return launch_bulk<2>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_ranges, range4, nnz, epi | (flags & LGNN_SPMM_NO_HUB_ROWS), st);
-      default: return launch_bulk<3>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_ranges, range4, nnz, epi | (flags & LGNN_SPMM_NO_HUB_ROWS), st);
+      case 3: return launch_bulk<3>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_ranges, range4, nnz, epi | (flags & LGNN_SPMM_NO_HUB_ROWS), st);
+      default: return launch_bulk<4>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_ranges, range4, nnz, epi | (flags & LGNN_SPMM_NO_HUB_ROWS), st);
     }
   }
   if (vec_ok) {

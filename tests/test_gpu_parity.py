@@ -148,7 +148,7 @@ def test_spmm_bulk_kernel_empty_rows_hub_rows_and_leading_dimensions():
     ops = _ops()
     from laplace_gnn_b200.ops import CSR
     rng = np.random.Generator(np.random.PCG64(7))
-    n_rows, n_cols, d, ld = 300, 500, 2560, 2600
+    n_rows, n_cols, d, ld = 300, 500, 3840, 3900      # a width "auto" gives to the bulk kernel
     counts = rng.integers(0, 12, n_rows)
     counts[[0, 1, 57, 58, 298, 299]] = 0
     counts[100] = 9000                                    # > BULK_NNZ_PER_CTA, below the hub threshold
@@ -164,7 +164,7 @@ def test_spmm_bulk_kernel_empty_rows_hub_rows_and_leading_dimensions():
     import scipy.sparse as sp
     ref = sp.csr_matrix((val.astype(np.float64), col, rowptr), shape=(n_rows, n_cols)) @ x[:, :d].astype(np.float64)
     xd = torch.from_numpy(x).to(DEV)
-    for impl in ("bulk", "auto"):                         # d = 2560 is a width "auto" gives to the bulk kernel
+    for impl in ("bulk", "auto"):
         out = torch.full((n_rows, ld), 7.0, device=DEV)
         ops.spmm(a, xd, out=out, d=d, impl=impl)
         assert max_rel_err(out[:, :d].cpu().numpy(), ref) <= 1e-5

@@ -11,7 +11,7 @@ rows = list(csv.DictReader(io.StringIO("\n".join(txt[start:]))))
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
 per = {}
 for r in rows:
-    if "spmm_bulk_kernel" not in r["Kernel Name"]:
+    if "spmm_bulk_kernel" not in r["Kernel Name"] and "spmm_vec_kernel" not in r["Kernel Name"]:
         continue
     e = per.setdefault(r["ID"], {})
     v = float(r["Metric Value"].replace(",", ""))
