@@ -1,7 +1,8 @@
 #!/bin/bash
 set -u
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_syrk_tcgen05.py -m gpu -q -x > gpurun_out/t_syrk.log 2>&1; echo "syrk tests rc=$?"; tail -8 gpurun_out/t_syrk.log | cut -c1-250
-timeout 300 python tools/syrk_lab.py --n 256,48,100,128 --impl tcgen05 --k 4000000 2>&1 | tee gpurun_out/syrk_lab.log | tail -10
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "spmm" > gpurun_out/t_spmm.log 2>&1; echo "spmm tests rc=$?"; tail -3 gpurun_out/t_spmm.log | cut -c1-250
-timeout 600 python tools/spmm_lab.py --d 3840,4096,3072,2560 --impl ldg,bulk 2>&1 | tee gpurun_out/spmm_lab3.log | tail -10
+timeout 600 python -m pytest tests -m gpu -q > gpurun_out/t1.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/t1.log | cut -c1-250
+FULL="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline"
+$FULL > gpurun_out/plain_full.log 2>&1 &&
+ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:"spmm_bulk|spmm_vec" --csv --log-file gpurun_out/traffic.csv $FULL > gpurun_out/ncu0.log 2>&1; echo "ncu traffic rc=$?"
+tail -c 900 gpurun_out/plain_full.log
