@@ -60,3 +60,52 @@ class Graph:
     def partition_bounds(self, nparts: int) -> torch.Tensor:
         """nnz-balanced contiguous row blocks of Â (int64 [nparts+1], device)."""
         return ops.row_partition(self.ahat.rowptr, nparts)
+
+
+# ------------------------------------------------------------------------------------------------
+# graph ingest (SURVEY §8f row 4): on-disk cache of the built CSR, k-nearest-neighbour graphs
+# ------------------------------------------------------------------------------------------------
+
+
+def save_graph(graph: Graph, path: str) -> None:
+    """Cache a built graph (integer CSR, degrees, values) so that it is not rebuilt per run."""
+    def pack(c: CSR):
+        return {"n_rows": c.n_rows, "n_cols": c.n_cols, "rowptr": c.rowptr.cpu(), "col": c.col.cpu(),
+                "val": None if c.val is None else c.val.cpu(), "max_row_nnz": c.max_row_nnz}
+    same = graph.ahat_t is graph.ahat
+    torch.save({"n": graph.n, "deg": graph.deg.cpu(), "dis": graph.dis.cpu(), "ahat": pack(graph.ahat),
+                "ahat_t": None if same else pack(graph.ahat_t), "symmetric_pattern": graph.symmetric_pattern,
+                "meta": graph.meta}, path)
+
+
+def load_graph(path: str, device) -> Graph:
+    z = torch.load(path, map_location="cpu", weights_only=False)
+
+    def unpack(d):
+        return CSR(d["n_rows"], d["n_cols"], d["rowptr"].to(device), d["col"].to(device),
+                   None if d["val"] is None else d["val"].to(device), d["max_row_nnz"])
+    a = unpack(z["ahat"])
+    at = a if z["ahat_t"] is None else unpack(z["ahat_t"])
+    return Graph(z["n"], z["deg"].to(device), z["dis"].to(device), a, at, z["symmetric_pattern"], z["meta"])
+
+
+def knn_edge_index(X: torch.Tensor, k: int = 3, chunk: int = 4096) -> torch.Tensor:
+    """Directed k-nearest-neighbour edges (neighbour -> node, Euclidean, no self loops) like the
+    ``knn_graph(X, k, loop=False, cosine=False)`` call inside ``get_knn_graph`` (gnn/utils.py:355-369).
+    Build the reference's kNN graph (symmetrised, self loops set) with
+    ``Graph.from_edge_index(knn_edge_index(X, k), n, symmetric=True)``.  Distances are evaluated in
+    row chunks (a library GEMM + top-k per chunk), never as an N x N matrix."""
+    n = X.shape[0]
+    if not 1 <= k < n:
+        raise ValueError("knn_edge_index needs 1 <= k < number of nodes")
+    Xf = X.float()
+    sq = (Xf * Xf).sum(1)
+    src, dst = [], []
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
+        d2 = sq[s:e, None] + sq[None, :] - 2.0 * (Xf[s:e] @ Xf.t())
+        d2[torch.arange(e - s, device=X.device), torch.arange(s, e, device=X.device)] = float("inf")   # loop=False
+        nb = torch.topk(d2, k, dim=1, largest=False).indices                     # [chunk, k]
+        src.append(nb.reshape(-1))
+        dst.append(torch.arange(s, e, device=X.device).repeat_interleave(k))
+    return torch.stack([torch.cat(src), torch.cat(dst)]).to(torch.int64)

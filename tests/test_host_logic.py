@@ -224,3 +224,29 @@ def test_marglik_training_epoch_loop(fake_ops):
             assert max_rel_err(a.numpy(), b.numpy()) <= 1e-6
     stopped = L.marglik_training(model, idx, y, val_idx, val_y, n_epochs=50, lr=0.0, patience=2, early_stop=True)
     assert stopped.stopped_epoch < 50                                               # lr = 0: no improvement, patience ends it
+
+
+def test_knn_graph_and_graph_cache(fake_ops, tmp_path):
+    """the reference's kNN graph recipe (gnn/utils.py:355-369: Euclidean kNN without
+    self loops, symmetrised, diagonal set) and the on-disk CSR cache."""
+    import laplace_gnn_b200 as L
+    rng = np.random.Generator(np.random.PCG64(3))
+    X = torch.from_numpy(rng.standard_normal((200, 7)).astype(np.float32))
+    k = 4
+    ei = L.knn_edge_index(X, k, chunk=64)
+    d = ((X[:, None, :] - X[None, :, :]) ** 2).sum(-1)
+    d.fill_diagonal_(float("inf"))
+    ref_nb = torch.topk(d, k, dim=1, largest=False).indices
+    assert ei.shape == (2, 200 * k) and torch.equal(ei[1].view(200, k)[:, 0], torch.arange(200))
+    assert torch.equal(torch.sort(ei[0].view(200, k), 1).values, torch.sort(ref_nb, 1).values)
+    g = L.Graph.from_edge_index(ei, 200, symmetric=True)
+    dense = torch.zeros(200, 200)
+    dense[ei[0], ei[1]] = 1
+    dense = ((dense + dense.T) > 0).float()
+    dense.fill_diagonal_(1)                                           # get_knn_graph's adjacency
+    assert g.nnz == int(dense.sum()) and torch.equal(g.deg, dense.sum(1).long())
+    path = str(tmp_path / "g.pt")
+    L.save_graph(g, path)
+    g2 = L.load_graph(path, "cpu")
+    assert g2.n == g.n and torch.equal(g2.ahat.rowptr, g.ahat.rowptr) and torch.equal(g2.ahat.col, g.ahat.col)
+    assert torch.equal(g2.ahat.val, g.ahat.val) and g2.ahat_t is g2.ahat
