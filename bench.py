@@ -51,7 +51,7 @@ def parse_args():
     ap.add_argument("--no-fused-gemm", action="store_true", help="cuBLAS fp32 GEMM + mask kernel instead of the fused tcgen05 kernel")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-div", type=int, default=32,
+    ap.add_argument("--cpu-sample-div", type=int, default=16,
                     help="the CPU arm / cpu_baseline run the same workload shape at 1/div of the nodes and edges")
     return ap.parse_args()
 
