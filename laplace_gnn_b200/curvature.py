@@ -212,11 +212,14 @@ class _B200KFAC:
         """RowPartition of the model's graph for this backend's process group (built once)."""
         if self.process_group is None:
             return None
-        part = getattr(self, "_part", None)
+        # cached on the graph: a new Laplace object (one per epoch in the reference's loop) makes a new
+        # backend, the row slices of the CSR do not change
+        cache = self.model.graph.meta.setdefault("_partitions", {})
+        part = cache.get(id(self.process_group))
         if part is None or part.pg is not self.process_group:
             from .dist import RowPartition
             part = RowPartition.build(self.model.graph, self.process_group)
-            self._part = part
+            cache[id(self.process_group)] = part
         return part
 
     def _chain(self, lay, logits, idx, Hs, Ws, Wp, c0, gc, buf_a, buf_b, G):
@@ -385,7 +388,7 @@ class _B200KFAC:
                 part.all_reduce_sum([loss])
         self.last_stats = {"group": grp, "n_groups": n_groups, "M": M, "C": C,
                            "world": 1 if part is None else part.world,
-                           "halo_fraction": None if part is None else part.halo_fraction}
+                           "partition": part}
 
         Kron = _kron_class()
         kfacs = []

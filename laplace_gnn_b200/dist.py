@@ -43,7 +43,18 @@ class RowPartition:
     pad: int                # rows per slot of the padded all-gather layout
     ahat: CSR               # rows [lo, hi) of Â,   columns in padded layout
     ahat_t: CSR             # rows [lo, hi) of Â^T, columns in padded layout
-    halo_fraction: float    # fraction of the other ranks' rows this rank's SpMM reads
+    graph: object = None    # the full graph (for the lazily evaluated halo statistic)
+    _halo_fraction: float | None = None
+
+    @property
+    def halo_fraction(self) -> float:
+        """Fraction of the other ranks' rows this rank's backward SpMM reads (lgnn_halo_mark; one host
+        sync, evaluated on first use only)."""
+        if self._halo_fraction is None:
+            n_other = self.graph.n - (self.hi - self.lo)
+            halo = ops.halo_columns(self.graph.ahat_t, self.lo, self.hi)
+            self._halo_fraction = float(halo.numel()) / n_other if n_other > 0 else 0.0
+        return self._halo_fraction
 
     @property
     def lo(self) -> int:
@@ -74,10 +85,7 @@ class RowPartition:
         lo, hi = bounds[rank], bounds[rank + 1]
         a = ops.csr_slice_remap(graph.ahat, lo, hi, bounds_t, pad)
         at = a if graph.ahat_t is graph.ahat else ops.csr_slice_remap(graph.ahat_t, lo, hi, bounds_t, pad)
-        n_other = graph.n - (hi - lo)
-        halo = ops.halo_columns(graph.ahat_t, lo, hi)
-        frac = float(halo.numel()) / n_other if n_other > 0 else 0.0
-        return cls(pg, rank, world, bounds, pad, a, at, frac)
+        return cls(pg, rank, world, bounds, pad, a, at, graph)
 
     # ---- collectives -------------------------------------------------------------------
     def all_gather_slab(self, slab: torch.Tensor, async_op: bool = False):

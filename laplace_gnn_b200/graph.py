@@ -75,7 +75,7 @@ def save_graph(graph: Graph, path: str) -> None:
     same = graph.ahat_t is graph.ahat
     torch.save({"n": graph.n, "deg": graph.deg.cpu(), "dis": graph.dis.cpu(), "ahat": pack(graph.ahat),
                 "ahat_t": None if same else pack(graph.ahat_t), "symmetric_pattern": graph.symmetric_pattern,
-                "meta": graph.meta}, path)
+                "meta": {k: v for k, v in graph.meta.items() if not k.startswith("_")}}, path)
 
 
 def load_graph(path: str, device) -> Graph:

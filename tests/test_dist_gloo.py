@@ -41,7 +41,7 @@ def _worker(rank, world, port, name, mode, out):
         ml = la.log_marginal_likelihood()
         check_against_golden(g, la.loss, la.H_facs.kfacs, ml)
         st = la.backend.last_stats
-        assert st["world"] == world and 0.0 <= st["halo_fraction"] <= 1.0
+        assert st["world"] == world and 0.0 <= st["partition"].halo_fraction <= 1.0
         # every rank ends with bit-identical factors (same all-reduce result)
         flat = torch.cat([h.reshape(-1) for blk in la.H_facs.kfacs for h in blk])
         gathered = [torch.empty_like(flat) for _ in range(world)]
