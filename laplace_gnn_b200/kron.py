@@ -22,7 +22,16 @@ from torch.nn.utils import parameters_to_vector
 
 
 def _eigh_psd(m: torch.Tensor):
-    lam, q = torch.linalg.eigh(m, UPLO="U")
+    """symeig of the reference (laplace/utils/utils.py:193-226): eigh(UPLO="U"), eigenvalues clamped
+    at 0, NaN -> 0.  On the device the decomposition itself runs in float64 for n <= 1024 and is cast
+    back: cusolver's double-precision path is 2-3x FASTER than the Jacobi solver torch picks for small
+    fp32 matrices (B200: n = 256: 2.4 vs 5.3 ms, n = 500: 5.5 vs 15.6 ms; profiles/r1f_eigh_lab.txt) and
+    its eigenvalues are exact to fp32 rounding."""
+    if m.is_cuda and m.dtype == torch.float32 and m.shape[-1] <= 1024:
+        lam, q = torch.linalg.eigh(m.double(), UPLO="U")
+        lam, q = lam.to(m.dtype), q.to(m.dtype)
+    else:
+        lam, q = torch.linalg.eigh(m, UPLO="U")
     return torch.nan_to_num(lam.clamp(min=0.0)), torch.nan_to_num(q)
 
 
