@@ -284,7 +284,8 @@ def main():
             a = groups.setdefault(gk, {"ms": 0.0, "launches": 0, "bytes": 0.0})
             a["ms"] += ms
             a["launches"] += 1
-            a["bytes"] += rec["bytes"]          # algorithmic bytes (SpMM) or useful flops (SYRK / GEMM), summed
+            w = rec["bytes"]() if callable(rec["bytes"]) else rec["bytes"]
+            a["bytes"] += w                      # algorithmic bytes (SpMM) or useful flops (SYRK / GEMM), summed
         spmm_ms = sum(v["ms"] for (k, _), v in groups.items() if k == "spmm") / args.steps
         syrk_ms = sum(v["ms"] for (k, _), v in groups.items() if k == "syrk") / args.steps
         by_kind = {}
