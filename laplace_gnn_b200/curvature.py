@@ -139,6 +139,12 @@ class _B200KFAC:
         self.overlap = bool(overlap)
         self.fused_gemm = bool(fused_gemm)
         self.skip_zero_rows = True
+        # zero-compress the relu-masked slabs below the output layer (csrc/spmm_packed.cu).  Correct and
+        # bit-identical, but OFF by default: per-element bitmask decoding in the SpMM consumer costs more
+        # than the halved gather saves (products, d = 3840: 594 ms against 286 ms dense;
+        # profiles/r1g_pack_lab.txt)
+        self.pack_slabs = False
+        self.pack_min_width = 1024
         # A_0 = X^T X does not depend on the weights: with cache_input_factor the raw Gram matrix of
         # this rank's feature rows is kept (per backend, or in a dict shared across backends by the
         # epoch loop) and only rescaled per call
@@ -225,29 +231,39 @@ class _B200KFAC:
     def _chain(self, lay, logits, idx, Hs, Ws, Wp, c0, gc, buf_a, buf_b, G):
         """One group of ``gc`` Hessian-sqrt columns pushed down all layers; a generator that yields
         after each layer so that two groups can be interleaved on two streams (their all-gathers
-        then overlap the other group's SpMM)."""
+        then overlap the other group's SpMM).
+
+        ``buf_a`` / ``buf_b`` alternate as SpMM input / output.  Below the output layer the input slab
+        delta = (gZ W) ⊙ relu' is about half zeros: when every row is local (single GPU, or the
+        column-parallel backward) it is zero-compressed (``ops.pack_rows``) into the buffer the dead
+        gZ occupied, and the SpMM gathers only the non-zeros (``ops.spmm_packed``)."""
         L = len(Ws)
         C = logits.shape[1]
         dims = [w.shape[0] for w in Ws]                 # d_1 .. d_L (d_L = C)
         c_pad = (C + 3) // 4 * 4
         n_loc, n_in, slot0 = lay.n_local, lay.total_rows, lay.slot0
-        slab = buf_a[: n_in * gc * c_pad].view(n_in, gc * c_pad)
+        P, Q = buf_a, buf_b                             # P: SpMM input, Q: SpMM output
+        slab = P[: n_in * gc * c_pad].view(n_in, gc * c_pad)
         delta = slab[slot0:slot0 + n_loc]
         with ops.timed("hess_rhs", gc):
             delta.zero_()
             ops.hess_rhs(logits, idx, c0, gc, delta, c_pad, self.hess_sqrt)
         width, ld = C, c_pad
+        packed = None
         for l in range(L - 1, -1, -1):
-            with ops.timed("allgather", gc * ld, 4.0 * n_in * gc * ld):
-                lay.gather(slab)
-            gz = buf_b[: n_loc * gc * ld].view(n_loc, gc * ld)
-            # output layer: the slab is zero outside the batch's train rows -> no gather for those edges
-            ops.spmm(lay.csr_t_top if (l == L - 1 and lay.csr_t_top is not None) else lay.csr_t, slab, out=gz)
+            gz = Q[: n_loc * gc * ld].view(n_loc, gc * ld)
+            if packed is not None:
+                ops.spmm_packed(lay.csr_t, packed, out=gz)
+            else:
+                with ops.timed("allgather", gc * ld, 4.0 * n_in * gc * ld):
+                    lay.gather(slab)
+                # output layer: the slab is zero outside the batch's train rows -> no gather for those edges
+                ops.spmm(lay.csr_t_top if (l == L - 1 and lay.csr_t_top is not None) else lay.csr_t, slab, out=gz)
             gz_rows = gz.view(n_loc * gc, ld)
             ops.syrk(gz_rows, n=width, alpha=1.0, beta=1.0, out=G[l], impl=self._impl(width))
             if l > 0:
                 d_prev = dims[l - 1]
-                slab = buf_a[: n_in * gc * d_prev].view(n_in, gc * d_prev)
+                slab = P[: n_in * gc * d_prev].view(n_in, gc * d_prev)
                 nxt = slab[slot0:slot0 + n_loc].view(n_loc * gc, d_prev)
                 if Wp[l] is not None:      # fused 3xTF32 tensor-core GEMM + relu' mask
                     ops.gemm_mask(gz_rows, Wp[l], Hs[l], gc, out=nxt, m_rows=n_loc * gc)
@@ -257,7 +273,16 @@ class _B200KFAC:
                     with ops.timed("relu_mask", d_prev, 2.0 * n_loc * gc * d_prev * 4):
                         ops.relu_mask_mul(nxt, Hs[l], gc)
                 width, ld = d_prev, d_prev
+                packed = None
+                if self._can_pack(lay, gc * d_prev):
+                    packed = ops.pack_rows(slab, gc * d_prev, out=Q.view(torch.uint8))   # gZ in Q is dead
+                    P, Q = Q, P            # the packed slab is the next input, the dense one the next output
             yield
+
+    def _can_pack(self, lay, width: int) -> bool:
+        # narrow slabs stay dense: the ring kernel needs multi-KB copies to reach the HBM roofline
+        return (self.pack_slabs and not lay.communicates and width % 4 == 0 and
+                self.pack_min_width <= width <= ops.PACK_MAX_WIDTH and lay.csr_t.val.is_cuda)
 
     def _backward_columns(self, lay, logits, idx, Hs, Ws, cols, G):
         """Multi-RHS KFAC backward for the Hessian-sqrt columns ``cols = (first, count)`` on the
@@ -271,6 +296,10 @@ class _B200KFAC:
         n_loc, n_in = lay.n_local, lay.total_rows
         lanes = 2 if (self.overlap and lay.communicates and dev.type == "cuda") else 1
         grp = self._group_size(lanes * n_in, lanes * n_loc, dmax, C, dev)
+        hidden = max(dims[:-1]) if len(dims) > 1 else 0
+        can_pack = self.pack_slabs and not lay.communicates and dev.type == "cuda" and 0 < hidden <= ops.PACK_MAX_WIDTH
+        if can_pack:                       # keep the hidden-layer slabs narrow enough for the packed SpMM
+            grp = min(grp, max(1, ops.PACK_MAX_WIDTH // hidden))
         grp = lay.agree_min(max(1, min(grp, (c_count + lanes - 1) // lanes)))
         if c_count <= 0:
             return grp, 0
@@ -280,8 +309,12 @@ class _B200KFAC:
                        ops.gemm_mask_supported(Ws[l].shape[0], Ws[l].shape[1]) else None
                        for l in range(1, len(Ws))]
         lanes = min(lanes, len(groups))
-        bufs = [(torch.empty(n_in * grp * dmax, dtype=torch.float32, device=dev),          # SpMM inputs (slabs)
-                 torch.empty(max(n_loc, 1) * grp * dmax, dtype=torch.float32, device=dev))  # SpMM outputs
+        # two slabs per lane, alternating as SpMM input / output; a packed slab needs its header on top
+        row_floats = grp * dmax
+        if can_pack:
+            row_floats = max(row_floats, (ops.pack_rows_pitch(grp * hidden) + 3) // 4)
+        bufs = [(torch.empty(n_in * row_floats, dtype=torch.float32, device=dev),
+                 torch.empty(max(n_in if can_pack else n_loc, 1) * row_floats, dtype=torch.float32, device=dev))
                 for _ in range(lanes)]
         if lanes == 1:
             for c0, gc in groups:

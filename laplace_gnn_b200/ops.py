@@ -210,6 +210,65 @@ def spmm(a: CSR, x: torch.Tensor, relu: bool = False, out: torch.Tensor | None =
     return out
 
 
+# ------------------------------------------------------------------------------ zero-compressed slabs
+PACK_MAX_WIDTH = 4096
+
+
+@dataclass
+class PackedRows:
+    """Slab [n_rows, d] with its zeros squeezed out (csrc/spmm_packed.cu): ``data`` holds one slot of
+    ``pitch`` bytes per row, of which the SpMM reads the first ``len[r]``."""
+    n_rows: int
+    d: int
+    pitch: int
+    data: torch.Tensor      # uint8 [>= n_rows * pitch]
+    len: torch.Tensor       # int32 [n_rows]
+
+
+def pack_rows_pitch(d: int) -> int:
+    return int(_lib.load().lgnn_pack_rows_pitch(int(d)))
+
+
+def pack_rows(x: torch.Tensor, d: int | None = None, out: torch.Tensor | None = None) -> PackedRows:
+    """Compress the first d columns of x (row-major fp32).  ``out``: optional uint8 byte buffer."""
+    lib = _lib.load()
+    _f32c(x, "x")
+    d = int(x.shape[1]) if d is None else int(d)
+    n = int(x.shape[0])
+    pitch = pack_rows_pitch(d)
+    if out is None:
+        out = torch.empty(max(n * pitch, 16), dtype=torch.uint8, device=x.device)
+    if out.dtype != torch.uint8 or out.numel() < n * pitch:
+        raise ValueError("pack_rows: out must be a uint8 buffer of at least n_rows * pitch bytes")
+    ln = torch.empty(max(n, 1), dtype=torch.int32, device=x.device)[:n]
+    with _Timed("pack", d, float(n) * d * 4):
+        check(lib.lgnn_pack_rows_f32(ptr(x), x.stride(0), n, d, ptr(out), ptr(ln), stream()), "lgnn_pack_rows_f32")
+    _lib.count_launches(1)
+    return PackedRows(n, d, pitch, out, ln)
+
+
+def spmm_packed(a: CSR, pr: PackedRows, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Y = A @ unpack(pr); bit-identical to ``spmm(a, dense)``."""
+    lib = _lib.load()
+    if pr.n_rows < a.n_cols:
+        raise ValueError("spmm_packed: fewer packed rows than matrix columns")
+    if out is None:
+        out = torch.empty(a.n_rows, pr.d, dtype=torch.float32, device=pr.data.device)
+    _f32c(out, "out")
+    if out.shape[0] < a.n_rows or out.shape[1] < pr.d:
+        raise ValueError("spmm_packed: out too small")
+    # bytes: (col, val, len) per edge, rowptr, the live part of every gathered row, the dense output
+    work = lambda: (a.nnz * 12 + (a.n_rows + 1) * 8 + int(pr.len.to(torch.int64)[a.col.to(torch.int64)].sum())
+                    + a.n_rows * pr.d * 4)
+    with _Timed("spmm_packed", pr.d, work):
+        check(lib.lgnn_spmm_packed_f32(a.n_rows, a.nnz, ptr(a.rowptr), ptr(a.col), ptr(a.val), ptr(pr.data),
+                                       ptr(pr.len), pr.d, ptr(out), out.stride(0),
+                                       _lib.SPMM_NO_HUB_ROWS if a.max_row_nnz is not None and a.max_row_nnz <= 4096 else 0,
+                                       stream()), "lgnn_spmm_packed_f32")
+    _lib.count_launches(1)
+    return out
+
+
 # ------------------------------------------------------------------------------ loss / Hessian sqrt
 def softmax_ce_sum(logits: torch.Tensor, idx: torch.Tensor, y: torch.Tensor, C: int | None = None):
     """(sum CE as a 0-d float64 tensor, number of argmax hits as 0-d int64)."""

@@ -111,9 +111,21 @@ def csr_with_masked_sources(a, keep):
     return CSR(a.n_rows, a.n_cols, a.rowptr, a.col, val, a.max_row_nnz, masked=True)
 
 
+PACK_MAX_WIDTH = 4096
+
+
+def pack_rows_pitch(d):
+    nblk = (d + 127) // 128
+    return nblk * 16 + (nblk * 4 + 15) // 16 * 16 + nblk * 512
+
+
+def pack_rows(x, d=None, out=None):
+    raise AssertionError("the CPU double never packs (B200GGN packs on CUDA devices only)")
+
+
 def gemm_mask_supported(k, n):
     return False          # the CPU double keeps the two-step path (torch.mm + relu_mask_mul)
 
 
-ALL = ["gemm_mask_supported", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
+ALL = ["gemm_mask_supported", "pack_rows_pitch", "pack_rows", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
        "halo_columns", "csr_slice_remap", "spmm", "softmax_ce_sum", "hess_rhs", "relu_mask_mul", "syrk"]
