@@ -49,6 +49,7 @@ def parse_args():
                     help="multi-GPU layout of the KFAC backward (laplace_gnn_b200/dist.py)")
     ap.add_argument("--no-overlap", action="store_true", help="rows layout: one column group in flight instead of two")
     ap.add_argument("--no-fused-gemm", action="store_true", help="cuBLAS fp32 GEMM + mask kernel instead of the fused tcgen05 kernel")
+    ap.add_argument("--dense-slabs", action="store_true", help="keep the slabs below the output layer dense (no unit compaction)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-div", type=int, default=16,
@@ -229,7 +230,8 @@ def main():
     nnz = model.graph.nnz
     if args.no_e2e:
         del edge_index
-    bk = {"hess_sqrt": args.hess_sqrt, "syrk_impl": args.syrk, "fused_gemm": not args.no_fused_gemm}
+    bk = {"hess_sqrt": args.hess_sqrt, "syrk_impl": args.syrk, "fused_gemm": not args.no_fused_gemm,
+          "unit_slabs": not args.dense_slabs}
     if pg is not None:
         bk["process_group"] = pg
         bk["backward_parallel"] = args.backward_parallel
@@ -281,18 +283,23 @@ def main():
         for rec in prof:
             ms = rec["start"].elapsed_time(rec["end"])
             gk = (rec["kind"], rec["d"])
-            a = groups.setdefault(gk, {"ms": 0.0, "launches": 0, "bytes": 0.0})
+            a = groups.setdefault(gk, {"ms": 0.0, "launches": 0, "bytes": 0.0, "dense_bytes": 0.0})
             a["ms"] += ms
             a["launches"] += 1
             w = rec["bytes"]() if callable(rec["bytes"]) else rec["bytes"]
             a["bytes"] += w                      # algorithmic bytes (SpMM) or useful flops (SYRK / GEMM), summed
-        spmm_ms = sum(v["ms"] for (k, _), v in groups.items() if k == "spmm") / args.steps
+            a["dense_bytes"] += rec.get("dense_bytes", 0.0)
+        is_spmm = lambda k: k.startswith("spmm")
+        spmm_ms = sum(v["ms"] for (k, _), v in groups.items() if is_spmm(k)) / args.steps
         syrk_ms = sum(v["ms"] for (k, _), v in groups.items() if k == "syrk") / args.steps
         by_kind = {}
         for (k, _), v in groups.items():
             by_kind[k] = by_kind.get(k, 0.0) + v["ms"] / args.steps
-        # the dominant kernel is the multi-RHS SpMM; report the roofline of its widest launch group
-        spmm_groups = {kv[0]: kv[1] for kv in groups.items() if kv[0][0] == "spmm"}
+        # the dominant kernel is the multi-RHS SpMM; report the roofline of its heaviest launch group.
+        # "spmm_units" = the SpMM over unit-compacted slabs: its algorithmic bytes are the LIVE units of the
+        # gathered rows (+ headers, col / val, the dense output) — what the algorithm asks of HBM after the
+        # dead relu units are squeezed out; dense_equivalent is the same launch priced at the dense slab
+        spmm_groups = {kv[0]: kv[1] for kv in groups.items() if is_spmm(kv[0][0])}
         (kind, d), top = max(spmm_groups.items(), key=lambda kv: kv[1]["ms"])
         avg_ms = top["ms"] / top["launches"]
         achieved = top["bytes"] / (top["ms"] * 1e-3) / 1e9
@@ -301,7 +308,7 @@ def main():
         traffic, traffic_src = None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            ent = tj.get(f"{args.workload}:{args.scale}:{world}:spmm d={d}")
+            ent = tj.get(f"{args.workload}:{args.scale}:{world}:{kind} d={d}")
             if ent and ent.get("nnz") == nnz:
                 traffic, traffic_src = ent["dram_bytes_per_launch"], ent.get("source")
         except Exception:
@@ -314,6 +321,18 @@ def main():
                 "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
                 "spmm_ms_per_step": spmm_ms, "syrk_ms_per_step": syrk_ms,
                 "ms_per_step_by_kind": {k: round(v, 2) for k, v in sorted(by_kind.items())}}
+        if top["dense_bytes"] > 0:
+            roof["dense_equivalent"] = {
+                "bytes_per_launch": top["dense_bytes"] / top["launches"],
+                "gbs": top["dense_bytes"] / (top["ms"] * 1e-3) / 1e9,
+                "note": "the same launches priced at the uncompacted slab (SURVEY 8d B_spmm); exceeds the HBM "
+                        "peak because the dead units are never read"}
+        # every SpMM group, so that the dense launches (forward, output layer) stay visible
+        roof["spmm_groups"] = [
+            {"kernel": f"{k} d={dd}", "launches_per_step": v["launches"] / args.steps,
+             "avg_launch_ms": v["ms"] / v["launches"], "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
+             "frac": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / hbm_peak}
+            for (k, dd), v in sorted(spmm_groups.items(), key=lambda kv: -kv[1]["ms"]) if v["ms"] > 0]
         # secondary, tensor-bound kernels: useful TFLOP/s (3xTF32 issues 3x that) against the TF32 dense
         # peak taken as half the measured bf16 GEMM figure (MEASURED_PEAKS.json has no tf32 entry)
         tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
@@ -380,6 +399,7 @@ def main():
         "config": {"workload": workload_name(args.workload, h, l),
                    "nodes": n, "nnz": nnz, "features": f, "classes": c, "train_nodes": int(idx.numel()),
                    "hess_sqrt": args.hess_sqrt, "syrk": args.syrk, "scale": args.scale,
+                   "slabs": "dense" if args.dense_slabs else "unit-compacted below the output layer",
                    "l2": "inputs (>= 10 GB per SpMM) far exceed the 126 MB L2; no explicit flush",
                    "parallelism": "single GPU" if world == 1 else
                    f"row-partitioned x{world} (halo all-gather), backward over {args.backward_parallel}"},

@@ -152,6 +152,26 @@ int lgnn_spmm_packed_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr, con
                          const float* val, const void* packed, const int32_t* len, int64_t d, float* y,
                          int64_t ldy, int flags, lgnn_stream_t stream);
 
+/* Unit-compacted slabs.  delta[n, c, u] = (gZ W)[n, c, u] * 1[H[n, u] > 0] (curvlinops/kfac.py:653-661
+ * through the relu of gnn/models/base_gnn.py:150): the g Hessian-sqrt columns of a node share ONE zero
+ * pattern, that of the node's hidden units.  The slab row [g][h] of node n is rewritten in place as
+ * [active unit slot][g] (the g values of a live unit contiguous) with a header word per 32 units,
+ * hdr[n][w] = {uint32 mask, uint32 slot of the block's first live unit}; the SpMM then moves only the
+ * live units' bytes and adds them in the neighbour order of lgnn_spmm_f32 (bit-identical result).
+ * g in {4, 8, 12, 16}, h a multiple of 32 up to 1024 (lgnn_unit_slabs_supported).
+ *   lgnn_unit_pack_f32    slab [n_rows, lds] dense [g][h] rows -> compact, in place; act = H [n_rows, lda]
+ *                         decides which units live (values of dead units are dropped, whatever they hold);
+ *                         hdr: uint2 [n_rows, h/32]
+ *   lgnn_spmm_units_f32   Y[i, c*h + u] = sum_k val[k] * delta[col[k], c, u];  Y: [n_rows, ldy >= g*h] dense;
+ *                         n_cols = rows of the slab (columns of the matrix).
+ *                         Rows are walked whole by one warp per 32 units: meant for graphs without hub rows. */
+int lgnn_unit_slabs_supported(int64_t g, int64_t h);
+int lgnn_unit_pack_f32(float* slab, int64_t lds, const float* act, int64_t lda, int64_t n_rows, int64_t g,
+                       int64_t h, void* hdr, lgnn_stream_t stream);
+int lgnn_spmm_units_f32(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* rowptr, const int32_t* col,
+                        const float* val, const float* slab, int64_t lds, const void* hdr, int64_t g,
+                        int64_t h, float* y, int64_t ldy, int flags, lgnn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * loss + Hessian-sqrt right-hand sides
  * ---------------------------------------------------------------------------------------- */
@@ -172,6 +192,11 @@ int lgnn_softmax_ce_sum(const float* logits, int64_t ld, int32_t C, const int64_
 int lgnn_hess_rhs_f32(const float* logits, int64_t ld, int32_t C, const int64_t* idx, int64_t m,
                       int32_t c0, int32_t ncols, int32_t ldc, int mode, float* delta,
                       lgnn_stream_t stream);
+/* Same with an explicit row pitch ld_delta >= ncols*ldc (floats) of delta: column groups padded with
+ * all-zero right-hand sides (the unit-compacted slabs want a multiple of 4 columns per group). */
+int lgnn_hess_rhs_pitched_f32(const float* logits, int64_t ld, int32_t C, const int64_t* idx, int64_t m,
+                              int32_t c0, int32_t ncols, int32_t ldc, int64_t ld_delta, int mode,
+                              float* delta, lgnn_stream_t stream);
 
 /* out[k] = keep[col[k]] ? val[k] : 0 for the nnz entries of a CSR.  The right-hand sides injected at
  * the logits are zero outside the batch's train nodes (curvlinops/kfac.py:653-661 back-propagates

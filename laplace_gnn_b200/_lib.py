@@ -40,8 +40,12 @@ PROTOTYPES = {
     "lgnn_pack_rows_pitch": (_i64, [_i64]),
     "lgnn_pack_rows_f32": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "lgnn_spmm_packed_f32": (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
+    "lgnn_unit_slabs_supported": (C.c_int, [_i64, _i64]),
+    "lgnn_unit_pack_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "lgnn_spmm_units_f32": (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, C.c_int, _vp]),
     "lgnn_softmax_ce_sum": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
     "lgnn_hess_rhs_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, C.c_int, _vp, _vp]),
+    "lgnn_hess_rhs_pitched_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _i64, C.c_int, _vp, _vp]),
     "lgnn_mask_edge_values": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "lgnn_relu_mask_mul_f32": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i64, _vp]),
     "lgnn_gemm_mask_supported": (C.c_int, [_i64, _i64]),

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(HESS_THREADS) softmax_ce_sum_kernel(
 // warp per train sample.  Shared memory per warp: p[C], fc[C] (= f - fbar).
 __global__ void __launch_bounds__(HESS_THREADS) hess_rhs_kernel(
     const float* __restrict__ logits, int64_t ld, int C, const int64_t* __restrict__ idx, int64_t m,
-    int c0, int ncols, int ldc, int mode, float* __restrict__ delta) {
+    int c0, int ncols, int ldc, int64_t ld_delta, int mode, float* __restrict__ delta) {
   extern __shared__ float sh[];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   float* p = sh + (size_t)w * 2 * C;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(HESS_THREADS) hess_rhs_kernel(
     fbar = warp_sum(fbar);
     for (int k = lane; k < C; k += 32) fc[k] = f[k] - fbar;
     __syncwarp();
-    float* out = delta + node * (int64_t)ncols * ldc;
+    float* out = delta + node * ld_delta;
     for (int g = 0; g < ncols; ++g) {
       const int c = c0 + g;
       const float pc = p[c];
@@ -173,7 +173,14 @@ int lgnn_softmax_ce_sum(const float* logits, int64_t ld, int32_t C, const int64_
 int lgnn_hess_rhs_f32(const float* logits, int64_t ld, int32_t C, const int64_t* idx, int64_t m,
                       int32_t c0, int32_t ncols, int32_t ldc, int mode, float* delta,
                       lgnn_stream_t stream) {
-  if (!logits || !delta || C < 1 || ld < C || m < 0 || c0 < 0 || ncols < 0 || c0 + ncols > C || ldc < C)
+  return lgnn_hess_rhs_pitched_f32(logits, ld, C, idx, m, c0, ncols, ldc, (int64_t)ncols * ldc, mode, delta, stream);
+}
+
+int lgnn_hess_rhs_pitched_f32(const float* logits, int64_t ld, int32_t C, const int64_t* idx, int64_t m,
+                              int32_t c0, int32_t ncols, int32_t ldc, int64_t ld_delta, int mode,
+                              float* delta, lgnn_stream_t stream) {
+  if (!logits || !delta || C < 1 || ld < C || m < 0 || c0 < 0 || ncols < 0 || c0 + ncols > C || ldc < C ||
+      ld_delta < (int64_t)ncols * ldc)
     return fail(LGNN_E_BADARG, "hess_rhs: bad argument");
   if (mode != LGNN_HESS_REFERENCE && mode != LGNN_HESS_GGN) return fail(LGNN_E_BADARG, "hess_rhs: unknown mode %d", mode);
   if (m == 0 || ncols == 0) return LGNN_OK;
@@ -186,7 +193,7 @@ int lgnn_hess_rhs_f32(const float* logits, int64_t ld, int32_t C, const int64_t*
   int64_t cap = (int64_t)sm_count() * 8;
   if (blocks > cap) blocks = cap;
   hess_rhs_kernel<<<(unsigned)blocks, HESS_THREADS, smem, as_stream(stream)>>>(
-      logits, ld, C, idx, m, c0, ncols, ldc, mode, delta);
+      logits, ld, C, idx, m, c0, ncols, ldc, ld_delta, mode, delta);
   LGNN_LAUNCH_CHECK("hess_rhs_kernel");
   return LGNN_OK;
 }

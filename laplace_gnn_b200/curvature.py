@@ -116,7 +116,7 @@ class _B200KFAC:
 
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
-                    fused_gemm=True, cache_input_factor=False, _shared_cache=None):
+                    fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if backward_parallel not in ("rows", "columns"):
@@ -145,6 +145,11 @@ class _B200KFAC:
         # profiles/r1g_pack_lab.txt)
         self.pack_slabs = False
         self.pack_min_width = 1024
+        # unit-compacted slabs below the output layer (csrc/spmm_units.cu): the relu' mask is shared by all
+        # columns of a node, so the slab rows keep only their live hidden units and the SpMM gathers about
+        # half the bytes.  Column groups are then padded to a multiple of 4 with all-zero right-hand sides.
+        self.unit_slabs = bool(unit_slabs)
+        self.unit_min_width = 1024          # narrower slabs stay dense (one row is a few hundred bytes anyway)
         # A_0 = X^T X does not depend on the weights: with cache_input_factor the raw Gram matrix of
         # this rank's feature rows is kept (per backend, or in a dict shared across backends by the
         # epoch loop) and only rescaled per call
@@ -228,56 +233,76 @@ class _B200KFAC:
             cache[id(self.process_group)] = part
         return part
 
-    def _chain(self, lay, logits, idx, Hs, Ws, Wp, c0, gc, buf_a, buf_b, G):
+    def _chain(self, lay, logits, idx, Hs, Ws, Wp, c0, gc, gq, buf_a, buf_b, G, hdr=None):
         """One group of ``gc`` Hessian-sqrt columns pushed down all layers; a generator that yields
         after each layer so that two groups can be interleaved on two streams (their all-gathers
-        then overlap the other group's SpMM).
+        then overlap the other group's SpMM).  ``gq >= gc`` is the group's width in the slabs: the
+        columns beyond ``gc`` are all-zero right-hand sides (padding for the unit-compacted layout).
 
         ``buf_a`` / ``buf_b`` alternate as SpMM input / output.  Below the output layer the input slab
-        delta = (gZ W) ⊙ relu' is about half zeros: when every row is local (single GPU, or the
-        column-parallel backward) it is zero-compressed (``ops.pack_rows``) into the buffer the dead
-        gZ occupied, and the SpMM gathers only the non-zeros (``ops.spmm_packed``)."""
+        delta = (gZ W) ⊙ relu' is about half zeros, in a pattern the columns of a node share: when every
+        row is local (single GPU, or the column-parallel backward) it is compacted in place to the live
+        units of each node (``ops.unit_pack``, which applies the mask itself) and the SpMM gathers only
+        those (``ops.spmm_units``).  ``pack_slabs`` is the older per-element compression (off)."""
         L = len(Ws)
         C = logits.shape[1]
         dims = [w.shape[0] for w in Ws]                 # d_1 .. d_L (d_L = C)
         c_pad = (C + 3) // 4 * 4
         n_loc, n_in, slot0 = lay.n_local, lay.total_rows, lay.slot0
         P, Q = buf_a, buf_b                             # P: SpMM input, Q: SpMM output
-        slab = P[: n_in * gc * c_pad].view(n_in, gc * c_pad)
+        slab = P[: n_in * gq * c_pad].view(n_in, gq * c_pad)
         delta = slab[slot0:slot0 + n_loc]
         with ops.timed("hess_rhs", gc):
             delta.zero_()
             ops.hess_rhs(logits, idx, c0, gc, delta, c_pad, self.hess_sqrt)
         width, ld = C, c_pad
-        packed = None
+        packed = units = None
         for l in range(L - 1, -1, -1):
-            gz = Q[: n_loc * gc * ld].view(n_loc, gc * ld)
-            if packed is not None:
+            gz = Q[: n_loc * gq * ld].view(n_loc, gq * ld)
+            if units is not None:
+                ops.spmm_units(lay.csr_t, units, out=gz)
+                self._n_unit_spmm += 1
+            elif packed is not None:
                 ops.spmm_packed(lay.csr_t, packed, out=gz)
             else:
-                with ops.timed("allgather", gc * ld, 4.0 * n_in * gc * ld):
+                with ops.timed("allgather", gq * ld, 4.0 * n_in * gq * ld):
                     lay.gather(slab)
                 # output layer: the slab is zero outside the batch's train rows -> no gather for those edges
                 ops.spmm(lay.csr_t_top if (l == L - 1 and lay.csr_t_top is not None) else lay.csr_t, slab, out=gz)
-            gz_rows = gz.view(n_loc * gc, ld)
+            gz_rows = gz.view(n_loc * gq, ld)
             ops.syrk(gz_rows, n=width, alpha=1.0, beta=1.0, out=G[l], impl=self._impl(width))
             if l > 0:
                 d_prev = dims[l - 1]
-                slab = P[: n_in * gc * d_prev].view(n_in, gc * d_prev)
-                nxt = slab[slot0:slot0 + n_loc].view(n_loc * gc, d_prev)
-                if Wp[l] is not None:      # fused 3xTF32 tensor-core GEMM + relu' mask
-                    ops.gemm_mask(gz_rows, Wp[l], Hs[l], gc, out=nxt, m_rows=n_loc * gc)
+                slab = P[: n_in * gq * d_prev].view(n_in, gq * d_prev)
+                nxt = slab[slot0:slot0 + n_loc].view(n_loc * gq, d_prev)
+                to_units = hdr is not None and self._can_unit(lay, gq, d_prev)
+                act = None if to_units else Hs[l]           # unit_pack drops the dead units: no mask needed
+                if Wp[l] is not None:      # fused 3xTF32 tensor-core GEMM (+ relu' mask)
+                    ops.gemm_mask(gz_rows, Wp[l], act, gq, out=nxt, m_rows=n_loc * gq)
                 else:                      # shapes the fused kernel does not take: cuBLAS + mask kernel
-                    with ops.timed("gemm_bwd", d_prev, 2.0 * n_loc * gc * width * d_prev):
+                    with ops.timed("gemm_bwd", d_prev, 2.0 * n_loc * gq * width * d_prev):
                         torch.mm(gz_rows[:, :width], Ws[l], out=nxt)
-                    with ops.timed("relu_mask", d_prev, 2.0 * n_loc * gc * d_prev * 4):
-                        ops.relu_mask_mul(nxt, Hs[l], gc)
+                    if act is not None:
+                        with ops.timed("relu_mask", d_prev, 2.0 * n_loc * gq * d_prev * 4):
+                            ops.relu_mask_mul(nxt, act, gq)
                 width, ld = d_prev, d_prev
-                packed = None
-                if self._can_pack(lay, gc * d_prev):
-                    packed = ops.pack_rows(slab, gc * d_prev, out=Q.view(torch.uint8))   # gZ in Q is dead
+                packed = units = None
+                if to_units:
+                    units = ops.unit_pack(slab, Hs[l], gq, hdr=hdr)
+                elif self._can_pack(lay, gq * d_prev):
+                    packed = ops.pack_rows(slab, gq * d_prev, out=Q.view(torch.uint8))   # gZ in Q is dead
                     P, Q = Q, P            # the packed slab is the next input, the dense one the next output
             yield
+
+    def _units_possible(self, lay) -> bool:
+        """Unit-compacted slabs need every row local and a graph without hub rows (the kernel gives one
+        warp a whole row)."""
+        mx = lay.csr_t.max_row_nnz
+        return self.unit_slabs and not lay.communicates and mx is not None and mx <= 4096
+
+    def _can_unit(self, lay, g: int, h: int) -> bool:
+        return (self._units_possible(lay) and g * h >= self.unit_min_width and
+                ops.unit_slabs_supported(g, h))
 
     def _can_pack(self, lay, width: int) -> bool:
         # narrow slabs stay dense: the ring kernel needs multi-KB copies to reach the HBM roofline
@@ -295,15 +320,25 @@ class _B200KFAC:
         dev = logits.device
         n_loc, n_in = lay.n_local, lay.total_rows
         lanes = 2 if (self.overlap and lay.communicates and dev.type == "cuda") else 1
-        grp = self._group_size(lanes * n_in, lanes * n_loc, dmax, C, dev)
+        room = self._group_size(lanes * n_in, lanes * n_loc, dmax, 1 << 30, dev)   # columns the HBM budget allows
+        grp = min(room, C)
         hidden = max(dims[:-1]) if len(dims) > 1 else 0
         can_pack = self.pack_slabs and not lay.communicates and dev.type == "cuda" and 0 < hidden <= ops.PACK_MAX_WIDTH
         if can_pack:                       # keep the hidden-layer slabs narrow enough for the packed SpMM
             grp = min(grp, max(1, ops.PACK_MAX_WIDTH // hidden))
         grp = lay.agree_min(max(1, min(grp, (c_count + lanes - 1) // lanes)))
+        # unit-compacted slabs want groups of 4, 8, 12 or 16 columns: the last group of a pass is padded
+        # with all-zero right-hand sides (47 classes -> 12 + 12 + 12 + 11(+1))
+        cand = min(room // 4 * 4, 16, (max(c_count, 1) + 3) // 4 * 4)
+        pad4 = (self._units_possible(lay) and not can_pack and cand >= 4 and
+                any(self._can_unit(lay, cand, h) for h in dims[:-1]))
+        if pad4:
+            grp = cand
         if c_count <= 0:
             return grp, 0
         groups = [(c0, min(grp, c_first + c_count - c0)) for c0 in range(c_first, c_first + c_count, grp)]
+        width_of = (lambda gc: (gc + 3) // 4 * 4) if pad4 else (lambda gc: gc)
+        hdr = torch.empty(n_in, max(max(dims[:-1]) // 32, 1), 2, dtype=torch.int32, device=dev) if pad4 else None
         # W_l [d_l, d_{l-1}] as resident tensor-core operands, once per pass
         Wp = [None] + [ops.gemm_mask_prepare(Ws[l]) if self.fused_gemm and dev.type == "cuda" and
                        ops.gemm_mask_supported(Ws[l].shape[0], Ws[l].shape[1]) else None
@@ -318,7 +353,7 @@ class _B200KFAC:
                 for _ in range(lanes)]
         if lanes == 1:
             for c0, gc in groups:
-                for _ in self._chain(lay, logits, idx, Hs, Ws, Wp, c0, gc, bufs[0][0], bufs[0][1], G):
+                for _ in self._chain(lay, logits, idx, Hs, Ws, Wp, c0, gc, width_of(gc), bufs[0][0], bufs[0][1], G, hdr):
                     pass
             return grp, len(groups)
         # two column groups in flight, each on its own stream with its own buffers and factor
@@ -335,7 +370,7 @@ class _B200KFAC:
                 with torch.cuda.stream(streams[i]):
                     if active[i] is None and pending:
                         c0, gc = pending.pop(0)
-                        active[i] = self._chain(lay, logits, idx, Hs, Ws, Wp, c0, gc, bufs[i][0], bufs[i][1], G_lane[i])
+                        active[i] = self._chain(lay, logits, idx, Hs, Ws, Wp, c0, gc, gc, bufs[i][0], bufs[i][1], G_lane[i])
                     if active[i] is not None:
                         try:
                             next(active[i])
@@ -390,6 +425,7 @@ class _B200KFAC:
 
         # output-side factors G_l: multi-RHS backward in groups of Hessian-sqrt columns
         G = [torch.zeros(w.shape[0], w.shape[0], dtype=torch.float32, device=dev) for w in Ws]
+        self._n_unit_spmm = 0
         whole = _Whole(g)
         if self.skip_zero_rows and (part is None or self.backward_parallel == "columns") and M < g.n:
             keep = torch.zeros(g.n, dtype=torch.uint8, device=dev)
@@ -421,7 +457,7 @@ class _B200KFAC:
                 part.all_reduce_sum([loss])
         self.last_stats = {"group": grp, "n_groups": n_groups, "M": M, "C": C,
                            "world": 1 if part is None else part.world,
-                           "partition": part}
+                           "partition": part, "unit_slabs": self._n_unit_spmm}
 
         Kron = _kron_class()
         kfacs = []
@@ -456,7 +492,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  dict_key_x="input_ids", dict_key_y="labels", stochastic=False,
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
-                 fused_gemm=True, cache_input_factor=False, _shared_cache=None):
+                 fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -466,7 +502,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                           dict_key_y, stochastic)
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
-                         backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache)
+                         backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

@@ -269,6 +269,76 @@ def spmm_packed(a: CSR, pr: PackedRows, out: torch.Tensor | None = None) -> torc
     return out
 
 
+# ------------------------------------------------------------------------------ unit-compacted slabs
+@dataclass
+class UnitSlab:
+    """Slab [n_rows, g*h] whose rows hold only the live hidden units of their node, as [slot][g]
+    (csrc/spmm_units.cu); ``hdr`` [n_rows, h/32, 2] int32 = (mask, first slot) per 32 units; ``act`` is
+    the activation matrix that decided which units live (kept for the byte accounting only)."""
+    n_rows: int
+    g: int
+    h: int
+    slab: torch.Tensor
+    hdr: torch.Tensor
+    act: torch.Tensor | None = None
+    _live: torch.Tensor | None = None
+
+    def live_units(self) -> torch.Tensor:
+        """int64 [n_rows]: live units per node (profiling only; evaluated outside timed regions)."""
+        if self._live is None:
+            self._live = (self.act[:, : self.h] > 0).sum(1)
+        return self._live
+
+
+def unit_slabs_supported(g: int, h: int) -> bool:
+    return bool(_lib.load().lgnn_unit_slabs_supported(int(g), int(h)))
+
+
+def unit_pack(slab: torch.Tensor, act: torch.Tensor, g: int, hdr: torch.Tensor | None = None) -> UnitSlab:
+    """Compact the dense rows [g][h] of ``slab`` ([n_rows, >= g*h], h = act.shape[1]) IN PLACE: units with
+    act[n, u] <= 0 are dropped, whatever the slab holds there."""
+    lib = _lib.load()
+    _f32c(slab, "slab"); _f32c(act, "act")
+    n, h = int(act.shape[0]), int(act.shape[1])
+    if slab.shape[0] < n or slab.shape[1] < g * h:
+        raise ValueError("unit_pack: slab smaller than [act rows, g*h]")
+    if hdr is None:
+        hdr = torch.empty(max(n, 1), h // 32, 2, dtype=torch.int32, device=slab.device)
+    if hdr.dtype != torch.int32 or hdr.numel() < n * (h // 32) * 2 or not hdr.is_contiguous():
+        raise ValueError("unit_pack: hdr must be a contiguous int32 buffer of n_rows * h/32 * 2 entries")
+    with _Timed("unit_pack", g * h, float(n) * h * (g * 6 + 4)):     # dense read + ~half written back + act
+        check(lib.lgnn_unit_pack_f32(ptr(slab), slab.stride(0), ptr(act), act.stride(0), n, int(g), h, ptr(hdr),
+                                     stream()), "lgnn_unit_pack_f32")
+    _lib.count_launches(1)
+    return UnitSlab(n, int(g), h, slab, hdr, act)
+
+
+def spmm_units(a: CSR, us: UnitSlab, out: torch.Tensor | None = None, variant: int = 0) -> torch.Tensor:
+    """Y = A @ dense(us), Y: [n_rows, g*h] dense; bit-identical to ``spmm(a, dense slab)``."""
+    lib = _lib.load()
+    if us.n_rows < a.n_cols:
+        raise ValueError("spmm_units: fewer slab rows than matrix columns")
+    d = us.g * us.h
+    if out is None:
+        out = torch.empty(a.n_rows, d, dtype=torch.float32, device=us.slab.device)
+    _f32c(out, "out")
+    if out.shape[0] < a.n_rows or out.shape[1] < d:
+        raise ValueError("spmm_units: out too small")
+    # bytes actually asked of HBM: (col, val) + one header row per edge, rowptr, the live units of every
+    # gathered row, the dense output
+    nblk = us.h // 32
+    work = lambda: (a.nnz * (8 + 8 * nblk) + (a.n_rows + 1) * 8 + a.n_rows * d * 4
+                    + int(us.live_units()[a.col.to(torch.int64)].sum()) * us.g * 4)
+    with _Timed("spmm_units", d, work) as rec:
+        check(lib.lgnn_spmm_units_f32(a.n_rows, us.n_rows, a.nnz, ptr(a.rowptr), ptr(a.col), ptr(a.val), ptr(us.slab),
+                                      us.slab.stride(0), ptr(us.hdr), us.g, us.h, ptr(out), out.stride(0),
+                                      (int(variant) & 0xff) << 8, stream()), "lgnn_spmm_units_f32")
+    if rec.rec is not None:
+        rec.rec["dense_bytes"] = spmm_algorithmic_bytes(a.n_rows, a.nnz, d)
+    _lib.count_launches(1)
+    return out
+
+
 # ------------------------------------------------------------------------------ loss / Hessian sqrt
 def softmax_ce_sum(logits: torch.Tensor, idx: torch.Tensor, y: torch.Tensor, C: int | None = None):
     """(sum CE as a 0-d float64 tensor, number of argmax hits as 0-d int64)."""
@@ -289,7 +359,8 @@ def softmax_ce_sum(logits: torch.Tensor, idx: torch.Tensor, y: torch.Tensor, C: 
 
 def hess_rhs(logits: torch.Tensor, idx: torch.Tensor, c0: int, ncols: int, delta: torch.Tensor,
              ldc: int, mode: str = "reference", C: int | None = None) -> torch.Tensor:
-    """Scatter-add the Hessian-sqrt columns [c0, c0+ncols) into delta ([n_nodes, ncols*ldc], zeroed)."""
+    """Scatter-add the Hessian-sqrt columns [c0, c0+ncols) into delta ([n_nodes, >= ncols*ldc], zeroed;
+    a wider row leaves all-zero padding columns behind the group)."""
     lib = _lib.load()
     _f32c(logits, "logits")
     C = int(logits.shape[1]) if C is None else int(C)
@@ -297,8 +368,9 @@ def hess_rhs(logits: torch.Tensor, idx: torch.Tensor, c0: int, ncols: int, delta
     if m is None:
         raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {mode!r}")
     idx = idx.contiguous()
-    check(lib.lgnn_hess_rhs_f32(ptr(logits), logits.stride(0), C, ptr(idx), idx.numel(), c0, ncols, ldc, m,
-                                ptr(delta), stream()), "lgnn_hess_rhs_f32")
+    _f32c(delta, "delta")
+    check(lib.lgnn_hess_rhs_pitched_f32(ptr(logits), logits.stride(0), C, ptr(idx), idx.numel(), c0, ncols, ldc,
+                                        delta.stride(0), m, ptr(delta), stream()), "lgnn_hess_rhs_pitched_f32")
     _lib.count_launches(1)
     return delta
 

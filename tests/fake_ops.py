@@ -80,7 +80,7 @@ def softmax_ce_sum(logits, idx, y, C=None):
 def hess_rhs(logits, idx, c0, ncols, delta, ldc, mode="reference", C=None):
     C = logits.shape[1] if C is None else C
     V = O.hess_sqrt_rhs(logits[idx][:, :C], mode)          # [m, C(col), C]
-    d3 = delta.view(delta.shape[0], ncols, ldc)
+    d3 = delta.view(delta.shape[0], -1, ldc)             # a wider row = zero padding columns behind the group
     for g in range(ncols):
         d3[:, g, :C].index_add_(0, idx, V[:, c0 + g, :])
     return delta
@@ -123,9 +123,34 @@ def pack_rows(x, d=None, out=None):
     raise AssertionError("the CPU double never packs (B200GGN packs on CUDA devices only)")
 
 
+def unit_slabs_supported(g, h):
+    return 4 <= g <= 16 and g % 4 == 0 and 32 <= h <= 1024 and h % 32 == 0
+
+
+def unit_pack(slab, act, g, hdr=None):
+    """Same in-place [live unit slot][g] layout as csrc/spmm_units.cu (header words left to the GPU test)."""
+    from laplace_gnn_b200.ops import UnitSlab
+    n, h = act.shape
+    live = act > 0
+    dense = slab[:n, : g * h].reshape(n, g, h).clone()
+    order = torch.argsort((~live).to(torch.int8), dim=1, stable=True)       # live units first, ascending
+    comp = torch.gather(dense.permute(0, 2, 1), 1, order[:, :, None].expand(n, h, g))   # [n, slot, g]
+    slab[:n, : g * h] = comp.reshape(n, g * h)           # slots beyond the live count hold garbage, never read
+    return UnitSlab(n, g, h, slab, hdr if hdr is not None else torch.zeros(n, h // 32, 2, dtype=torch.int32), act)
+
+
+def spmm_units(a, us, out=None, variant=0):
+    n, g, h = us.n_rows, us.g, us.h
+    live = us.act[:, :h] > 0
+    slot = (torch.cumsum(live, 1) - 1).clamp(min=0)
+    comp = us.slab[:n, : g * h].reshape(n, h, g)
+    dense = (torch.gather(comp, 1, slot[:, :, None].expand(n, h, g)) * live[:, :, None]).permute(0, 2, 1)
+    return spmm(a, dense.reshape(n, g * h).contiguous(), out=out)
+
+
 def gemm_mask_supported(k, n):
     return False          # the CPU double keeps the two-step path (torch.mm + relu_mask_mul)
 
 
-ALL = ["gemm_mask_supported", "pack_rows_pitch", "pack_rows", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
+ALL = ["unit_slabs_supported", "unit_pack", "spmm_units", "gemm_mask_supported", "pack_rows_pitch", "pack_rows", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
        "halo_columns", "csr_slice_remap", "spmm", "softmax_ce_sum", "hess_rhs", "relu_mask_mul", "syrk"]

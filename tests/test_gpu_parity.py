@@ -537,3 +537,133 @@ def test_packed_backward_gives_the_same_factors():
         for a, b in zip(fa, fb):
             assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-6
     check_against_golden(g, l1, k1.kfacs, torch.tensor(g.marglik))
+
+
+# ---------------------------------------------------------------------------------- unit-compacted slabs
+def _masked_slab(n, g, h, density, seed, pitch_extra=0):
+    gen = torch.Generator(device=DEV).manual_seed(seed)
+    act = torch.randn(n, h, device=DEV, generator=gen)
+    act *= (torch.rand(n, h, device=DEV, generator=gen) < density)          # <= 0 <-> dead unit
+    act[3] = 0                                                              # a node with no live unit
+    if n > 5:
+        act[5] = 1                                                          # ... and one with all of them
+    slab = torch.randn(n, g * h + pitch_extra, device=DEV, generator=gen)
+    slab[:, : g * h].view(n, g, h).mul_((act > 0)[:, None, :])
+    return slab, act
+
+
+@pytest.mark.parametrize("g,h", [(4, 32), (8, 64), (12, 256), (16, 256), (12, 96), (4, 1024)])
+@pytest.mark.parametrize("density", [0.0, 0.5, 1.0])
+def test_unit_pack_layout(g, h, density):
+    """lgnn_unit_pack_f32: header words and the in-place [slot][g] layout, against a numpy restatement."""
+    ops = _ops()
+    n = 257
+    slab, act = _masked_slab(n, g, h, density, seed=g * 1000 + h, pitch_extra=4)
+    dense = slab[:, : g * h].view(n, g, h).cpu().numpy().copy()
+    live = (act > 0).cpu().numpy()
+    us = ops.unit_pack(slab, act, g)
+    hdr = us.hdr.cpu().numpy().view(np.uint32)
+    out = slab.cpu().numpy()
+    for r in range(n):
+        units = np.nonzero(live[r])[0]
+        first = 0
+        for w in range(h // 32):
+            blk = live[r, 32 * w: 32 * w + 32]
+            mask = int(sum(1 << i for i in range(32) if blk[i]))
+            assert hdr[r, w, 0] == mask and hdr[r, w, 1] == first
+            first += int(blk.sum())
+        want = dense[r][:, units].T.reshape(-1)                   # [slot][g]
+        assert np.array_equal(out[r, : want.size], want)
+    assert us.live_units().cpu().numpy().tolist() == live.sum(1).tolist()
+
+
+@pytest.mark.parametrize("g,h", [(4, 32), (8, 64), (12, 256), (16, 256), (12, 96), (8, 512)])
+@pytest.mark.parametrize("density", [0.0, 0.5, 1.0])
+def test_unit_spmm_is_bit_identical_to_dense(g, h, density):
+    """unit_pack + spmm_units against the dense SpMM of the same masked slab: identical bits (same
+    neighbour order, dead units are the dense kernel's multiplications by zero); every unroll variant."""
+    ops = _ops()
+    n = 5000
+    ei = O.synthetic_edges(n, 40_000, seed=g + h)
+    G = _dev_graph(ei, n)
+    slab, act = _masked_slab(n, g, h, density, seed=g * 7 + h, pitch_extra=8)
+    dense = ops.spmm(G.ahat, slab, d=g * h, impl="ldg")
+    us = ops.unit_pack(slab, act, g)
+    for variant in [0, 1] + list(range(8, 16)):      # default, simple kernel, every staged configuration
+        y = ops.spmm_units(G.ahat, us, variant=variant)
+        assert torch.equal(y, dense), variant
+    # rows of a directed pattern (Â^T != Â) and an output with a wider pitch
+    out = torch.full((n, g * h + 12), -1.0, device=DEV)
+    ops.spmm_units(G.ahat_t, us, out=out)
+    assert torch.equal(out[:, : g * h], ops.spmm(G.ahat_t, _unpack(us), impl="ldg"))
+    assert bool((out[:, g * h:] == -1).all())
+
+
+def _unpack(us):
+    """Dense [n, g*h] slab of a UnitSlab (test helper, torch on the device)."""
+    n, g, h = us.n_rows, us.g, us.h
+    live = us.act[:, :h] > 0
+    slot = torch.cumsum(live, 1) - 1                                        # slot of each live unit
+    comp = us.slab[:, : g * h].reshape(n, h, g)                             # [slot][g] (tail unused)
+    vals = torch.gather(comp, 1, slot.clamp(min=0)[:, :, None].expand(n, h, g))
+    return (vals * live[:, :, None]).permute(0, 2, 1).reshape(n, g * h).contiguous()
+
+
+def test_unit_slab_arguments_are_checked():
+    ops = _ops()
+    from laplace_gnn_b200._lib import LgnnError
+    assert ops.unit_slabs_supported(12, 256) and ops.unit_slabs_supported(16, 1024)
+    assert not ops.unit_slabs_supported(11, 256) and not ops.unit_slabs_supported(12, 100)
+    assert not ops.unit_slabs_supported(20, 256) and not ops.unit_slabs_supported(4, 2048)
+    slab, act = _masked_slab(64, 4, 48, 0.5, seed=1)                        # h = 48: not a multiple of 32
+    with pytest.raises(LgnnError):
+        ops.unit_pack(slab, act, 4, hdr=torch.empty(64, 2, 2, dtype=torch.int32, device=DEV))
+
+
+def test_unit_compacted_backward_gives_the_same_factors():
+    """The KFAC backward with unit-compacted slabs below the output layer against the dense slabs:
+    same loss, factors equal to rounding of the SYRK's zero-padded column groups, reference goldens."""
+    import laplace_gnn_b200 as L
+    for name in ("pubmed_shape", "tiny_directed_3l"):
+        g = Golden(name)
+        model = build_model(g, DEV)
+        idx, y = torch.from_numpy(g.idx).to(DEV), torch.from_numpy(g.y).to(DEV)
+        be1 = L.B200GGN(model, "classification", unit_slabs=True)
+        be1.unit_min_width = 0
+        be2 = L.B200GGN(model, "classification", unit_slabs=False)
+        l1, k1 = be1.kron(idx, y, N=len(y))
+        l2, k2 = be2.kron(idx, y, N=len(y))
+        if g.h % 32 == 0:
+            assert be1.last_stats["unit_slabs"] > 0, name
+        assert float(l1) == float(l2)
+        for fa, fb in zip(k1.kfacs, k2.kfacs):
+            for a, b in zip(fa, fb):
+                assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 2e-6
+        check_against_golden(g, l1, k1.kfacs, torch.tensor(g.marglik))
+
+
+@pytest.mark.parametrize("h,C,layers", [(64, 10, 3), (256, 47, 3), (128, 6, 2)])
+def test_unit_compacted_backward_products_like_shapes(h, C, layers):
+    """Same comparison on synthetic models whose hidden widths take the fused tcgen05 GEMM (no mask in
+    its epilogue when unit_pack follows) and whose class count needs a zero-padded last group."""
+    import laplace_gnn_b200 as L
+    n, U, F = 3000, 15_000, 20
+    ei = torch.from_numpy(O.synthetic_edges(n, U, seed=h + C)).to(DEV)
+    graph = L.Graph.from_edge_index(ei, n)
+    gen = torch.Generator().manual_seed(h)
+    X = torch.randn(n, F, generator=gen).to(DEV)
+    torch.manual_seed(C)
+    model = L.SparseGCN(F, h, C, layers, X, graph).to(DEV)
+    idx = torch.randperm(n, generator=gen)[: int(0.6 * n)].sort().values.to(DEV)
+    y = torch.randint(0, C, (idx.numel(),), generator=gen).to(DEV)
+    res = []
+    for units in (True, False):
+        be = L.B200GGN(model, "classification", unit_slabs=units)
+        be.unit_min_width = 0
+        loss, kron = be.kron(idx, y, N=len(y))
+        assert (be.last_stats["unit_slabs"] > 0) == units
+        res.append((float(loss), kron.kfacs))
+    assert res[0][0] == res[1][0]
+    for fa, fb in zip(res[0][1], res[1][1]):
+        for a, b in zip(fa, fb):
+            assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 2e-6

@@ -250,3 +250,36 @@ def test_knn_graph_and_graph_cache(fake_ops, tmp_path):
     g2 = L.load_graph(path, "cpu")
     assert g2.n == g.n and torch.equal(g2.ahat.rowptr, g.ahat.rowptr) and torch.equal(g2.ahat.col, g.ahat.col)
     assert torch.equal(g2.ahat.val, g.ahat.val) and g2.ahat_t is g2.ahat
+
+
+def _synthetic_model(n, U, F, h, C, layers, device="cpu", seed=0):
+    import laplace_gnn_b200 as L
+    from oracle import gcn_kfac_oracle as O
+    ei = torch.from_numpy(O.synthetic_edges(n, U, seed=seed)).to(device)
+    graph = L.Graph.from_edge_index(ei, n)
+    gen = torch.Generator().manual_seed(seed)
+    X = torch.randn(n, F, generator=gen).to(device)
+    torch.manual_seed(seed)
+    model = L.SparseGCN(F, h, C, layers, X, graph).to(device)
+    idx = torch.randperm(n, generator=gen)[: int(0.6 * n)].sort().values.to(device)
+    y = torch.randint(0, C, (idx.numel(),), generator=gen).to(device)
+    return model, idx, y
+
+
+@pytest.mark.parametrize("C,layers,budget", [(10, 3, None), (5, 2, None), (10, 3, 600 * 64 * 4 * 2 * 5)])
+def test_unit_compacted_groups_give_the_same_factors(fake_ops, C, layers, budget):
+    """Column groups padded to multiples of 4 + the in-place unit-compacted slab layout (CPU double of
+    csrc/spmm_units.cu) against the dense slabs: 10 classes -> groups 8 + 2(+2) or 4 + 4 + 2(+2)."""
+    import laplace_gnn_b200 as L
+    model, idx, y = _synthetic_model(600, 2400, 12, 64, C, layers)
+    be1 = L.B200GGN(model, "classification", unit_slabs=True, rhs_tile_bytes=budget)
+    be1.unit_min_width = 0
+    be2 = L.B200GGN(model, "classification", unit_slabs=False, rhs_tile_bytes=budget)
+    l1, k1 = be1.kron(idx, y, N=len(y))
+    l2, k2 = be2.kron(idx, y, N=len(y))
+    assert be1.last_stats["unit_slabs"] == (layers - 1) * be1.last_stats["n_groups"] > 0
+    assert be1.last_stats["group"] % 4 == 0 and be2.last_stats["unit_slabs"] == 0
+    assert float(l1) == float(l2)
+    for fa, fb in zip(k1.kfacs, k2.kfacs):
+        for a, b in zip(fa, fb):
+            assert max_rel_err(a.numpy(), b.numpy()) <= 1e-5
