@@ -10,6 +10,8 @@
 // of a gathered row that different warps touch are adjacent in DRAM.
 //
 // Algorithmic bytes per launch:  nnz*(4+4) + (n_rows+1)*8 + nnz*d*4 + n_rows*d*4.
+#include <limits.h>
+
 #include "common.cuh"
 #include "spmm_internal.cuh"
 
@@ -475,15 +477,35 @@ extern "C" int lgnn_spmm_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr,
       if (hub_blocks > 0)
         spmm_hub_kernel<2, 4><<<dim3((unsigned)hub_blocks, 1), SPMM_THREADS, 0, st>>>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4);
     } else {
-      int n_chunks = (d4 + 127) / 128;
+      // one warp per (row, chunk of VEC*32 float4): pick the chunk width that leaves the fewest idle lane
+      // slots in the last chunk (d = 576: one chunk of 160 float4 instead of 128 + a warp that walks the
+      // whole row for 16); ties go to VEC = 4, the width the wide slabs were tuned on
+      static const int cand[4] = {4, 5, 6, 3};
+      int vec = 4, best = INT32_MAX;
+      for (int i = 0; i < 4; ++i) {
+        const int slots = (d4 + cand[i] * 32 - 1) / (cand[i] * 32) * cand[i] * 32;
+        if (slots < best) { best = slots; vec = cand[i]; }
+      }
+      const int n_chunks = (d4 + vec * 32 - 1) / (vec * 32);
       int64_t warps = n_rows * n_chunks;
       int64_t blocks = (warps + warps_per_block - 1) / warps_per_block;
       if (blocks > 0x7fffffffLL) return fail(LGNN_E_UNSUPPORTED, "spmm: grid too large");
       if (n_chunks > 65535) return fail(LGNN_E_UNSUPPORTED, "spmm: d too large");
-      spmm_vec_kernel<4, 2><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(
-          n_rows, rowptr, col, val, x, ldx, y, ldy, d4, n_chunks, hub_len, epi);
-      if (hub_blocks > 0)
-        spmm_hub_kernel<4, 2><<<dim3((unsigned)hub_blocks, (unsigned)n_chunks), SPMM_THREADS, 0, st>>>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4);
+#define LGNN_VEC_LAUNCH(VEC_)                                                                                    \
+  do {                                                                                                           \
+    spmm_vec_kernel<VEC_, 2><<<(unsigned)blocks, SPMM_THREADS, 0, st>>>(n_rows, rowptr, col, val, x, ldx, y, ldy,  \
+                                                                        d4, n_chunks, hub_len, epi);             \
+    if (hub_blocks > 0)                                                                                          \
+      spmm_hub_kernel<VEC_, 2><<<dim3((unsigned)hub_blocks, (unsigned)n_chunks), SPMM_THREADS, 0, st>>>(           \
+          n_rows, rowptr, col, val, x, ldx, y, ldy, d4);                                                         \
+  } while (0)
+      switch (vec) {
+        case 3: LGNN_VEC_LAUNCH(3); break;
+        case 5: LGNN_VEC_LAUNCH(5); break;
+        case 6: LGNN_VEC_LAUNCH(6); break;
+        default: LGNN_VEC_LAUNCH(4); break;
+      }
+#undef LGNN_VEC_LAUNCH
     }
     if (hub_blocks > 0 && epi) {
       spmm_relu_hub_rows_kernel<<<(unsigned)zb, 256, 0, st>>>(n_rows, rowptr, LDG_HUB_LEN, y, ldy, d4);

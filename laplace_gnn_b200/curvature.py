@@ -116,7 +116,8 @@ class _B200KFAC:
 
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
-                    fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True):
+                    fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
+                    unit_min_width=1024):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if backward_parallel not in ("rows", "columns"):
@@ -149,7 +150,7 @@ class _B200KFAC:
         # columns of a node, so the slab rows keep only their live hidden units and the SpMM gathers about
         # half the bytes.  Column groups are then padded to a multiple of 4 with all-zero right-hand sides.
         self.unit_slabs = bool(unit_slabs)
-        self.unit_min_width = 1024          # narrower slabs stay dense (one row is a few hundred bytes anyway)
+        self.unit_min_width = int(unit_min_width)   # narrower slabs stay dense (one row is a few hundred bytes anyway)
         # A_0 = X^T X does not depend on the weights: with cache_input_factor the raw Gram matrix of
         # this rank's feature rows is kept (per backend, or in a dict shared across backends by the
         # epoch loop) and only rescaled per call
@@ -492,7 +493,8 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  dict_key_x="input_ids", dict_key_y="labels", stochastic=False,
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
-                 fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True):
+                 fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
+                 unit_min_width=1024):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -502,7 +504,8 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                           dict_key_y, stochastic)
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
-                         backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs)
+                         backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs,
+                         unit_min_width)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

@@ -66,6 +66,45 @@ def test_partitioned_fit_matches_reference_golden(world, mode, name):
         assert abs(vals[0] - Golden(name).marglik) <= 1e-3 * abs(Golden(name).marglik)
 
 
+def _unit_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import fake_ops as F
+        import laplace_gnn_b200 as L
+        import laplace_gnn_b200.ops as ops
+        for n in F.ALL:
+            setattr(ops, n, getattr(F, n))
+        from test_host_logic import _synthetic_model
+        model, idx, y = _synthetic_model(500, 2000, 10, 32, 10, 3)
+        ref = L.B200GGN(model, "classification", unit_slabs=False).kron(idx, y, N=len(y))
+        for mode in ("columns", "rows"):
+            be = L.B200GGN(model, "classification", process_group=dist.group.WORLD, backward_parallel=mode,
+                           unit_min_width=0)
+            loss, kron = be.kron(idx, y, N=len(y))
+            # column-parallel backward: every rank holds the whole graph -> its 5 columns travel as one
+            # zero-padded group of 8 through the unit-compacted slabs; the row layout exchanges dense slabs
+            assert (be.last_stats["unit_slabs"] > 0) == (mode == "columns")
+            assert abs(float(loss) - float(ref[0])) <= 1e-5 * abs(float(ref[0]))
+            for fa, fb in zip(kron.kfacs, ref[1].kfacs):
+                for a, b in zip(fa, fb):
+                    assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+        out[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_column_parallel_backward_uses_unit_compacted_slabs():
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_unit_worker, args=(2, port, out), nprocs=2, join=True)
+        assert len(out) == 2
+
+
 def test_column_share_covers_all_columns_once():
     from laplace_gnn_b200.dist import column_share
     for C in (1, 3, 7, 40, 47):

@@ -55,6 +55,9 @@ def _worker(rank, world, port, out):
                     assert err <= 2e-5, (kw, err)
             assert abs(ml - ref_ml) <= 1e-5 * abs(ref_ml), (kw, ml, ref_ml)
             assert abs(float(la.loss) - float(ref.loss)) <= 1e-6 * abs(float(ref.loss))
+            # unit-compacted slabs wherever every row is local (single GPU, column-parallel backward)
+            assert (la.backend.last_stats["unit_slabs"] > 0) == (kw["backward_parallel"] == "columns"), kw
+        assert ref.backend.last_stats["unit_slabs"] > 0
         out[rank] = ref_ml
     finally:
         dist.destroy_process_group()

@@ -101,7 +101,7 @@ def test_row_partition_and_halo_bit_exact(parts):
 
 
 # ---------------------------------------------------------------------------------- SpMM
-@pytest.mark.parametrize("d", [1, 3, 7, 16, 47, 64, 100, 128, 256, 376, 1024, 2048])
+@pytest.mark.parametrize("d", [1, 3, 7, 16, 47, 64, 100, 128, 256, 376, 576, 720, 1024, 2048])
 @pytest.mark.parametrize("relu", [False, True])
 def test_spmm_matches_oracle(d, relu):
     ops = _ops()
@@ -177,7 +177,7 @@ def test_spmm_bulk_kernel_empty_rows_hub_rows_and_leading_dimensions():
     assert max_rel_err(relu.cpu().numpy(), np.maximum(ref, 0)) <= 1e-5
 
 
-@pytest.mark.parametrize("d", [16, 64, 256, 1024, 2256])
+@pytest.mark.parametrize("d", [16, 64, 256, 576, 720, 1024, 2256])
 @pytest.mark.parametrize("relu", [False, True])
 def test_spmm_hub_rows_of_power_law_graphs(d, relu):
     """A star on top of a random graph: rows of 30 k and 9 k non-zeros are split into 2048-entry
@@ -191,7 +191,7 @@ def test_spmm_hub_rows_of_power_law_graphs(d, relu):
     stars = np.concatenate([star0, star1], axis=1)
     ei = np.concatenate([base, stars, stars[::-1]], axis=1)
     G, R = _dev_graph(ei, n), O.build_graph(ei, n)
-    assert int(np.diff(R.rowptr).max()) > 30_000
+    assert int(np.diff(R.rowptr).max()) >= 30_000          # the star (+ its self loop unless the permutation holds node 0)
     x = rng.standard_normal((n, d)).astype(np.float32)
     xd = torch.from_numpy(x).to(DEV)
     ref = O.spmm(R, x, dtype=torch.float64)
@@ -367,9 +367,16 @@ def test_arxiv_shape_properties():
     y = torch.randint(0, C, (idx.numel(),), device=DEV, generator=gen)
     be = L.B200GGN(model, "classification", syrk_impl="simt")
     loss, kron = be.kron(idx, y, N=idx.numel())
-    be2 = L.B200GGN(model, "classification", syrk_impl="simt", rhs_tile_bytes=2 * n * 256 * 4 * 7)
+    # a budget of 7 columns: dense slabs take groups of 7, unit-compacted slabs round down to 4
+    be2 = L.B200GGN(model, "classification", syrk_impl="simt", rhs_tile_bytes=2 * n * 256 * 4 * 7, unit_slabs=False)
     _, kron2 = be2.kron(idx, y, N=idx.numel())
-    assert be2.last_stats["group"] == 7 and be.last_stats["group"] > 7
+    be3 = L.B200GGN(model, "classification", syrk_impl="simt", rhs_tile_bytes=2 * n * 256 * 4 * 7)
+    _, kron3 = be3.kron(idx, y, N=idx.numel())
+    assert be2.last_stats["group"] == 7 and be3.last_stats["group"] == 4 and be.last_stats["group"] > 7
+    assert be.last_stats["unit_slabs"] > 0 and be3.last_stats["unit_slabs"] == 20 and be2.last_stats["unit_slabs"] == 0
+    for fa, fb in zip(kron.kfacs, kron3.kfacs):
+        for a, b in zip(fa, fb):
+            assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-4
     for fa, fb in zip(kron.kfacs, kron2.kfacs):
         for a, b in zip(fa, fb):
             assert torch.equal(a, a.T)
@@ -628,8 +635,7 @@ def test_unit_compacted_backward_gives_the_same_factors():
         g = Golden(name)
         model = build_model(g, DEV)
         idx, y = torch.from_numpy(g.idx).to(DEV), torch.from_numpy(g.y).to(DEV)
-        be1 = L.B200GGN(model, "classification", unit_slabs=True)
-        be1.unit_min_width = 0
+        be1 = L.B200GGN(model, "classification", unit_slabs=True, unit_min_width=0)
         be2 = L.B200GGN(model, "classification", unit_slabs=False)
         l1, k1 = be1.kron(idx, y, N=len(y))
         l2, k2 = be2.kron(idx, y, N=len(y))
@@ -638,7 +644,7 @@ def test_unit_compacted_backward_gives_the_same_factors():
         assert float(l1) == float(l2)
         for fa, fb in zip(k1.kfacs, k2.kfacs):
             for a, b in zip(fa, fb):
-                assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 2e-6
+                assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5
         check_against_golden(g, l1, k1.kfacs, torch.tensor(g.marglik))
 
 
@@ -658,12 +664,11 @@ def test_unit_compacted_backward_products_like_shapes(h, C, layers):
     y = torch.randint(0, C, (idx.numel(),), generator=gen).to(DEV)
     res = []
     for units in (True, False):
-        be = L.B200GGN(model, "classification", unit_slabs=units)
-        be.unit_min_width = 0
+        be = L.B200GGN(model, "classification", unit_slabs=units, unit_min_width=0)
         loss, kron = be.kron(idx, y, N=len(y))
         assert (be.last_stats["unit_slabs"] > 0) == units
         res.append((float(loss), kron.kfacs))
     assert res[0][0] == res[1][0]
     for fa, fb in zip(res[0][1], res[1][1]):
-        for a, b in zip(fa, fb):
-            assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 2e-6
+        for a, b in zip(fa, fb):            # same slabs bit for bit; the column grouping changes the SYRK's summation order
+            assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5

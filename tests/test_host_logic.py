@@ -272,8 +272,7 @@ def test_unit_compacted_groups_give_the_same_factors(fake_ops, C, layers, budget
     csrc/spmm_units.cu) against the dense slabs: 10 classes -> groups 8 + 2(+2) or 4 + 4 + 2(+2)."""
     import laplace_gnn_b200 as L
     model, idx, y = _synthetic_model(600, 2400, 12, 64, C, layers)
-    be1 = L.B200GGN(model, "classification", unit_slabs=True, rhs_tile_bytes=budget)
-    be1.unit_min_width = 0
+    be1 = L.B200GGN(model, "classification", unit_slabs=True, rhs_tile_bytes=budget, unit_min_width=0)
     be2 = L.B200GGN(model, "classification", unit_slabs=False, rhs_tile_bytes=budget)
     l1, k1 = be1.kron(idx, y, N=len(y))
     l2, k2 = be2.kron(idx, y, N=len(y))
