@@ -172,6 +172,15 @@ int lgnn_spmm_units_f32(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64
                         const float* val, const float* slab, int64_t lds, const void* hdr, int64_t g,
                         int64_t h, float* y, int64_t ldy, int flags, lgnn_stream_t stream);
 
+/* Sampled dense-dense products: out[e] (+)= U[rows[e], 0:d] . V[cols[e], 0:d] for n_pairs (row, column)
+ * pairs (int32).  The adjoint of Â[i, j] wherever the path computes Y = Â X is Ybar[i, :] . X[j, :]; summed
+ * over the forward and the KFAC backward this is d marglik / dÂ on the requested entries — what the
+ * reference materialises as the dense model.adj.grad (gnn/marglik_training.py:197-215,
+ * gnn/models/models.py:100-115).  accumulate != 0 adds onto out. */
+int lgnn_sddmm_f32(int64_t n_pairs, const int32_t* rows, const int32_t* cols, const float* u, int64_t ldu,
+                   const float* v, int64_t ldv, int64_t d, float* out, int accumulate,
+                   lgnn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * loss + Hessian-sqrt right-hand sides
  * ---------------------------------------------------------------------------------------- */

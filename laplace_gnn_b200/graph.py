@@ -55,7 +55,8 @@ class Graph:
         a.max_row_nnz = int(deg.max()) if num_nodes > 0 else 0
         if at is not a:
             at.max_row_nnz = int((at.rowptr[1:] - at.rowptr[:-1]).max()) if num_nodes > 0 else 0
-        return cls(int(num_nodes), deg, dis, at, a, symmetric or assume_undirected)
+        return cls(int(num_nodes), deg, dis, at, a, symmetric or assume_undirected,
+                   {"symmetrised": bool(symmetric)})
 
     def partition_bounds(self, nparts: int) -> torch.Tensor:
         """nnz-balanced contiguous row blocks of Â (int64 [nparts+1], device)."""

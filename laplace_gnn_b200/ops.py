@@ -339,6 +339,30 @@ def spmm_units(a: CSR, us: UnitSlab, out: torch.Tensor | None = None, variant: i
     return out
 
 
+# ------------------------------------------------------------------------------ SDDMM (adjacency gradient)
+def sddmm(rows: torch.Tensor, cols: torch.Tensor, u: torch.Tensor, v: torch.Tensor, d: int | None = None,
+          out: torch.Tensor | None = None, accumulate: bool = False) -> torch.Tensor:
+    """out[e] (+)= u[rows[e], :d] . v[cols[e], :d]  (rows / cols int32)."""
+    lib = _lib.load()
+    _f32c(u, "u"); _f32c(v, "v")
+    if rows.dtype != torch.int32 or cols.dtype != torch.int32 or rows.numel() != cols.numel():
+        raise TypeError("sddmm: rows and cols must be int32 tensors of the same length")
+    rows, cols = rows.contiguous(), cols.contiguous()
+    d = int(min(u.shape[1], v.shape[1])) if d is None else int(d)
+    n_pairs = int(rows.numel())
+    if out is None:
+        if accumulate:
+            raise ValueError("sddmm: accumulate needs out")
+        out = torch.empty(max(n_pairs, 1), dtype=torch.float32, device=u.device)[:n_pairs]
+    if out.dtype != torch.float32 or out.numel() < n_pairs or not out.is_contiguous():
+        raise ValueError("sddmm: out must be a contiguous float32 tensor with one entry per pair")
+    with _Timed("sddmm", d, float(n_pairs) * (8 + 4 * d) + 8.0 * n_pairs):
+        check(lib.lgnn_sddmm_f32(n_pairs, ptr(rows), ptr(cols), ptr(u), u.stride(0), ptr(v), v.stride(0), d,
+                                 ptr(out), int(bool(accumulate)), stream()), "lgnn_sddmm_f32")
+    _lib.count_launches(1)
+    return out
+
+
 # ------------------------------------------------------------------------------ loss / Hessian sqrt
 def softmax_ce_sum(logits: torch.Tensor, idx: torch.Tensor, y: torch.Tensor, C: int | None = None):
     """(sum CE as a 0-d float64 tensor, number of argmax hits as 0-d int64)."""

@@ -148,9 +148,18 @@ def spmm_units(a, us, out=None, variant=0):
     return spmm(a, dense.reshape(n, g * h).contiguous(), out=out)
 
 
+def sddmm(rows, cols, u, v, d=None, out=None, accumulate=False):
+    d = min(u.shape[1], v.shape[1]) if d is None else d
+    s = (u[rows.long(), :d] * v[cols.long(), :d]).sum(1)
+    if out is None:
+        return s
+    out[: s.numel()] = out[: s.numel()] + s if accumulate else s
+    return out
+
+
 def gemm_mask_supported(k, n):
     return False          # the CPU double keeps the two-step path (torch.mm + relu_mask_mul)
 
 
-ALL = ["unit_slabs_supported", "unit_pack", "spmm_units", "gemm_mask_supported", "pack_rows_pitch", "pack_rows", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
+ALL = ["sddmm", "unit_slabs_supported", "unit_pack", "spmm_units", "gemm_mask_supported", "pack_rows_pitch", "pack_rows", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
        "halo_columns", "csr_slice_remap", "spmm", "softmax_ce_sum", "hess_rhs", "relu_mask_mul", "syrk"]
