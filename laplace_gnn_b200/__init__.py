@@ -5,6 +5,7 @@ Public surface:
     Graph, SparseGCN, SparseGCNConv, GCNConvFunction   model side (mirrors gnn/models)
     B200GGN, make_backend                              curvature backend (laplace/curvature contract)
     Laplace, KronLaplace, DiagLaplace, Kron            stand-ins when the `laplace` package is absent
+    marglik_edge_grad, log_marginal_likelihood_of_edges  d marglik / dA on sparse entries (structure learning)
     ops                                                tensor-level wrappers over the C-ABI (include/lgnn.h)
 """
 from . import _lib, ops  # noqa: F401
@@ -14,6 +15,7 @@ from .curvature import B200GGN, make_backend  # noqa: F401
 from .data import TensorBatchLoader  # noqa: F401
 from .kron import DiagLaplace, Kron, KronDecomposed, KronLaplace, Laplace  # noqa: F401
 from .training import MarglikTrainingResult, marglik_training  # noqa: F401
+from .structure import EdgeGradient, log_marginal_likelihood_of_edges, marglik_edge_grad  # noqa: F401
 
 __all__ = ["Graph", "knn_edge_index", "save_graph", "load_graph", "SparseGCN", "SparseGCNConv", "GCNConvFunction", "B200GGN", "make_backend",
-           "TensorBatchLoader", "marglik_training", "MarglikTrainingResult", "Laplace", "KronLaplace", "DiagLaplace", "Kron", "KronDecomposed", "ops"]
+           "TensorBatchLoader", "marglik_edge_grad", "log_marginal_likelihood_of_edges", "EdgeGradient", "marglik_training", "MarglikTrainingResult", "Laplace", "KronLaplace", "DiagLaplace", "Kron", "KronDecomposed", "ops"]

@@ -124,8 +124,9 @@ class _B200KFAC:
             raise ValueError(f"backward_parallel must be 'rows' or 'columns', got {backward_parallel!r}")
         if differentiable:
             raise NotImplementedError(
-                "differentiable=True (gradients of the factors w.r.t. the adjacency) is outside the "
-                "fixed-adjacency GCN hot path (SURVEY §8f row 3)")
+                "differentiable=True (autograd graphs through the factors) is not provided; the gradient of "
+                "the marginal likelihood w.r.t. the adjacency entries is laplace_gnn_b200.structure."
+                "marglik_edge_grad (SURVEY §8f row 3)")
         if self.likelihood != "classification":
             raise ValueError("B200GGN implements the classification (softmax CE) hot path only")
         if not isinstance(self.model, SparseGCN):
