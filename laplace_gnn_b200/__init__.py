@@ -16,7 +16,7 @@ from .data import TensorBatchLoader  # noqa: F401
 from . import datasets  # noqa: F401
 from .kron import DiagLaplace, Kron, KronDecomposed, KronLaplace, Laplace  # noqa: F401
 from .training import MarglikTrainingResult, marglik_training  # noqa: F401
-from .structure import EdgeGradient, log_marginal_likelihood_of_edges, marglik_edge_grad  # noqa: F401
+from .structure import EdgeGradient, EdgeScores, log_marginal_likelihood_of_edges, marglik_edge_grad  # noqa: F401
 
 __all__ = ["Graph", "knn_edge_index", "save_graph", "load_graph", "SparseGCN", "SparseGCNConv", "GCNConvFunction", "B200GGN", "make_backend",
-           "TensorBatchLoader", "datasets", "marglik_edge_grad", "log_marginal_likelihood_of_edges", "EdgeGradient", "marglik_training", "MarglikTrainingResult", "Laplace", "KronLaplace", "DiagLaplace", "Kron", "KronDecomposed", "ops"]
+           "TensorBatchLoader", "datasets", "marglik_edge_grad", "log_marginal_likelihood_of_edges", "EdgeGradient", "EdgeScores", "marglik_training", "MarglikTrainingResult", "Laplace", "KronLaplace", "DiagLaplace", "Kron", "KronDecomposed", "ops"]

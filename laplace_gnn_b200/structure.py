@@ -266,3 +266,70 @@ def log_marginal_likelihood_of_edges(model: SparseGCN, idx, y, edge_param: torch
     if edge_param.numel() != model.graph.ahat_t.nnz:
         raise ValueError("edge_param needs one entry per edge of A (graph.ahat_t.nnz, self loops included)")
     return _EdgeMarglik.apply(edge_param, model, idx, y, prior_precision, hess_sqrt)
+
+
+# ------------------------------------------------------------------------------------------------
+# straight-through edge scores: the sparse analogue of STEGCN's dense ``adj`` parameter
+# ------------------------------------------------------------------------------------------------
+class EdgeScores(torch.nn.Module):
+    """One real-valued score per TRACKED entry A[m, k] (m != k) — the existing edges (score 1) and a
+    caller-chosen set of candidate entries (score 0) — binarised by a threshold in the forward pass and
+    updated with the gradient of the binarised graph (straight-through), like the reference's dense
+    ``adj`` parameter (STEGCN, gnn/models/models.py:65-118; BinarizeSTE, gnn/models/utils.py:42-86).
+    The reference tracks all N^2 entries; here the untracked ones stay 0 forever."""
+
+    def __init__(self, edge_index: torch.Tensor, num_nodes: int, candidates: torch.Tensor | None = None,
+                 threshold: float = 0.5):
+        super().__init__()
+        n = int(num_nodes)
+        dev = edge_index.device
+        parts = [(edge_index.to(torch.int64), 1.0)]
+        if candidates is not None and candidates.numel() > 0:
+            parts.append((candidates.to(torch.int64).to(dev), 0.0))
+        key = torch.cat([p[0][0] * n + p[0][1] for p in parts])
+        val = torch.cat([torch.full((p[0].shape[1],), p[1], device=dev) for p in parts])
+        off = (key // n) != (key % n)                               # the diagonal is a constant 1
+        key, val = key[off], val[off]
+        # unique entries sorted by (m, k); an entry listed as edge and as candidate is an edge
+        order = torch.argsort(key * 2 + (1 - val.long()), stable=True)
+        key, val = key[order], val[order]
+        first = torch.ones_like(key, dtype=torch.bool)
+        first[1:] = key[1:] != key[:-1]
+        key, val = key[first], val[first]
+        self.n = n
+        self.threshold = float(threshold)
+        self.register_buffer("entries", torch.stack([key // n, key % n]))
+        self.score = torch.nn.Parameter(val.to(torch.float32))
+
+    @property
+    def active(self) -> torch.Tensor:
+        return self.score.detach() > self.threshold
+
+    def edge_index(self) -> torch.Tensor:
+        return self.entries[:, self.active]
+
+    def graph(self):
+        from .graph import Graph
+        return Graph.from_edge_index(self.edge_index().contiguous(), self.n)
+
+    def neg_marglik_step(self, model: SparseGCN, idx, y, optimizer: torch.optim.Optimizer, prior_precision=1.0,
+                         hess_sqrt: str = "reference", grad_norm: bool = False) -> torch.Tensor:
+        """One ``adj_optimizer.zero_grad(); neg_marglik.backward(); adj_optimizer.step()`` of
+        gnn/marglik_training.py:206-220 on the tracked entries, then the model's graph is rebuilt from
+        the re-binarised scores.  Returns the marglik BEFORE the step."""
+        act = self.active
+        res = marglik_edge_grad(model, idx, y, prior_precision, hess_sqrt,
+                                candidates=self.entries[:, ~act] if bool((~act).any()) else None)
+        off = res.rows != res.cols                              # CSR order == (m, k) order of the active entries
+        grad = torch.zeros_like(self.score)
+        grad[act] = -res.grad_edges[off]
+        if res.grad_candidates is not None:
+            grad[~act] = -res.grad_candidates
+        optimizer.zero_grad()
+        self.score.grad = grad
+        if grad_norm:
+            torch.nn.utils.clip_grad_norm_([self.score], max_norm=1.0)
+        optimizer.step()
+        if not torch.equal(self.active, act):
+            model.graph = self.graph()
+        return res.marglik

@@ -154,3 +154,52 @@ def test_sddmm_matches_torch(d):
     ops.sddmm(rows, cols, u, v, d, out=out, accumulate=True)
     assert float((out.double() - 2 * ref).abs().max()) <= 2 * tol
     assert ops.sddmm(rows[:0], cols[:0], u, v, d).numel() == 0
+
+
+def test_edge_scores_step_reproduces_the_reference_adj_update(fake_ops):
+    """Tracking ALL off-diagonal entries, one SGD step on the straight-through scores must give the
+    binarised adjacency the reference gets from ``adj_optimizer.step()`` on its dense parameter
+    (gnn/marglik_training.py:213-220): adj - lr * adj.grad, thresholded at 0.5."""
+    import laplace_gnn_b200 as L
+    name, lr = "tiny_directed_dups_2l", 0.4
+    g = Golden(name)
+    model = build_model(g)
+    idx, y = torch.from_numpy(g.idx), torch.from_numpy(g.y)
+    n = g.n
+    A = AG.dense_adj01(g.edge_index, n)
+    allpairs = torch.from_numpy(np.stack(np.nonzero(np.ones((n, n)) - np.eye(n))))
+    es = L.EdgeScores(torch.from_numpy(g.edge_index), n, candidates=allpairs)
+    assert es.score.numel() == n * n - n and int(es.active.sum()) == int((A * (1 - np.eye(n))).sum())
+    opt = torch.optim.SGD([es.score], lr=lr)
+    ml = es.neg_marglik_step(model, idx, y, opt)
+    z = np.load(os.path.join(GOLDEN_DIR, f"adjgrad_{name}.npz"))
+    assert abs(float(ml) + float(z["neg_marglik"])) <= 1e-3 * abs(float(z["neg_marglik"]))
+    new_adj = A - lr * z["neg_marglik_adj_grad"].astype(np.float64)
+    want = (new_adj > 0.5) & ~np.eye(n, dtype=bool)
+    m, k = es.entries.numpy()
+    # entries whose updated score is within rounding of the threshold are not decided by fp32
+    clear = np.abs(new_adj[m, k] - 0.5) > 1e-4
+    assert np.array_equal(es.active.numpy()[clear], want[m, k][clear])
+    assert np.abs(es.score.detach().numpy() - new_adj[m, k]).max() <= 1e-4
+    assert (es.active.numpy() != (A[m, k] > 0)).sum() > 0                     # the step did flip entries
+    # the model now runs on the rebuilt graph: its pattern is the re-binarised matrix + the diagonal
+    at = model.graph.ahat_t
+    rows = np.repeat(np.arange(n), np.diff(at.rowptr.numpy()))
+    got = np.zeros((n, n), bool); got[rows, at.col.numpy()] = True
+    assert np.array_equal(got[m, k], es.active.numpy()) and got.diagonal().all()
+
+
+def test_structure_learning_inside_the_epoch_loop(fake_ops):
+    import laplace_gnn_b200 as L
+    g = Golden("tiny_undirected_2l")
+    model = build_model(g)
+    idx, y = torch.from_numpy(g.idx), torch.from_numpy(g.y)
+    rng = np.random.Generator(np.random.PCG64(0))
+    cand = torch.from_numpy(rng.integers(0, g.n, (2, 200)))
+    es = L.EdgeScores(torch.from_numpy(g.edge_index), g.n, candidates=cand)
+    before = int(es.active.sum())
+    res = L.marglik_training(model, idx, y, idx[:8], y[:8], n_epochs=4, edge_scores=es, lr_adj=0.3,
+                             n_hypersteps=2, n_epochs_burnin=2, marglik_frequency=2)
+    assert [e for e, _ in res.n_edges] == [2, 4] and len(res.neg_margliks) == 4
+    assert res.n_edges[-1][1] == int(es.active.sum()) and int(es.active.sum()) != before
+    assert model.graph.ahat_t.nnz == int(es.active.sum()) + g.n
