@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-overlap", action="store_true", help="rows layout: one column group in flight instead of two")
     ap.add_argument("--no-fused-gemm", action="store_true", help="cuBLAS fp32 GEMM + mask kernel instead of the fused tcgen05 kernel")
     ap.add_argument("--dense-slabs", action="store_true", help="keep the slabs below the output layer dense (no unit compaction)")
+    ap.add_argument("--rhs-tile-gb", type=float, default=None,
+                    help="HBM budget of the two multi-RHS slabs (sizes the column groups; default: 40 %% of HBM)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-div", type=int, default=16,
@@ -232,6 +234,8 @@ def main():
         del edge_index
     bk = {"hess_sqrt": args.hess_sqrt, "syrk_impl": args.syrk, "fused_gemm": not args.no_fused_gemm,
           "unit_slabs": not args.dense_slabs}
+    if args.rhs_tile_gb is not None:
+        bk["rhs_tile_bytes"] = int(args.rhs_tile_gb * 1e9)
     if pg is not None:
         bk["process_group"] = pg
         bk["backward_parallel"] = args.backward_parallel
