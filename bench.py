@@ -261,6 +261,7 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ops.PROFILE = []
     launches0 = _lib.launch_count()
+    mem0 = torch.cuda.memory_stats(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     e0.record()
@@ -270,6 +271,9 @@ def main():
     sync()
     ms_total = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
+    mem1 = torch.cuda.memory_stats(dev)
+    allocator = {k: int(mem1.get(k, 0) - mem0.get(k, 0)) for k in ("num_device_alloc", "num_device_free", "num_alloc_retries")}
+    allocator["reserved_gb"] = round(mem1.get("reserved_bytes.all.current", 0) / 1e9, 2)
     prof = ops.PROFILE
     ops.PROFILE = None
     clocks = sampler.stop() if sampler else None
@@ -407,7 +411,7 @@ def main():
                    "l2": "inputs (>= 10 GB per SpMM) far exceed the 126 MB L2; no explicit flush",
                    "parallelism": "single GPU" if world == 1 else
                    f"row-partitioned x{world} (halo all-gather), backward over {args.backward_parallel}"},
-        "marglik": marglik, "gpu_launches": launches, "clocks": clocks, "e2e": e2e, "roofline": roof,
+        "marglik": marglik, "gpu_launches": launches, "allocator_in_timed_region": allocator, "clocks": clocks, "e2e": e2e, "roofline": roof,
         "cpu_baseline": cpu,
     }
     print(json.dumps(out))
