@@ -221,13 +221,22 @@ class _B200KFAC:
         for l in range(L):
             d_out = Ws[l].shape[0]
             if part is None:
-                with ops.timed("gemm_fwd", d_out, 2.0 * h.shape[0] * Ws[l].numel()):
-                    z = torch.mm(h, Ws[l].t()) if bs[l] is None else torch.addmm(bs[l], h, Ws[l].t())
-                    if d_out % 4:      # odd class count: pad the pitch so the SpMM takes its 128-bit path
-                        zp = torch.zeros(z.shape[0], (d_out + 3) // 4 * 4, dtype=z.dtype, device=z.device)
-                        zp[:, :d_out] = z
-                        z = zp
-                h = ops.spmm(g.ahat, z, relu=(l < L - 1))[:, :d_out]
+                # Z_l and P_l / H_l live in the persistent workspace (one pair per layer): the activations are
+                # rewritten by every pass and a fresh 2.5 GB allocation per layer per fit is a cudaMalloc each
+                n_rows = h.shape[0]
+                ldz = (d_out + 3) // 4 * 4     # odd class count: pad the pitch so the SpMM takes its 128-bit path
+                z = _slab(h.device, 1000 + l, 0, n_rows * ldz).view(n_rows, ldz)
+                with ops.timed("gemm_fwd", d_out, 2.0 * n_rows * Ws[l].numel()):
+                    if ldz == d_out:
+                        if bs[l] is None:
+                            torch.mm(h, Ws[l].t(), out=z)
+                        else:
+                            torch.addmm(bs[l], h, Ws[l].t(), out=z)
+                    else:
+                        z[:, :d_out] = torch.mm(h, Ws[l].t()) if bs[l] is None else torch.addmm(bs[l], h, Ws[l].t())
+                        z[:, d_out:] = 0
+                out = _slab(h.device, 1000 + l, 1, n_rows * ldz).view(n_rows, ldz)
+                h = ops.spmm(g.ahat, z, relu=(l < L - 1), out=out)[:, :d_out]
             else:
                 slab = torch.empty(part.total_rows, d_out, dtype=torch.float32, device=h.device)
                 z = slab[part.slot0:part.slot0 + part.n_local]
