@@ -321,6 +321,18 @@ def main():
                 traffic, traffic_src = ent["dram_bytes_per_launch"], ent.get("source")
         except Exception:
             pass
+        # no capture of this exact shape: report the same kernel's measured traffic on its nearest captured shape
+        sibling = None
+        if traffic is None:
+            try:
+                pre = f"{args.workload}:{args.scale}:{world}:{kind} d="
+                for key, ent in tj.items():
+                    if key.startswith(pre) and ent.get("nnz") == nnz:
+                        sibling = {"kernel": key.split(":")[-1], "dram_bytes_per_launch": ent["dram_bytes_per_launch"],
+                                   "algorithmic_bytes_per_launch": ent.get("algorithmic_bytes_per_launch"),
+                                   "source": ent.get("source")}
+            except Exception:
+                pass
         roof = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": f"{kind} d={d}",
@@ -329,6 +341,8 @@ def main():
                 "algorithmic_bytes_per_launch": top["bytes"] / top["launches"],
                 "spmm_ms_per_step": spmm_ms, "syrk_ms_per_step": syrk_ms,
                 "ms_per_step_by_kind": {k: round(v, 2) for k, v in sorted(by_kind.items())}}
+        if sibling is not None:
+            roof["traffic_same_kernel_other_shape"] = sibling
         if top["dense_bytes"] > 0:
             roof["dense_equivalent"] = {
                 "bytes_per_launch": top["dense_bytes"] / top["launches"],
