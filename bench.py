@@ -73,19 +73,29 @@ def shape(args):
 
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi polled every 200 ms.  Started BEFORE the warm-up (NVML initialisation takes driver locks for
+    tens of milliseconds — as long as a whole Cora / Pubmed step); only the samples stamped inside the timed
+    region count, unless the region is shorter than one polling interval."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t_begin = self.t_end = None
         try:
             self.p = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                  "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def begin(self):
+        self.t_begin = time.time()
+
+    def end(self):
+        self.t_end = time.time()
 
     def stop(self) -> dict:
         if self.p is None:
@@ -97,23 +107,32 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f.read().splitlines():
             parts = [p.strip() for p in line.split(",")]
-            if len(parts) < 7:
+            if len(parts) < 8:
                 continue
             try:
-                sm.append(float(parts[0])); mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = None                                  # unknown stamp format: keep the sample
+            try:
+                rows.append((ts, float(parts[1]), float(parts[2]),
+                             {nm for nm, v in zip(names, parts[4:8]) if v.lower().startswith("active")}))
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
         os.unlink(self.f.name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        inside = [r for r in rows if r[0] is None or (self.t_begin is not None and self.t_end is not None
+                                                      and self.t_begin <= r[0] <= self.t_end + 0.2)]
+        window = "timed region"
+        if not inside:
+            inside, window = rows[-3:], "last samples before the end of the timed region (region < 200 ms)"
+        sm = sorted(r[1] for r in inside)
+        reasons = set().union(*[r[3] for r in inside]) if inside else set()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max((r[2] for r in inside), default=None),
+                "reasons": sorted(reasons), "samples": len(inside), "window": window}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -253,22 +272,26 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for _ in range(args.warmup):
         la, ml = step(model, loader)
     sync()
 
     # ---------------- timed region (HBM-resident inputs)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     ops.PROFILE = []
     launches0 = _lib.launch_count()
     mem0 = torch.cuda.memory_stats(dev)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
+    if sampler:
+        sampler.begin()
     e0.record()
     for _ in range(args.steps):
         la, ml = step(model, loader)
     e1.record()
     sync()
+    if sampler:
+        sampler.end()
     ms_total = e0.elapsed_time(e1)
     launches = _lib.launch_count() - launches0
     mem1 = torch.cuda.memory_stats(dev)

@@ -1,5 +1,7 @@
 """CPU: host-side logic (backend orchestration, factor packing, Laplace drivers, autograd
 Function) with the kernels replaced by the oracle-backed test double (tests/fake_ops.py)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -282,3 +284,37 @@ def test_unit_compacted_groups_give_the_same_factors(fake_ops, C, layers, budget
     for fa, fb in zip(k1.kfacs, k2.kfacs):
         for a, b in zip(fa, fb):
             assert max_rel_err(a.numpy(), b.numpy()) <= 1e-5
+
+
+def test_bench_clock_sampler_keeps_the_timed_region(monkeypatch):
+    """bench.ClockSampler: nvidia-smi lines stamped outside the timed region are dropped, throttle reasons
+    inside it are reported, an unparsable stamp keeps the sample."""
+    import datetime, importlib, subprocess, sys, time
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    bench = importlib.import_module("bench")
+
+    class FakeProc:
+        def __init__(self, cmd, stdout=None, stderr=None):
+            self.out = stdout
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+        def kill(self): pass
+    monkeypatch.setattr(subprocess, "Popen", FakeProc)
+    s = bench.ClockSampler(0)
+    t0 = time.time()
+    fmt = lambda t: datetime.datetime.fromtimestamp(t).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+    lines = [f"{fmt(t0 - 5.0)}, 1200, 1965, 300.0, Not Active, Not Active, Not Active, Not Active",     # warm-up
+             f"{fmt(t0 + 0.1)}, 1900, 1965, 900.0, Not Active, Not Active, Not Active, Active",
+             f"{fmt(t0 + 0.3)}, 1800, 1965, 950.0, Not Active, Not Active, Not Active, Active",
+             f"{fmt(t0 + 0.5)}, 1850, 1965, 940.0, Not Active, Not Active, Not Active, Not Active",
+             f"{fmt(t0 + 9.0)}, 600, 1965, 100.0, Active, Not Active, Not Active, Not Active"]          # after
+    s.f.write("\n".join(lines) + "\n")
+    s.t_begin, s.t_end = t0, t0 + 0.6
+    c = s.stop()
+    assert c["samples"] == 3 and c["sm_mhz"] == 1850.0 and c["sm_max_mhz"] == 1965.0
+    assert c["reasons"] == ["sw_power_cap"] and c["window"] == "timed region"
+    s2 = bench.ClockSampler(0)
+    s2.f.write(lines[0] + "\n")
+    s2.t_begin, s2.t_end = t0, t0 + 0.01                                  # shorter than one polling interval
+    c2 = s2.stop()
+    assert c2["samples"] == 1 and c2["sm_mhz"] == 1200.0 and "region < 200 ms" in c2["window"]
