@@ -26,7 +26,8 @@ A and any list of candidate (non-)edges — with the kernels of the hot path plu
                     dA[m, k] = dAhat[k, m] Â[k, m] + r_m,  r_m = -(rowsum_m(S) + colsum_m(S)) / (2 d_m),
                     S = dAhat * Â; the diagonal is a constant (fill_diagonal_) and gets 0.
 
-Scope: one full batch (N = len(idx)), scalar or per-block prior precision, the weights are constants.
+Scope: one full batch or the reference's per-batch accumulation, scalar or per-block prior precision, the
+weights are constants.
 Graphs built with ``symmetric=True`` (the model-side (A + A^T) symmetrisation) are not covered.
 Cost: about four fits (every SpMM of the KFAC backward once more with Â, plus an SDDMM that reads
 both slabs per edge).
@@ -100,10 +101,14 @@ def _factor_adjoints(kfacs, has_bias, deltas):
 
 def marglik_edge_grad(model: SparseGCN, idx: torch.Tensor, y: torch.Tensor, prior_precision=1.0,
                       hess_sqrt: str = "reference", candidates: torch.Tensor | None = None,
-                      group: int | None = None) -> EdgeGradient:
-    """log marginal likelihood of ``Laplace(model, "classification", "all", "kron")`` after one
-    full-batch fit on (idx, y), and its gradient with respect to A[m, k] for every edge of the
-    graph and every ``candidates[:, e] = (m, k)`` (int64 [2, K]; entries that are not edges)."""
+                      group: int | None = None, batch_size: int | None = None) -> EdgeGradient:
+    """log marginal likelihood of ``Laplace(model, "classification", "all", "kron")`` after ``fit`` on
+    (idx, y), and its gradient with respect to A[m, k] for every edge of the graph and every
+    ``candidates[:, e] = (m, k)`` (int64 [2, K]; entries that are not edges).  ``batch_size=None`` is one
+    full batch; otherwise the reference's per-batch accumulation (``loss += loss_b; H += H_b``,
+    baselaplace.py:778-854, with the driver's ``batch_size=10000``, gnn/marglik_training.py:125-127): every
+    batch back-propagates its own train nodes through the whole graph, the factors add up, and so do
+    the batches' adjoints (the factor adjoints come from the summed factors)."""
     if not isinstance(model, SparseGCN):
         raise TypeError("marglik_edge_grad needs a laplace_gnn_b200.SparseGCN model")
     g = model.graph
@@ -116,7 +121,12 @@ def marglik_edge_grad(model: SparseGCN, idx: torch.Tensor, y: torch.Tensor, prio
     y = y.to(torch.int64).contiguous()
     M = int(idx.numel())
     dev = Ws[0].device
-    loss, kron = be.kron(idx, y, N=M)
+    bsz = M if batch_size is None else max(1, int(batch_size))
+    batches = [(s0, min(M, s0 + bsz)) for s0 in range(0, M, bsz)]
+    loss, kron = None, None
+    for s0, s1 in batches:                                   # ParametricLaplace.fit
+        lb, kb = be.kron(idx[s0:s1], y[s0:s1], N=M)
+        loss, kron = (lb, kb) if kron is None else (loss + lb, kron + kb)
     Hs, logits = be._forward(Ws, bs)
     C = logits.shape[1]
     c_pad = (C + 3) // 4 * 4
@@ -169,11 +179,12 @@ def marglik_edge_grad(model: SparseGCN, idx: torch.Tensor, y: torch.Tensor, prio
         group = max(1, min(C, int(0.4 * free // per_col)))
     f_train = logits[idx][:, :C].contiguous()
     fbar = torch.zeros(M, C, dtype=torch.float32, device=dev)
-    for c0 in range(0, C, group):
+    for (s0, s1), c0 in ((b, c) for b in batches for c in range(0, C, group)):
         gc = min(group, C - c0)
+        idx_b = idx[s0:s1]
         deltas, gzs = [None] * L, [None] * L
         delta = torch.zeros(n, gc * c_pad, dtype=torch.float32, device=dev)
-        ops.hess_rhs(logits, idx, c0, gc, delta, c_pad, hess_sqrt)
+        ops.hess_rhs(logits, idx_b, c0, gc, delta, c_pad, hess_sqrt)
         width, ld = C, c_pad
         for l in range(L - 1, -1, -1):                       # the KFAC backward, slabs kept
             gz = ops.spmm(at, delta)
@@ -200,14 +211,15 @@ def marglik_edge_grad(model: SparseGCN, idx: torch.Tensor, y: torch.Tensor, prio
             dbar = ops.spmm(g.ahat, gzbar_slab)
             deltas[l] = gzs[l] = None
         # top: delta_L[idx[m], c, :] = v_c(f_m)  ->  fbar_m += sum_c J_{v_c}(f_m)^T dbar_L[idx[m], c, :]
-        cot = dbar.view(n, gc, c_pad)[idx][:, :, :C]
+        cot = dbar.view(n, gc, c_pad)[idx_b][:, :, :C]
         step = max(1, (64 << 20) // max(1, C * C * 4))
-        for s in range(0, M, step):
-            fs = f_train[s:s + step].detach().requires_grad_(True)
+        for s in range(s0, s1, step):
+            e = min(s1, s + step)
+            fs = f_train[s:e].detach().requires_grad_(True)
             with torch.enable_grad():
                 V = hess_sqrt_columns(fs, hess_sqrt)[:, c0:c0 + gc, :]
-                (gf,) = torch.autograd.grad((V * cot[s:s + step]).sum(), fs)
-            fbar[s:s + step] += gf
+                (gf,) = torch.autograd.grad((V * cot[s - s0:e - s0]).sum(), fs)
+            fbar[s:e] += gf
         del dbar, cot
 
     # ---- forward part (single right-hand side)
@@ -224,7 +236,7 @@ def marglik_edge_grad(model: SparseGCN, idx: torch.Tensor, y: torch.Tensor, prio
         if l > 0:
             zbar = ops.spmm(at, pbar)
             hbar = torch.mm(zbar[:, :width], Ws[l])
-            hbar += torch.mm(Hs[l], Abar[l]) * (2.0 / M)     # A_l = H_{l-1}^T H_{l-1} / N
+            hbar += torch.mm(Hs[l], Abar[l]) * (2.0 * len(batches) / M)     # A_l = sum_b H_{l-1}^T H_{l-1} / N
             ops.relu_mask_mul(hbar, Hs[l], 1)
             pbar = hbar
 
@@ -313,13 +325,15 @@ class EdgeScores(torch.nn.Module):
         return Graph.from_edge_index(self.edge_index().contiguous(), self.n)
 
     def neg_marglik_step(self, model: SparseGCN, idx, y, optimizer: torch.optim.Optimizer, prior_precision=1.0,
-                         hess_sqrt: str = "reference", grad_norm: bool = False) -> torch.Tensor:
+                         hess_sqrt: str = "reference", grad_norm: bool = False,
+                         batch_size: int | None = None) -> torch.Tensor:
         """One ``adj_optimizer.zero_grad(); neg_marglik.backward(); adj_optimizer.step()`` of
         gnn/marglik_training.py:206-220 on the tracked entries, then the model's graph is rebuilt from
         the re-binarised scores.  Returns the marglik BEFORE the step."""
         act = self.active
         res = marglik_edge_grad(model, idx, y, prior_precision, hess_sqrt,
-                                candidates=self.entries[:, ~act] if bool((~act).any()) else None)
+                                candidates=self.entries[:, ~act] if bool((~act).any()) else None,
+                                batch_size=batch_size)
         off = res.rows != res.cols                              # CSR order == (m, k) order of the active entries
         grad = torch.zeros_like(self.score)
         grad[act] = -res.grad_edges[off]

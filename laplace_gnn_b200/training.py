@@ -83,7 +83,7 @@ def marglik_training(model, train_idx, train_y, val_idx, val_y, n_epochs: int = 
             model.eval()
             for _ in range(n_hypersteps):
                 edge_scores.neg_marglik_step(model, train_idx, train_y, adj_opt, prior_precision,
-                                             kw.get("hess_sqrt", "reference"), grad_norm)
+                                             kw.get("hess_sqrt", "reference"), grad_norm, batch_size)
             res.n_edges.append((epoch, int(edge_scores.active.sum())))
 
         la = laplace(model, "classification", subset_of_weights="all", hessian_structure=hessian_structure,

@@ -41,10 +41,12 @@ def normalized_adj_dense(A: torch.Tensor) -> torch.Tensor:
 
 
 def marglik_of_dense_adj(A: torch.Tensor, x, weights: Sequence, biases: Sequence, idx, y,
-                         prior_prec: float = 1.0, mode: str = "reference") -> torch.Tensor:
-    """log marginal likelihood of ``Laplace(model, "classification", "all", "kron")`` after one
-    full-batch ``fit`` as a differentiable function of the dense 0/1 adjacency A (float64).
-    Follows oracle/gcn_kfac_oracle.py (kron_factors, log_marglik) line by line, dense instead of CSR."""
+                         prior_prec: float = 1.0, mode: str = "reference", batch_size=None) -> torch.Tensor:
+    """log marginal likelihood of ``Laplace(model, "classification", "all", "kron")`` after ``fit`` as a
+    differentiable function of the dense 0/1 adjacency A (float64).  Follows oracle/gcn_kfac_oracle.py
+    (kron_factors, fit_and_marglik, log_marglik) line by line, dense instead of CSR.  ``batch_size``:
+    the reference's per-batch accumulation ``loss += loss_b; H += H_b`` (baselaplace.py:778-854): every
+    batch runs the full-graph pipeline on its own train nodes, A_b = H^T H / N each."""
     dt = A.dtype
     ahat = normalized_adj_dense(A)
     idx_t = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
@@ -63,21 +65,26 @@ def marglik_of_dense_adj(A: torch.Tensor, x, weights: Sequence, biases: Sequence
         if l < L - 1:
             h = torch.relu(p)
             hs.append(h)
-    f = ps[-1][idx_t]
     M = idx_t.numel()
-    loss = torch.nn.functional.cross_entropy(f, y_t, reduction="sum")
-    V = O.hess_sqrt_rhs(f, mode)                      # [M, C, C], differentiable in f (fork: not detached)
-    C = f.shape[1]
+    bsz = M if batch_size is None else int(batch_size)
     n = A.shape[0]
-    A_fac = [(hh.T @ hh) / M for hh in hs]            # single full batch: (1/M) * (M/N) with N = M
+    C = ps[-1].shape[1]
+    loss = torch.zeros((), dtype=dt)
+    A_fac = [torch.zeros(hh.shape[1], hh.shape[1], dtype=dt) for hh in hs]
     G_fac = [torch.zeros(w.shape[0], w.shape[0], dtype=dt) for w in Ws]
-    for c in range(C):
-        delta = torch.zeros(n, C, dtype=dt).index_add(0, idx_t, V[:, c, :])
-        for l in range(L - 1, -1, -1):
-            gz = ahat.T @ delta
-            G_fac[l] = G_fac[l] + gz.T @ gz
-            if l > 0:
-                delta = (gz @ Ws[l]) * (ps[l - 1] > 0).to(dt)
+    for s in range(0, M, bsz):
+        ib, yb = idx_t[s:s + bsz], y_t[s:s + bsz]
+        f = ps[-1][ib]
+        loss = loss + torch.nn.functional.cross_entropy(f, yb, reduction="sum")
+        V = O.hess_sqrt_rhs(f, mode)                  # [m, C, C], differentiable in f (fork: not detached)
+        A_fac = [a + (hh.T @ hh) / M for a, hh in zip(A_fac, hs)]      # (1/M_b) * (M_b/N), N = M
+        for c in range(C):
+            delta = torch.zeros(n, C, dtype=dt).index_add(0, ib, V[:, c, :])
+            for l in range(L - 1, -1, -1):
+                gz = ahat.T @ delta
+                G_fac[l] = G_fac[l] + gz.T @ gz
+                if l > 0:
+                    delta = (gz @ Ws[l]) * (ps[l - 1] > 0).to(dt)
     logdet = torch.zeros((), dtype=dt)
     n_params = 0
     theta_sq = torch.zeros((), dtype=dt)
@@ -95,10 +102,10 @@ def marglik_of_dense_adj(A: torch.Tensor, x, weights: Sequence, biases: Sequence
 
 
 def marglik_adj_grad(adj01: np.ndarray, x, weights, biases, idx, y, prior_prec: float = 1.0,
-                     mode: str = "reference"):
+                     mode: str = "reference", batch_size=None):
     """(marglik, d marglik / dA as a dense [n, n] float64 array; zero diagonal)."""
     A = torch.tensor(np.asarray(adj01), dtype=torch.float64, requires_grad=True)
-    ml = marglik_of_dense_adj(A, x, weights, biases, idx, y, prior_prec, mode)
+    ml = marglik_of_dense_adj(A, x, weights, biases, idx, y, prior_prec, mode, batch_size)
     (g,) = torch.autograd.grad(ml, A)
     return float(ml), g.numpy()
 

@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 from oracle import ref_loader  # noqa: E402
 from oracle.make_golden import CASES, GOLDEN_DIR, dense_adj_from_edges, make_inputs  # noqa: E402
 
-ADJGRAD_CASES = ["tiny_undirected_2l", "tiny_directed_3l", "tiny_directed_dups_2l"]
+ADJGRAD_CASES = ["tiny_undirected_2l", "tiny_directed_3l", "tiny_directed_dups_2l", "small_multibatch_2l"]
 
 
 def main():
@@ -46,7 +46,7 @@ def main():
                 conv.lin.bias.copy_(torch.from_numpy(z[f"b{l}"]))
         model.eval()
         idx_t, y = torch.from_numpy(idx), torch.from_numpy(y_all[idx])
-        loader = DataLoader(TensorDataset(idx_t, y), batch_size=len(idx), shuffle=False)
+        loader = DataLoader(TensorDataset(idx_t, y), batch_size=cfg.get("batch_size", len(idx)), shuffle=False)
         la = R.Laplace(model, "classification", subset_of_weights="all", hessian_structure="kron")
         la.fit(loader)
         neg = -la.log_marginal_likelihood()

@@ -42,6 +42,18 @@ def test_bad_arguments_are_rejected_before_any_launch():
     assert rc == -1
     rc = lib.lgnn_syrk_f32(None, 8, 10, 8, 1.0, 0.0, None, 8, None, 0, 0, None)
     assert rc == -1
+    # unit-compacted slabs: shape support is a host-side predicate; bad shapes / pitches never launch
+    assert lib.lgnn_unit_slabs_supported(12, 256) == 1 and lib.lgnn_unit_slabs_supported(16, 1024) == 1
+    assert lib.lgnn_unit_slabs_supported(11, 256) == 0 and lib.lgnn_unit_slabs_supported(12, 100) == 0
+    assert lib.lgnn_unit_pack_f32(None, 3072, None, 256, 10, 11, 256, None, None) == -5          # LGNN_E_UNSUPPORTED
+    assert lib.lgnn_unit_pack_f32(None, 3072, None, 256, 10, 12, 256, None, None) == -1          # null pointers
+    assert lib.lgnn_unit_pack_f32(None, 3072, None, 256, 0, 12, 256, None, None) == 0            # nothing to do
+    assert lib.lgnn_spmm_units_f32(5, 5, 10, None, None, None, None, 3072, None, 12, 256, None, 3072, 0, None) == -1
+    assert lib.lgnn_spmm_units_f32(5, 5, 10, None, None, None, None, 3072, None, 20, 256, None, 3072, 0, None) == -5
+    assert lib.lgnn_sddmm_f32(-1, None, None, None, 4, None, 4, 4, None, 0, None) == -1
+    assert lib.lgnn_sddmm_f32(0, None, None, None, 4, None, 4, 4, None, 0, None) == 0
+    assert lib.lgnn_sddmm_f32(3, None, None, None, 4, None, 4, 4, None, 0, None) == -1 and b"sddmm" in lib.lgnn_last_error()
+    assert lib.lgnn_hess_rhs_pitched_f32(None, 4, 4, None, 1, 0, 4, 4, 8, 0, None, None) == -1
 
 
 def test_missing_library_fails_loudly(tmp_path):

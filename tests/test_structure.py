@@ -15,7 +15,7 @@ from conftest import GOLDEN_DIR, Golden
 from helpers import build_model
 from oracle import adj_grad_oracle as AG
 
-ADJGRAD = ["tiny_undirected_2l", "tiny_directed_3l", "tiny_directed_dups_2l"]
+ADJGRAD = ["tiny_undirected_2l", "tiny_directed_3l", "tiny_directed_dups_2l", "small_multibatch_2l"]
 TOL = 1e-4
 
 
@@ -28,7 +28,8 @@ def _ref_grad(name):
 def test_oracle_matches_reference_adj_grad(name):
     g = Golden(name)
     ref, ref_ml = _ref_grad(name)
-    ml, grad = AG.marglik_adj_grad(AG.dense_adj01(g.edge_index, g.n), g.x, g.Ws, g.bs, g.idx, g.y)
+    ml, grad = AG.marglik_adj_grad(AG.dense_adj01(g.edge_index, g.n), g.x, g.Ws, g.bs, g.idx, g.y,
+                                   batch_size=g.batch_size)
     assert abs(ml - ref_ml) <= 1e-5 * abs(ref_ml)
     assert np.abs(grad - ref).max() <= 1e-5 * np.abs(ref).max()
     assert np.abs(np.diag(grad)).max() == 0.0
@@ -41,11 +42,13 @@ def _check_package(name, device, mode="reference", prior=1.0):
     model = build_model(g, device)
     idx, y = torch.from_numpy(g.idx).to(device), torch.from_numpy(g.y).to(device)
     A = AG.dense_adj01(g.edge_index, g.n)
-    ml, dense = AG.marglik_adj_grad(A, g.x, g.Ws, g.bs, g.idx, g.y, prior_prec=prior, mode=mode)
+    ml, dense = AG.marglik_adj_grad(A, g.x, g.Ws, g.bs, g.idx, g.y, prior_prec=prior, mode=mode,
+                                    batch_size=g.batch_size)
     # candidates: every non-edge of the first rows, plus a diagonal entry (must come back as 0)
     cm, ck = np.nonzero(A[:12] + np.eye(g.n)[:12] == 0)
     cand = torch.from_numpy(np.stack([np.append(cm, 3), np.append(ck, 3)])).to(device)
-    res = marglik_edge_grad(model, idx, y, prior_precision=prior, hess_sqrt=mode, candidates=cand, group=2)
+    res = marglik_edge_grad(model, idx, y, prior_precision=prior, hess_sqrt=mode, candidates=cand, group=2,
+                            batch_size=None if g.batch_size == len(g.idx) else g.batch_size)
     scale = np.abs(dense).max()
     rows, cols = res.rows.cpu().numpy(), res.cols.cpu().numpy()
     assert abs(float(res.marglik) - ml) <= 1e-4 * abs(ml)
