@@ -152,9 +152,11 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024):
+                    unit_min_width=1024, diag_mode="exact"):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
+        if diag_mode not in ("exact", "node_factorised"):
+            raise ValueError(f"diag_mode must be 'exact' or 'node_factorised', got {diag_mode!r}")
         if backward_parallel not in ("rows", "columns"):
             raise ValueError(f"backward_parallel must be 'rows' or 'columns', got {backward_parallel!r}")
         if differentiable:
@@ -169,6 +171,8 @@ class _B200KFAC:
         if self.last_layer or self.subnetwork_indices is not None:
             raise NotImplementedError("last_layer / subnetwork Laplace are outside the hot path")
         self.hess_sqrt = hess_sqrt
+        self.diag_mode = diag_mode
+        self._layer_hook = None              # diag.diag_ggn_node_factorised taps gZ_l of every column group here
         self.process_group = process_group
         self.rhs_tile_bytes = rhs_tile_bytes
         self.syrk_impl = syrk_impl
@@ -318,6 +322,8 @@ class _B200KFAC:
                 ops.spmm(lay.csr_t_top if (l == L - 1 and lay.csr_t_top is not None) else lay.csr_t, slab, out=gz)
             gz_rows = gz.view(n_loc * gq, ld)
             ops.syrk(gz_rows, n=width, alpha=1.0, beta=1.0, out=G[l], impl=self._impl(width))
+            if self._layer_hook is not None:
+                self._layer_hook(l, gz, gq, ld, width)
             if l > 0:
                 d_prev = dims[l - 1]
                 slab = P[: n_in * gq * d_prev].view(n_in, gq * d_prev)
@@ -524,9 +530,15 @@ class _B200KFAC:
     def diag(self, x: torch.Tensor, y: torch.Tensor, N: int | None = None, **kwargs):
         """(loss, diag GGN [P]) with the true Λ = diag(p) - pp^T (curvature.py:365-372, 412-432).
 
-        Exact, and therefore — like the reference, which materialises an (M, C, P) Jacobian — only
-        for small graphs: one back-propagated column per (train node, class) pair, processed as
-        multi-RHS tiles through the same SpMM kernel."""
+        ``diag_mode="exact"`` (default): exact, and therefore — like the reference, which materialises an
+        (M, C, P) Jacobian — only for small graphs: one back-propagated column per (train node, class)
+        pair, processed as multi-RHS tiles through the same SpMM kernel.
+        ``diag_mode="node_factorised"``: an APPROXIMATION for graphs where that is infeasible:
+        sum_c (gZ_c ∘ gZ_c)^T (H ∘ H), one multi-RHS backward like ``kron``; exact when no edge couples
+        two nodes."""
+        if self.diag_mode == "node_factorised":
+            from .diag import diag_ggn_node_factorised
+            return diag_ggn_node_factorised(self, x, y)
         from .diag import diag_ggn_exact
         return diag_ggn_exact(self, x, y)
 
@@ -540,7 +552,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024):
+                 unit_min_width=1024, diag_mode="exact"):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -551,7 +563,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
                          backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs,
-                         unit_min_width)
+                         unit_min_width, diag_mode)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

@@ -318,3 +318,54 @@ def test_bench_clock_sampler_keeps_the_timed_region(monkeypatch):
     s2.t_begin, s2.t_end = t0, t0 + 0.01                                  # shorter than one polling interval
     c2 = s2.stop()
     assert c2["samples"] == 1 and c2["sm_mhz"] == 1200.0 and "region < 200 ms" in c2["window"]
+
+
+def test_node_factorised_diag_is_exact_without_edges_and_close_to_bruteforce(fake_ops):
+    """diag_mode="node_factorised": on an edgeless graph (Â = I) the node-factorised diagonal IS the exact
+    diagonal GGN; on a real graph it equals its definition sum_n sum_c gZ_c[n, i]^2 H[n, j]^2 computed from
+    the oracle's dense restatement; DiagLaplace runs on it."""
+    import laplace_gnn_b200 as L
+    from oracle import gcn_kfac_oracle as O
+    n, F, h, C = 60, 7, 64, 5
+    gen = torch.Generator().manual_seed(1)
+    X = torch.randn(n, F, generator=gen)
+    idx = torch.randperm(n, generator=gen)[:36].sort().values
+    y = torch.randint(0, C, (36,), generator=gen)
+    empty = torch.zeros(2, 0, dtype=torch.int64)
+    torch.manual_seed(1)
+    model = L.SparseGCN(F, h, C, 3, X, L.Graph.from_edge_index(empty, n))
+    exact = L.B200GGN(model, "classification").diag(idx, y)
+    approx = L.B200GGN(model, "classification", diag_mode="node_factorised", unit_min_width=0).diag(idx, y)
+    assert float(exact[0]) == float(approx[0])
+    assert max_rel_err(approx[1].numpy(), exact[1].numpy()) <= 1e-5
+
+    ei = O.synthetic_edges(n, 150, seed=2, directed=True)
+    torch.manual_seed(2)
+    model = L.SparseGCN(F, h, C, 2, X, L.Graph.from_edge_index(torch.from_numpy(ei), n))
+    be = L.B200GGN(model, "classification", diag_mode="node_factorised", rhs_tile_bytes=2 * n * h * 4 * 2)
+    loss, d = be.diag(idx, y)
+    # brute force from the oracle's pieces (dense, float64)
+    R = O.build_graph(ei, n)
+    Ws = [c.lin.weight.detach().numpy() for c in model.convs]
+    bs = [c.lin.bias.detach().numpy() for c in model.convs]
+    hs, ps = O.forward(R, X.numpy(), Ws, bs, torch.float64)
+    V = O.hess_sqrt_rhs(ps[-1][idx], "ggn")
+    at = torch.from_numpy(np.zeros((n, n))); rows = np.repeat(np.arange(n), np.diff(R.t_rowptr))
+    at[rows, R.t_col.astype(np.int64)] = torch.from_numpy(R.t_val.astype(np.float64))
+    want = [torch.zeros(w.shape, dtype=torch.float64) for w in Ws], [torch.zeros(w.shape[0], dtype=torch.float64) for w in Ws]
+    for c in range(C):
+        delta = torch.zeros(n, C, dtype=torch.float64).index_add(0, idx, V[:, c, :])
+        for l in (1, 0):
+            gz = at @ delta
+            want[0][l] += (gz ** 2).T @ (hs[l] ** 2)
+            want[1][l] += (gz ** 2).sum(0)
+            if l > 0:
+                delta = (gz @ torch.from_numpy(Ws[l]).double()) * (ps[l - 1] > 0)
+    ref = torch.cat([want[0][0].reshape(-1), want[1][0], want[0][1].reshape(-1), want[1][1]])
+    assert max_rel_err(d.numpy(), ref.numpy()) <= 1e-5
+    la = L.Laplace(model, "classification", hessian_structure="diag", backend=L.B200GGN,
+                   backend_kwargs={"diag_mode": "node_factorised"})
+    la.fit(L.TensorBatchLoader(idx, y))
+    assert torch.isfinite(la.log_marginal_likelihood())
+    with pytest.raises(ValueError):
+        L.B200GGN(model, "classification", diag_mode="fast")
