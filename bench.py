@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-overlap", action="store_true", help="rows layout: one column group in flight instead of two")
     ap.add_argument("--no-fused-gemm", action="store_true", help="cuBLAS fp32 GEMM + mask kernel instead of the fused tcgen05 kernel")
     ap.add_argument("--dense-slabs", action="store_true", help="keep the slabs below the output layer dense (no unit compaction)")
+    ap.add_argument("--unit-even-groups", action="store_true",
+                    help="lab: column groups of any even width (csrc/spmm_units_even.cu) instead of multiples of 4")
     ap.add_argument("--rhs-tile-gb", type=float, default=None,
                     help="HBM budget of the two multi-RHS slabs (sizes the column groups; default: 40 %% of HBM)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -252,7 +254,7 @@ def main():
     if args.no_e2e:
         del edge_index
     bk = {"hess_sqrt": args.hess_sqrt, "syrk_impl": args.syrk, "fused_gemm": not args.no_fused_gemm,
-          "unit_slabs": not args.dense_slabs}
+          "unit_slabs": not args.dense_slabs, "unit_even_groups": args.unit_even_groups}
     if args.rhs_tile_gb is not None:
         bk["rhs_tile_bytes"] = int(args.rhs_tile_gb * 1e9)
     if pg is not None:
@@ -444,7 +446,8 @@ def main():
         "config": {"workload": workload_name(args.workload, h, l),
                    "nodes": n, "nnz": nnz, "features": f, "classes": c, "train_nodes": int(idx.numel()),
                    "hess_sqrt": args.hess_sqrt, "syrk": args.syrk, "scale": args.scale,
-                   "slabs": "dense" if args.dense_slabs else "unit-compacted below the output layer",
+                   "slabs": "dense" if args.dense_slabs else "unit-compacted below the output layer" +
+                   (", even column groups" if args.unit_even_groups else ""),
                    "l2": "inputs (>= 10 GB per SpMM) far exceed the 126 MB L2; no explicit flush",
                    "parallelism": "single GPU" if world == 1 else
                    f"row-partitioned x{world} (halo all-gather), backward over {args.backward_parallel}"},

@@ -158,7 +158,10 @@ int lgnn_spmm_packed_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr, con
  * [active unit slot][g] (the g values of a live unit contiguous) with a header word per 32 units,
  * hdr[n][w] = {uint32 mask, uint32 slot of the block's first live unit}; the SpMM then moves only the
  * live units' bytes and adds them in the neighbour order of lgnn_spmm_f32 (bit-identical result).
- * g in {4, 8, 12, 16}, h a multiple of 32 up to 1024 (lgnn_unit_slabs_supported).
+ * g even, 2 .. 16, h a multiple of 32 up to 1024 (lgnn_unit_slabs_supported).  For g % 4 == 2 a slot is
+ * 8*odd bytes, so every block's run starts on an EVEN slot (hdr "first" = the previous blocks' live counts,
+ * each rounded up to even): the runs stay 16-byte aligned for the SpMM's 16-byte copies, and the compact row
+ * still fits the dense pitch.
  *   lgnn_unit_pack_f32    slab [n_rows, lds] dense [g][h] rows -> compact, in place; act = H [n_rows, lda]
  *                         decides which units live (values of dead units are dropped, whatever they hold);
  *                         hdr: uint2 [n_rows, h/32]

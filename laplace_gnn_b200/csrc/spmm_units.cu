@@ -327,8 +327,9 @@ static int launch_units(int64_t n_rows, const int64_t* rowptr, const int32_t* co
   return LGNN_OK;
 }
 
+// g % 4 == 0: the kernels of this file; g % 4 == 2: spmm_units_even.cu (block runs start on even slots)
 static bool units_shape_ok(int64_t g, int64_t h) {
-  return g >= 4 && g <= 16 && g % 4 == 0 && h >= 32 && h <= 1024 && h % 32 == 0;
+  return g >= 2 && g <= 16 && g % 2 == 0 && h >= 32 && h <= 1024 && h % 32 == 0;
 }
 
 }  // namespace lgnn
@@ -340,7 +341,7 @@ extern "C" int lgnn_unit_slabs_supported(int64_t g, int64_t h) { return units_sh
 extern "C" int lgnn_unit_pack_f32(float* slab, int64_t lds, const float* act, int64_t lda, int64_t n_rows,
                                   int64_t g, int64_t h, void* hdr, lgnn_stream_t stream) {
   if (n_rows < 0) return fail(LGNN_E_BADARG, "unit_pack: negative row count");
-  if (!units_shape_ok(g, h)) return fail(LGNN_E_UNSUPPORTED, "unit_pack: g must be 4, 8, 12 or 16 and h a multiple of 32 up to 1024 (g=%lld h=%lld)", (long long)g, (long long)h);
+  if (!units_shape_ok(g, h)) return fail(LGNN_E_UNSUPPORTED, "unit_pack: g must be even, 2 .. 16, and h a multiple of 32 up to 1024 (g=%lld h=%lld)", (long long)g, (long long)h);
   if (n_rows == 0) return LGNN_OK;
   if (!slab || !act || !hdr) return fail(LGNN_E_BADARG, "unit_pack: null pointer");
   if (lds < g * h || lda < h) return fail(LGNN_E_BADARG, "unit_pack: pitch smaller than the row");
@@ -349,6 +350,7 @@ extern "C" int lgnn_unit_pack_f32(float* slab, int64_t lds, const float* act, in
   if (n_rows > 0x7fffffffLL) return fail(LGNN_E_UNSUPPORTED, "unit_pack: too many rows");
   cudaStream_t st = as_stream(stream);
   uint2* hd = reinterpret_cast<uint2*>(hdr);
+  if (g % 4 != 0) return unit_pack_even(slab, lds, act, lda, n_rows, (int)g, (int)h, hd, st);
   const unsigned grid = (unsigned)n_rows, block = (unsigned)h;
   switch (g / 4) {
     case 1: unit_pack_kernel<1><<<grid, block, 0, st>>>(slab, lds, act, lda, (int)h, hd); break;
@@ -365,7 +367,7 @@ extern "C" int lgnn_spmm_units_f32(int64_t n_rows, int64_t n_cols, int64_t nnz, 
                                    int64_t g, int64_t h, float* y, int64_t ldy, int flags,
                                    lgnn_stream_t stream) {
   if (n_rows < 0 || n_cols < 0 || nnz < 0) return fail(LGNN_E_BADARG, "spmm_units: negative size");
-  if (!units_shape_ok(g, h)) return fail(LGNN_E_UNSUPPORTED, "spmm_units: g must be 4, 8, 12 or 16 and h a multiple of 32 up to 1024 (g=%lld h=%lld)", (long long)g, (long long)h);
+  if (!units_shape_ok(g, h)) return fail(LGNN_E_UNSUPPORTED, "spmm_units: g must be even, 2 .. 16, and h a multiple of 32 up to 1024 (g=%lld h=%lld)", (long long)g, (long long)h);
   if (n_rows == 0) return LGNN_OK;
   if (!rowptr || !slab || !hdr || !y) return fail(LGNN_E_BADARG, "spmm_units: null pointer");
   if (nnz > 0 && (!col || !val)) return fail(LGNN_E_BADARG, "spmm_units: null col / val");
@@ -378,6 +380,10 @@ extern "C" int lgnn_spmm_units_f32(int64_t n_rows, int64_t n_cols, int64_t nnz, 
   const int variant = (flags >> 8) & 0xff;   // lab / test override of the unroll and occupancy choice
   // the pipelined kernel addresses the slab with 32-bit float4 offsets: slabs up to 64 GB
   const bool narrow = n_cols * lds <= ((int64_t)1 << 34);
+  if (g % 4 != 0) {
+    if (!narrow) return fail(LGNN_E_UNSUPPORTED, "spmm_units: g = %lld needs a slab of at most 64 GB", (long long)g);
+    return spmm_units_even(n_rows, rowptr, col, val, slab, lds, hd, (int)g, nblk, y, ldy, variant, st);
+  }
   if ((variant == 0 || variant >= 8) && narrow) {  // default: the staged kernel, 4 rows per group
     const int rpg = 4 << ((variant >> 2) & 1);     // 8..11: 4 rows per group, 12..15: 8 rows
     const int cfg = variant & 3;

@@ -152,7 +152,7 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact"):
+                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -191,6 +191,10 @@ class _B200KFAC:
         # half the bytes.  Column groups are then padded to a multiple of 4 with all-zero right-hand sides.
         self.unit_slabs = bool(unit_slabs)
         self.unit_min_width = int(unit_min_width)   # narrower slabs stay dense (one row is a few hundred bytes anyway)
+        # column groups of 2, 6, 10 or 14 as well (csrc/spmm_units_even.cu): a rank of the 8-GPU column split
+        # owns 6 of the products shape's 47 columns and would otherwise carry 8.  OFF by default until those
+        # kernels have been run against the dense SpMM on a B200 (tests/test_gpu_parity.py, LGNN_LAB=1)
+        self.unit_even_groups = bool(unit_even_groups)
         # A_0 = X^T X does not depend on the weights: with cache_input_factor the raw Gram matrix of
         # this rank's feature rows is kept (per backend, or in a dict shared across backends by the
         # epoch loop) and only rescaled per call
@@ -380,17 +384,18 @@ class _B200KFAC:
         if can_pack:                       # keep the hidden-layer slabs narrow enough for the packed SpMM
             grp = min(grp, max(1, ops.PACK_MAX_WIDTH // hidden))
         grp = lay.agree_min(max(1, min(grp, (c_count + lanes - 1) // lanes)))
-        # unit-compacted slabs want groups of 4, 8, 12 or 16 columns: the last group of a pass is padded
-        # with all-zero right-hand sides (47 classes -> 12 + 12 + 12 + 11(+1))
-        cand = min(room // 4 * 4, 16, (max(c_count, 1) + 3) // 4 * 4)
-        pad4 = (self._units_possible(lay) and not can_pack and cand >= 4 and
+        # unit-compacted slabs want groups of 4, 8, 12 or 16 columns (any even count with unit_even_groups):
+        # the last group of a pass is padded with all-zero right-hand sides (47 classes -> 16 + 16 + 15(+1))
+        q = 2 if self.unit_even_groups else 4
+        cand = min(room // q * q, 16, (max(c_count, 1) + q - 1) // q * q)
+        pad4 = (self._units_possible(lay) and not can_pack and cand >= q and
                 any(self._can_unit(lay, cand, h) for h in dims[:-1]))
         if pad4:
             grp = cand
         if c_count <= 0:
             return grp, 0
         groups = [(c0, min(grp, c_first + c_count - c0)) for c0 in range(c_first, c_first + c_count, grp)]
-        width_of = (lambda gc: (gc + 3) // 4 * 4) if pad4 else (lambda gc: gc)
+        width_of = (lambda gc: (gc + q - 1) // q * q) if pad4 else (lambda gc: gc)
         hdr = torch.empty(n_in, max(max(dims[:-1]) // 32, 1), 2, dtype=torch.int32, device=dev) if pad4 else None
         # W_l [d_l, d_{l-1}] as resident tensor-core operands, once per pass
         Wp = [None] + [ops.gemm_mask_prepare(Ws[l]) if self.fused_gemm and dev.type == "cuda" and
@@ -552,7 +557,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact"):
+                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -563,7 +568,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
                          backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs,
-                         unit_min_width, diag_mode)
+                         unit_min_width, diag_mode, unit_even_groups)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

@@ -124,7 +124,7 @@ def pack_rows(x, d=None, out=None):
 
 
 def unit_slabs_supported(g, h):
-    return 4 <= g <= 16 and g % 4 == 0 and 32 <= h <= 1024 and h % 32 == 0
+    return 2 <= g <= 16 and g % 2 == 0 and 32 <= h <= 1024 and h % 32 == 0
 
 
 def unit_pack(slab, act, g, hdr=None):

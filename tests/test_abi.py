@@ -45,6 +45,11 @@ def test_bad_arguments_are_rejected_before_any_launch():
     # unit-compacted slabs: shape support is a host-side predicate; bad shapes / pitches never launch
     assert lib.lgnn_unit_slabs_supported(12, 256) == 1 and lib.lgnn_unit_slabs_supported(16, 1024) == 1
     assert lib.lgnn_unit_slabs_supported(11, 256) == 0 and lib.lgnn_unit_slabs_supported(12, 100) == 0
+    # g % 4 == 2: the even-group kernels (spmm_units_even.cu) behind the same entry points
+    assert all(lib.lgnn_unit_slabs_supported(g, 256) == 1 for g in (2, 6, 10, 14))
+    assert lib.lgnn_unit_slabs_supported(18, 256) == 0 and lib.lgnn_unit_slabs_supported(0, 256) == 0
+    assert lib.lgnn_unit_pack_f32(None, 1536, None, 256, 10, 6, 256, None, None) == -1          # null pointers
+    assert lib.lgnn_spmm_units_f32(5, 5, 10, None, None, None, None, 1536, None, 6, 256, None, 1536, 0, None) == -1
     assert lib.lgnn_unit_pack_f32(None, 3072, None, 256, 10, 11, 256, None, None) == -5          # LGNN_E_UNSUPPORTED
     assert lib.lgnn_unit_pack_f32(None, 3072, None, 256, 10, 12, 256, None, None) == -1          # null pointers
     assert lib.lgnn_unit_pack_f32(None, 3072, None, 256, 0, 12, 256, None, None) == 0            # nothing to do

@@ -92,6 +92,14 @@ def _unit_worker(rank, world, port, out):
             for fa, fb in zip(kron.kfacs, ref[1].kfacs):
                 for a, b in zip(fa, fb):
                     assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+        # unit_even_groups: the rank's 5 columns travel as a group of 6 instead of 8
+        be = L.B200GGN(model, "classification", process_group=dist.group.WORLD, backward_parallel="columns",
+                       unit_min_width=0, unit_even_groups=True)
+        loss, kron = be.kron(idx, y, N=len(y))
+        assert be.last_stats["group"] == 6 and be.last_stats["unit_slabs"] > 0
+        for fa, fb in zip(kron.kfacs, ref[1].kfacs):
+            for a, b in zip(fa, fb):
+                assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
         out[rank] = True
     finally:
         dist.destroy_process_group()

@@ -1,0 +1,94 @@
+"""GPU tests of the unit-compacted slabs for column groups with g % 4 == 2 (csrc/spmm_units_even.cu) — the
+kernels behind ``B200GGN(unit_even_groups=True)``, which is OFF by default.  They run with LGNN_LAB=1 only:
+the default ``-m gpu`` run covers what the package uses by default."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import lab_only, max_rel_err
+from helpers import unit_layout
+from oracle import gcn_kfac_oracle as O
+
+pytestmark = [pytest.mark.gpu, lab_only]
+
+DEV = "cuda:0"
+
+
+def _masked_slab(n, g, h, density, seed, pitch_extra=0):
+    gen = torch.Generator(device=DEV).manual_seed(seed)
+    act = torch.randn(n, h, device=DEV, generator=gen)
+    act *= (torch.rand(n, h, device=DEV, generator=gen) < density)
+    act[3] = 0                                                              # a node with no live unit
+    if n > 5:
+        act[5] = 1                                                          # ... and one with all of them
+    slab = torch.randn(n, g * h + pitch_extra, device=DEV, generator=gen)
+    slab[:, : g * h].view(n, g, h).mul_((act > 0)[:, None, :])
+    return slab, act
+
+
+@pytest.mark.parametrize("g,h", [(2, 32), (6, 64), (6, 256), (10, 256), (14, 256), (6, 96), (2, 1024)])
+@pytest.mark.parametrize("density", [0.0, 0.5, 1.0])
+def test_unit_pack_even_layout(g, h, density):
+    """Header words and the in-place [slot][g] layout with every block's run on an even slot."""
+    from laplace_gnn_b200 import ops
+    n = 257
+    slab, act = _masked_slab(n, g, h, density, seed=g * 1000 + h, pitch_extra=4)
+    dense = slab[:, : g * h].view(n, g, h).cpu().numpy().copy()
+    live = (act > 0).cpu().numpy()
+    us = ops.unit_pack(slab, act, g)
+    hdr = us.hdr.cpu().numpy().view(np.uint32)
+    out = slab.cpu().numpy()
+    for r in range(n):
+        want_hdr, slot = unit_layout(live[r], g)
+        for w, (mask, first) in enumerate(want_hdr):
+            assert hdr[r, w, 0] == mask and hdr[r, w, 1] == first and first % 2 == 0
+        for u in np.nonzero(live[r])[0]:
+            assert np.array_equal(out[r, slot[u] * g: slot[u] * g + g], dense[r][:, u])
+
+
+@pytest.mark.parametrize("g,h", [(2, 32), (6, 64), (6, 256), (10, 256), (14, 256), (6, 96), (10, 512)])
+@pytest.mark.parametrize("density", [0.0, 0.5, 1.0])
+def test_unit_spmm_even_is_bit_identical_to_dense(g, h, density):
+    from laplace_gnn_b200 import ops
+    import laplace_gnn_b200 as L
+    n = 5000
+    ei = O.synthetic_edges(n, 40_000, seed=g + h)
+    G = L.Graph.from_edge_index(torch.from_numpy(ei).to(DEV), n)
+    slab, act = _masked_slab(n, g, h, density, seed=g * 7 + h, pitch_extra=8)
+    masked = slab.clone()
+    dense = ops.spmm(G.ahat, masked, d=g * h, impl="ldg")
+    dense_t = ops.spmm(G.ahat_t, masked, d=g * h, impl="ldg")
+    us = ops.unit_pack(slab, act, g)
+    for variant in [0, 1, 2] + list(range(8, 16)):
+        y = ops.spmm_units(G.ahat, us, variant=variant)
+        assert torch.equal(y, dense), variant
+    out = torch.full((n, g * h + 12), -1.0, device=DEV)
+    ops.spmm_units(G.ahat_t, us, out=out)
+    assert torch.equal(out[:, : g * h], dense_t)
+    assert bool((out[:, g * h:] == -1).all())
+
+
+@pytest.mark.parametrize("h,C,layers", [(64, 10, 3), (256, 6, 3), (256, 5, 2), (128, 14, 2)])
+def test_even_groups_give_the_same_factors(h, C, layers):
+    """B200GGN(unit_even_groups=True) against dense slabs: same loss, factors equal to SYRK rounding."""
+    import laplace_gnn_b200 as L
+    n, U, F = 3000, 15_000, 20
+    ei = torch.from_numpy(O.synthetic_edges(n, U, seed=h + C)).to(DEV)
+    graph = L.Graph.from_edge_index(ei, n)
+    gen = torch.Generator().manual_seed(h)
+    X = torch.randn(n, F, generator=gen).to(DEV)
+    torch.manual_seed(C)
+    model = L.SparseGCN(F, h, C, layers, X, graph).to(DEV)
+    idx = torch.randperm(n, generator=gen)[: int(0.6 * n)].sort().values.to(DEV)
+    y = torch.randint(0, C, (idx.numel(),), generator=gen).to(DEV)
+    be1 = L.B200GGN(model, "classification", unit_slabs=True, unit_min_width=0, unit_even_groups=True)
+    be2 = L.B200GGN(model, "classification", unit_slabs=False)
+    l1, k1 = be1.kron(idx, y, N=len(y))
+    l2, k2 = be2.kron(idx, y, N=len(y))
+    assert be1.last_stats["unit_slabs"] > 0 and be1.last_stats["group"] % 2 == 0
+    if C in (5, 6, 10, 14):
+        assert be1.last_stats["group"] % 4 == 2          # the group really took the even-g kernels
+    assert float(l1) == float(l2)
+    for fa, fb in zip(k1.kfacs, k2.kfacs):
+        for a, b in zip(fa, fb):
+            assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5

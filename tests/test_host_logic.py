@@ -286,6 +286,26 @@ def test_unit_compacted_groups_give_the_same_factors(fake_ops, C, layers, budget
             assert max_rel_err(a.numpy(), b.numpy()) <= 1e-5
 
 
+@pytest.mark.parametrize("C,want_group", [(6, 6), (5, 6), (10, 10), (7, 8), (47, 16)])
+def test_even_column_groups_take_what_the_rank_owns(fake_ops, C, want_group):
+    """unit_even_groups: groups of any even width (csrc/spmm_units_even.cu) — the 6 (or 5) columns a rank of the
+    8-GPU column split owns travel as 6, not 8; the default keeps multiples of 4."""
+    import laplace_gnn_b200 as L
+    model, idx, y = _synthetic_model(400, 1600, 12, 64, C, 3)
+    be1 = L.B200GGN(model, "classification", unit_min_width=0, unit_even_groups=True)
+    be2 = L.B200GGN(model, "classification", unit_min_width=0)
+    be3 = L.B200GGN(model, "classification", unit_slabs=False)
+    l1, k1 = be1.kron(idx, y, N=len(y))
+    l2, k2 = be2.kron(idx, y, N=len(y))
+    l3, k3 = be3.kron(idx, y, N=len(y))
+    assert be1.last_stats["group"] == want_group and be1.last_stats["unit_slabs"] > 0
+    assert be2.last_stats["group"] == min(16, (C + 3) // 4 * 4)
+    assert float(l1) == float(l2) == float(l3)
+    for fa, fb, fc in zip(k1.kfacs, k2.kfacs, k3.kfacs):
+        for a, b, c in zip(fa, fb, fc):
+            assert max_rel_err(a.numpy(), c.numpy()) <= 1e-5 and max_rel_err(b.numpy(), c.numpy()) <= 1e-5
+
+
 def test_bench_clock_sampler_keeps_the_timed_region(monkeypatch):
     """bench.ClockSampler: nvidia-smi lines stamped outside the timed region are dropped, throttle reasons
     inside it are reported, an unparsable stamp keeps the sample."""
