@@ -152,7 +152,7 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False):
+                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=True):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -195,6 +195,9 @@ class _B200KFAC:
         # owns 6 of the products shape's 47 columns and would otherwise carry 8.  OFF by default until those
         # kernels have been run against the dense SpMM on a B200 (tests/test_gpu_parity.py, LGNN_LAB=1)
         self.unit_even_groups = bool(unit_even_groups)
+        # with a process group the stand-in KronLaplace spreads the factor eigendecompositions over the ranks
+        # (kron.Kron.decompose); False keeps them replicated
+        self.shard_eigh = bool(shard_eigh)
         # A_0 = X^T X does not depend on the weights: with cache_input_factor the raw Gram matrix of
         # this rank's feature rows is kept (per backend, or in a dict shared across backends by the
         # epoch loop) and only rescaled per call
@@ -557,7 +560,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False):
+                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=True):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -568,7 +571,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
                          backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs,
-                         unit_min_width, diag_mode, unit_even_groups)
+                         unit_min_width, diag_mode, unit_even_groups, shard_eigh)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

@@ -35,6 +35,45 @@ def _eigh_psd(m: torch.Tensor):
     return torch.nan_to_num(lam.clamp(min=0.0)), torch.nan_to_num(q)
 
 
+def eigh_assignment(sizes: Sequence[int], world: int) -> list[int]:
+    """Owner rank of each factor: largest first onto the least-loaded rank (cost ~ n^3), ties to the lower
+    rank — a pure function of the sizes, so every rank computes the same table."""
+    load = [0] * world
+    owner = [0] * len(sizes)
+    for i in sorted(range(len(sizes)), key=lambda i: (-sizes[i], i)):
+        r = min(range(world), key=lambda r: (load[r], r))
+        owner[i] = r
+        load[r] += sizes[i] ** 3
+    return owner
+
+
+def _sharded_eigh(factors: Sequence[torch.Tensor], process_group):
+    """[(eigenvalues, eigenvectors)] of every factor, each computed by one rank and all-gathered."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(process_group), dist.get_world_size(process_group)
+    sizes = [int(h.shape[-1]) for h in factors]
+    owner = eigh_assignment(sizes, world)
+    seg = max(sum(n + n * n for n, o in zip(sizes, owner) if o == r) for r in range(world))
+    dev, dt = factors[0].device, factors[0].dtype
+    buf = torch.zeros(world, seg, dtype=dt, device=dev)
+    off = 0
+    for h, n, o in zip(factors, sizes, owner):
+        if o == rank:
+            lam, q = _eigh_psd(h)
+            buf[rank, off:off + n] = lam
+            buf[rank, off + n:off + n + n * n] = q.reshape(-1)
+            off += n + n * n
+    mine = buf[rank] if buf.is_cuda else buf[rank].clone()      # gloo (CPU tests): no in-place guarantee
+    dist.all_gather_into_tensor(buf.view(-1), mine, group=process_group)
+    offs = [0] * world
+    out = []
+    for n, o in zip(sizes, owner):
+        a = offs[o]
+        out.append((buf[o, a:a + n].clone(), buf[o, a + n:a + n + n * n].reshape(n, n).clone()))
+        offs[o] = a + n + n * n
+    return out
+
+
 class Kron:
     """Block-diagonal Kronecker-factored matrix: one block per parameter tensor, a block is
     ``[G, A]`` (weight: G ⊗ A, output-side factor first) or ``[G]`` (bias)."""
@@ -76,21 +115,36 @@ class Kron:
 
     __rmul__ = __mul__
 
-    def decompose(self, damping: bool = False) -> "KronDecomposed":
+    def decompose(self, damping: bool = False, process_group=None) -> "KronDecomposed":
         """eigh per factor (matrix.py:118-145).  A bias block's G that the backend marked as a copy
         of the preceding weight block's G (``_dup_of``) reuses that decomposition instead of
-        repeating the identical eigh — same values, one third fewer eigendecompositions."""
-        vecs, vals = [], []
-        done = {}
+        repeating the identical eigh — same values, one third fewer eigendecompositions.
+
+        With a ``process_group`` (the multi-GPU pass: every rank holds the same all-reduced factors) the
+        distinct factors are spread over the ranks, each rank decomposes its share and ONE all-gather hands
+        everybody the same eigenpairs — bit-identical across ranks by construction, and the replicated
+        2L sequential cusolver calls (12 ms on the products shape, 4 % of an 8-GPU step) become one."""
+        distinct, owner_of = [], {}
         for f in self.kfacs:
-            pairs = []
             for h in f:
                 src = getattr(h, "_dup_of", None)
-                key = id(src) if src is not None and id(src) in done else None
-                pairs.append(done[key] if key is not None else _eigh_psd(h))
-                done[id(h)] = pairs[-1]
-            vals.append([p[0] for p in pairs])
-            vecs.append([p[1] for p in pairs])
+                if src is not None and id(src) in owner_of:
+                    owner_of[id(h)] = owner_of[id(src)]
+                else:
+                    owner_of[id(h)] = len(distinct)
+                    distinct.append(h)
+        world = 1
+        if process_group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(process_group)
+        if world > 1 and len(distinct) > 1:
+            pairs = _sharded_eigh(distinct, process_group)
+        else:
+            pairs = [_eigh_psd(h) for h in distinct]
+        vecs, vals = [], []
+        for f in self.kfacs:
+            vals.append([pairs[owner_of[id(h)]][0] for h in f])
+            vecs.append([pairs[owner_of[id(h)]][1] for h in f])
         return KronDecomposed(vecs, vals, damping=damping)
 
     def diag(self) -> torch.Tensor:
@@ -318,7 +372,10 @@ class KronLaplace(_ParametricLaplaceLite):
         self.H = self.H_facs
         super().fit(train_loader, override=override)
         self.H_facs = self.H
-        self.H = self.H_facs.decompose()
+        # multi-GPU pass: the factors are all-reduced, the eigendecompositions are spread over the ranks
+        pg = getattr(self.backend, "process_group", None)
+        shard = pg is not None and getattr(self.backend, "shard_eigh", True)
+        self.H = self.H_facs.decompose(process_group=pg) if shard else self.H_facs.decompose()
 
     @property
     def posterior_precision(self) -> KronDecomposed:

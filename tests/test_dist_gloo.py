@@ -124,3 +124,51 @@ def test_column_share_covers_all_columns_once():
             assert seen == list(range(C))
             sizes = [column_share(C, r, world)[1] for r in range(world)]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _eigh_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from laplace_gnn_b200.kron import Kron
+        gen = torch.Generator().manual_seed(7)
+        blocks = []
+        for n_out, n_in in ((16, 9), (16, 16), (5, 16)):
+            a, b = torch.randn(40, n_out, generator=gen), torch.randn(40, n_in, generator=gen)
+            G, A = a.T @ a, b.T @ b
+            dup = G.clone()
+            dup._dup_of = G
+            blocks += [[G, A], [dup]]
+        k = Kron(blocks)
+        ref = k.decompose()
+        got = k.decompose(process_group=dist.group.WORLD)
+        for vr, vg, qr, qg in zip(ref.eigenvalues, got.eigenvalues, ref.eigenvectors, got.eigenvectors):
+            for a, b in zip(vr + qr, vg + qg):
+                assert torch.equal(a, b)             # same LAPACK call on the same input, whoever ran it
+        assert float(got.logdet()) == float(ref.logdet())
+        out[rank] = float((got + torch.tensor(0.5)).logdet())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_eigh_equals_replicated(world):
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_eigh_worker, args=(world, port, out), nprocs=world, join=True)
+        vals = list(out.values())
+        assert len(vals) == world and all(v == vals[0] for v in vals)
+
+
+def test_eigh_assignment_balances_cubic_cost():
+    from laplace_gnn_b200.kron import eigh_assignment
+    sizes = [256, 100, 256, 256, 47, 256]                 # G_1, A_1, G_2, A_2, G_3, A_3 of the products shape
+    own = eigh_assignment(sizes, 8)
+    assert sorted(own) == [0, 1, 2, 3, 4, 5]              # six factors, six ranks, nobody holds two
+    own = eigh_assignment(sizes, 2)
+    load = [sum(s ** 3 for s, o in zip(sizes, own) if o == r) for r in range(2)]
+    assert abs(load[0] - load[1]) <= 100 ** 3 + 47 ** 3
+    assert eigh_assignment(sizes, 1) == [0] * 6 and eigh_assignment([], 4) == []
