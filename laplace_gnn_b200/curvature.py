@@ -118,6 +118,7 @@ class _Whole:
         self.slot0 = 0
         self.communicates = False
         self.csr_t_top = None        # Â^T with the edges from non-train rows zeroed (set per kron call)
+        self.split_t = None          # Â^T with its hub rows cut into pieces (graph.SplitCSR), for the unit SpMM
 
     def gather(self, slab):
         pass
@@ -135,6 +136,7 @@ class _Rows:
         self.n_local, self.total_rows, self.slot0 = part.n_local, part.total_rows, part.slot0
         self.communicates = True
         self.csr_t_top = None
+        self.split_t = None
 
     def gather(self, slab):
         self.part.all_gather_slab(slab)
@@ -152,7 +154,7 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=True):
+                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=True, unit_hub_split=False):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -198,6 +200,12 @@ class _B200KFAC:
         # with a process group the stand-in KronLaplace spreads the factor eigendecompositions over the ranks
         # (kron.Kron.decompose); False keeps them replicated
         self.shard_eigh = bool(shard_eigh)
+        # power-law graphs: the unit SpMM gives one warp group a whole row, so graphs with rows beyond
+        # unit_row_limit non-zeros keep dense slabs — unless unit_hub_split cuts those rows into pieces
+        # (graph.split_hub_rows; the pieces are summed by a small SpMM afterwards).  OFF by default until the
+        # R-MAT sweep has run with it on a B200 (tools/rmat_sweep.py --hub-split)
+        self.unit_hub_split = bool(unit_hub_split)
+        self.unit_row_limit = 4096
         # A_0 = X^T X does not depend on the weights: with cache_input_factor the raw Gram matrix of
         # this rank's feature rows is kept (per backend, or in a dict shared across backends by the
         # epoch loop) and only rescaled per call
@@ -317,7 +325,13 @@ class _B200KFAC:
         packed = units = None
         for l in range(L - 1, -1, -1):
             gz = Q[: n_loc * gq * ld].view(n_loc, gq * ld)
-            if units is not None:
+            if units is not None and lay.split_t is not None:
+                sp = lay.split_t                    # hub rows in pieces: extra output rows behind the slab
+                gz_all = Q[: (n_loc + sp.n_extra) * gq * ld].view(n_loc + sp.n_extra, gq * ld)
+                ops.spmm_units(sp.csr, units, out=gz_all)
+                sp.finish(gz_all, gq * ld)
+                self._n_unit_spmm += 1
+            elif units is not None:
                 ops.spmm_units(lay.csr_t, units, out=gz)
                 self._n_unit_spmm += 1
             elif packed is not None:
@@ -358,7 +372,8 @@ class _B200KFAC:
         """Unit-compacted slabs need every row local and a graph without hub rows (the kernel gives one
         warp a whole row)."""
         mx = lay.csr_t.max_row_nnz
-        return self.unit_slabs and not lay.communicates and mx is not None and mx <= 4096
+        return (self.unit_slabs and not lay.communicates and mx is not None and
+                (mx <= self.unit_row_limit or lay.split_t is not None))
 
     def _can_unit(self, lay, g: int, h: int) -> bool:
         return (self._units_possible(lay) and g * h >= self.unit_min_width and
@@ -405,12 +420,13 @@ class _B200KFAC:
                        ops.gemm_mask_supported(Ws[l].shape[0], Ws[l].shape[1]) else None
                        for l in range(1, len(Ws))]
         lanes = min(lanes, len(groups))
+        n_split = lay.split_t.n_extra if (pad4 and lay.split_t is not None) else 0
         # two slabs per lane, alternating as SpMM input / output; a packed slab needs its header on top
         row_floats = grp * dmax
         if can_pack:
             row_floats = max(row_floats, (ops.pack_rows_pitch(grp * hidden) + 3) // 4)
         bufs = [(_slab(dev, i, 0, n_in * row_floats),
-                 _slab(dev, i, 1, max(n_in if can_pack else n_loc, 1) * row_floats))
+                 _slab(dev, i, 1, max(n_in if can_pack else n_loc + n_split, 1) * row_floats))
                 for i in range(lanes)]
         if lanes == 1:
             for c0, gc in groups:
@@ -488,6 +504,13 @@ class _B200KFAC:
         G = [torch.zeros(w.shape[0], w.shape[0], dtype=torch.float32, device=dev) for w in Ws]
         self._n_unit_spmm = 0
         whole = _Whole(g)
+        mx_t = g.ahat_t.max_row_nnz
+        if self.unit_slabs and self.unit_hub_split and mx_t is not None and mx_t > self.unit_row_limit:
+            from .graph import split_hub_rows
+            cache = g.meta.setdefault("_split_t", {})            # per graph, per limit: index work done once
+            if self.unit_row_limit not in cache:
+                cache[self.unit_row_limit] = split_hub_rows(g.ahat_t, self.unit_row_limit)
+            whole.split_t = cache[self.unit_row_limit]
         if self.skip_zero_rows and (part is None or self.backward_parallel == "columns") and M < g.n:
             keep = torch.zeros(g.n, dtype=torch.uint8, device=dev)
             keep[idx] = 1
@@ -560,7 +583,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=True):
+                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=True, unit_hub_split=False):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -571,7 +594,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
                          backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs,
-                         unit_min_width, diag_mode, unit_even_groups, shard_eigh)
+                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

@@ -64,6 +64,68 @@ class Graph:
 
 
 # ------------------------------------------------------------------------------------------------
+# hub rows of power-law graphs, for the kernels that give one warp group a whole row
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class SplitCSR:
+    """A CSR whose rows longer than ``limit`` non-zeros are cut into pieces of at most ``limit``: the first
+    piece stays in the row, the others become extra rows appended behind the matrix (rows n_rows ..
+    n_rows + n_extra - 1, hub by hub, piece by piece).  ``finish`` adds the extra rows of an SpMM result
+    onto their owners.  (col, val) of the extra pieces are moved to the end; everything else keeps its place
+    and its order."""
+    csr: CSR                 # [n_rows + n_extra, n_cols]
+    n_rows: int              # rows of the original matrix
+    n_extra: int
+    hub_rows: torch.Tensor   # int64 [n_hub] rows that were cut, ascending
+    gather: CSR              # [n_hub, n_extra] ones: row k lists the extra rows of hub k, in piece order
+
+    def finish(self, y: torch.Tensor, d: int) -> torch.Tensor:
+        """y: [>= n_rows + n_extra, ld] holding the SpMM over ``csr``; returns y[:n_rows] with the pieces summed
+        (each hub's extra rows in piece order, then onto the first piece)."""
+        extra = y[self.n_rows:self.n_rows + self.n_extra]
+        sums = ops.spmm(self.gather, extra, d=d)
+        y[self.hub_rows, :d] = y[self.hub_rows, :d] + sums
+        return y[:self.n_rows]
+
+
+def split_hub_rows(a: CSR, limit: int = 4096) -> SplitCSR | None:
+    """``SplitCSR`` of ``a``, or None when no row is longer than ``limit``.  Index arithmetic only (torch, on
+    the matrix's device), done once per graph."""
+    if limit < 1:
+        raise ValueError("split_hub_rows: limit must be positive")
+    rp = a.rowptr
+    lens = rp[1:] - rp[:-1]
+    extra_per_row = torch.clamp((lens + (limit - 1)) // limit - 1, min=0)
+    hub_rows = torch.nonzero(extra_per_row > 0).reshape(-1)
+    if hub_rows.numel() == 0:
+        return None
+    dev = rp.device
+    n, nnz = a.n_rows, a.nnz
+    n_extra = int(extra_per_row.sum())
+    # entries past the first `limit` of a hub row move behind the matrix; only the hub rows are visited
+    moved = torch.zeros(nnz, dtype=torch.bool, device=dev)
+    new_lens = lens.clone()
+    extra_lens = []
+    begins, ends = rp[hub_rows].tolist(), rp[hub_rows + 1].tolist()       # one host read for all hubs
+    new_lens[hub_rows] = limit
+    for b, e in zip(begins, ends):                               # the hubs only, not the graph
+        moved[b + limit:e] = True
+        rest = e - b - limit
+        extra_lens += [limit] * (rest // limit) + ([rest % limit] if rest % limit else [])
+    all_lens = torch.cat([new_lens, torch.tensor(extra_lens, dtype=torch.int64, device=dev)])
+    rowptr = torch.zeros(n + n_extra + 1, dtype=torch.int64, device=dev)
+    rowptr[1:] = torch.cumsum(all_lens, 0)
+    col = torch.cat([a.col[~moved], a.col[moved]])
+    val = None if a.val is None else torch.cat([a.val[~moved], a.val[moved]])
+    csr = CSR(n + n_extra, a.n_cols, rowptr, col, val, min(limit, int(lens.max())))
+    g_rowptr = torch.zeros(hub_rows.numel() + 1, dtype=torch.int64, device=dev)
+    g_rowptr[1:] = torch.cumsum(extra_per_row[hub_rows], 0)
+    gather = CSR(int(hub_rows.numel()), n_extra, g_rowptr, torch.arange(n_extra, dtype=torch.int32, device=dev),
+                 torch.ones(n_extra, dtype=torch.float32, device=dev), int(extra_per_row.max()))
+    return SplitCSR(csr, n, n_extra, hub_rows, gather)
+
+
+# ------------------------------------------------------------------------------------------------
 # graph ingest (SURVEY §8f row 4): on-disk cache of the built CSR, k-nearest-neighbour graphs
 # ------------------------------------------------------------------------------------------------
 

@@ -1,5 +1,5 @@
 """GPU tests of the unit-compacted slabs for column groups with g % 4 == 2 (csrc/spmm_units_even.cu) — the
-kernels behind ``B200GGN(unit_even_groups=True)``, which is OFF by default.  They run with LGNN_LAB=1 only:
+kernels behind ``B200GGN(unit_even_groups=True)`` — and of ``unit_hub_split=True``; both are OFF by default.  They run with LGNN_LAB=1 only:
 the default ``-m gpu`` run covers what the package uses by default."""
 import numpy as np
 import pytest
@@ -90,5 +90,32 @@ def test_even_groups_give_the_same_factors(h, C, layers):
         assert be1.last_stats["group"] % 4 == 2          # the group really took the even-g kernels
     assert float(l1) == float(l2)
     for fa, fb in zip(k1.kfacs, k2.kfacs):
+        for a, b in zip(fa, fb):
+            assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("limit", [64, 1000])
+def test_hub_split_gives_the_same_factors(limit):
+    """B200GGN(unit_hub_split=True) on an R-MAT graph whose hub rows exceed the (lowered) row limit of the unit
+    SpMM: pieces as extra output rows + the gather SpMM, against dense slabs."""
+    import laplace_gnn_b200 as L
+    n, C, h = 6000, 12, 256
+    ei = torch.from_numpy(O.synthetic_edges(n, 120_000, seed=11, rmat=True, directed=True)).to(DEV)
+    graph = L.Graph.from_edge_index(ei, n)
+    assert graph.ahat_t.max_row_nnz > 1000
+    gen = torch.Generator().manual_seed(2)
+    X = torch.randn(n, 24, generator=gen).to(DEV)
+    torch.manual_seed(2)
+    model = L.SparseGCN(24, h, C, 3, X, graph).to(DEV)
+    idx = torch.randperm(n, generator=gen)[: int(0.6 * n)].sort().values.to(DEV)
+    y = torch.randint(0, C, (idx.numel(),), generator=gen).to(DEV)
+    be0 = L.B200GGN(model, "classification", unit_slabs=False)
+    l0, k0 = be0.kron(idx, y, N=len(y))
+    be1 = L.B200GGN(model, "classification", unit_hub_split=True)
+    be1.unit_row_limit = limit
+    l1, k1 = be1.kron(idx, y, N=len(y))
+    assert be1.last_stats["unit_slabs"] > 0 and graph.meta["_split_t"][limit].n_extra > 0
+    assert float(l0) == float(l1)
+    for fa, fb in zip(k1.kfacs, k0.kfacs):
         for a, b in zip(fa, fb):
             assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5

@@ -306,6 +306,45 @@ def test_even_column_groups_take_what_the_rank_owns(fake_ops, C, want_group):
             assert max_rel_err(a.numpy(), c.numpy()) <= 1e-5 and max_rel_err(b.numpy(), c.numpy()) <= 1e-5
 
 
+@pytest.mark.parametrize("limit", [1, 16, 64])
+def test_hub_rows_are_split_for_the_unit_spmm(fake_ops, limit):
+    """unit_hub_split: a power-law graph whose longest row exceeds the unit kernel's row limit takes the
+    unit-compacted slabs through graph.split_hub_rows (pieces as extra rows, summed afterwards) and gives the
+    factors of the dense slabs; without the switch it keeps dense slabs."""
+    import laplace_gnn_b200 as L
+    from laplace_gnn_b200.graph import split_hub_rows
+    from oracle import gcn_kfac_oracle as O
+    n, C = 500, 6
+    ei = torch.from_numpy(O.synthetic_edges(n, 6000, seed=3, rmat=True, directed=True))
+    graph = L.Graph.from_edge_index(ei, n)
+    assert graph.ahat_t.max_row_nnz > 64
+    gen = torch.Generator().manual_seed(1)
+    torch.manual_seed(1)
+    model = L.SparseGCN(9, 64, C, 3, torch.randn(n, 9, generator=gen), graph)
+    idx = torch.randperm(n, generator=gen)[:300].sort().values
+    y = torch.randint(0, C, (300,), generator=gen)
+    ref = L.B200GGN(model, "classification", unit_slabs=False)
+    l0, k0 = ref.kron(idx, y, N=300)
+    plain = L.B200GGN(model, "classification", unit_min_width=0)
+    plain.unit_row_limit = limit
+    plain.kron(idx, y, N=300)
+    assert plain.last_stats["unit_slabs"] == 0                      # hub rows and no split: dense slabs
+    be = L.B200GGN(model, "classification", unit_min_width=0, unit_hub_split=True)
+    be.unit_row_limit = limit
+    l1, k1 = be.kron(idx, y, N=300)
+    assert be.last_stats["unit_slabs"] > 0
+    sp = graph.meta["_split_t"][limit]
+    lens = sp.csr.rowptr[1:] - sp.csr.rowptr[:-1]
+    assert int(lens.max()) <= limit and sp.csr.nnz == graph.ahat_t.nnz and sp.csr.n_rows == n + sp.n_extra
+    assert float(l1) == float(l0)
+    for fa, fb in zip(k1.kfacs, k0.kfacs):
+        for a, b in zip(fa, fb):
+            assert max_rel_err(a.numpy(), b.numpy()) <= 1e-5
+    assert split_hub_rows(graph.ahat_t, 10 ** 6) is None
+    be.kron(idx, y, N=300)                                          # second call: the split is cached on the graph
+    assert graph.meta["_split_t"][limit] is sp
+
+
 def test_bench_clock_sampler_keeps_the_timed_region(monkeypatch):
     """bench.ClockSampler: nvidia-smi lines stamped outside the timed region are dropped, throttle reasons
     inside it are reported, an unparsable stamp keeps the sample."""

@@ -14,6 +14,8 @@ ap.add_argument("--degrees", default="16,64")
 ap.add_argument("--features", type=int, default=128)
 ap.add_argument("--classes", type=int, default=16)
 ap.add_argument("--hidden", type=int, default=256)
+ap.add_argument("--hub-split", action="store_true",
+                help="also time the fit with unit_hub_split=True (unit-compacted slabs on graphs with hub rows)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
@@ -67,6 +69,16 @@ for scale in [int(v) for v in a.scales.split(",")]:
             return la.log_marginal_likelihood()
         ms = timed(fit, reps=2)
         row += f" {ms:8.1f} ms {n/ms*1e3/1e6:6.2f} Mnodes/s"
+        if a.hub_split:
+            ml_dense = float(fit())
+            def fit_split():
+                la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs={"unit_hub_split": True})
+                la.fit(L.TensorBatchLoader(idx, yl))
+                return la.log_marginal_likelihood(), la.backend.last_stats["unit_slabs"]
+            ms2 = timed(fit_split, reps=2)
+            ml_split, n_units = fit_split()
+            row += (f" | hub split {ms2:8.1f} ms {n/ms2*1e3/1e6:6.2f} Mnodes/s, unit SpMMs {n_units}, "
+                    f"marglik rel diff {abs(float(ml_split) - ml_dense) / abs(ml_dense):.1e}")
         print(row, flush=True)
         del model, X, g
         torch.cuda.empty_cache()
