@@ -62,6 +62,19 @@ def _slab(dev, lane: int, slot: int, numel: int) -> torch.Tensor:
     return t[:max(numel, 1)]
 
 
+_LANE_STREAMS: dict = {}
+
+
+def _lane_streams(dev, lanes: int):
+    """The side streams of the overlapped row-partitioned backward, created once per device: per-stream
+    scratch (SYRK partials, ops._workspace) is keyed by stream and would otherwise be re-created for every
+    stream torch's pool hands out."""
+    have = _LANE_STREAMS.setdefault((dev.type, dev.index), [])
+    while len(have) < lanes:
+        have.append(torch.cuda.Stream(dev))
+    return have[:lanes]
+
+
 def workspace_bytes(dev=None) -> int:
     """Bytes held by the persistent slab workspace (on ``dev``, or everywhere)."""
     return sum(t.numel() * 4 for k, t in _SLABS.items()
@@ -436,7 +449,7 @@ class _B200KFAC:
         # two column groups in flight, each on its own stream with its own buffers and factor
         # accumulators: while one waits for its all-gather the other runs its SpMM / SYRK / GEMM
         main = torch.cuda.current_stream(dev)
-        streams = [torch.cuda.Stream(dev) for _ in range(lanes)]
+        streams = _lane_streams(dev, lanes)
         G_lane = [G] + [[torch.zeros_like(t) for t in G] for _ in range(lanes - 1)]
         for st in streams:
             st.wait_stream(main)

@@ -75,7 +75,7 @@ def marglik_training(model, train_idx, train_y, val_idx, val_y, n_epochs: int = 
             loss = crit(model(idx_b), y_b)
             loss.backward()
             opt.step()
-            epoch_loss += float(loss)
+            epoch_loss += float(loss.detach())
         res.losses.append(epoch_loss)
 
         if adj_opt is not None and epoch < n_hyper_stop and epoch % marglik_frequency == 0 \
