@@ -44,6 +44,9 @@ CASES = {
                                 batch_size=64),
     "cora_shape": dict(n=2708, U=5278, F=1433, C=7, h=16, L=2, directed=False, tier="O1", feat="bow"),
     "pubmed_shape": dict(n=19717, U=44324, F=500, C=3, h=64, L=2, directed=False, tier="O2", feat="bow"),
+    # the arxiv / products kernel shapes at a size the reference finishes in seconds: 3 layers, h = 256 (fused
+    # tcgen05 GEMM, tcgen05 SYRK n = 256, unit-compacted slabs), C = 40 (column groups 16 + 16 + 8)
+    "arxiv_mini_3l": dict(n=1200, U=8000, F=128, C=40, h=256, L=3, directed=False, tier="O2", feat="normal"),
 }
 
 

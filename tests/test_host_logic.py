@@ -345,6 +345,20 @@ def test_hub_rows_are_split_for_the_unit_spmm(fake_ops, limit):
     assert graph.meta["_split_t"][limit] is sp
 
 
+def test_backend_matches_reference_at_kernel_shapes(fake_ops):
+    """arxiv_mini_3l (3 layers, h = 256, C = 40; reference O2 fit): the backend's orchestration with unit-compacted
+    slabs and column groups 16 + 16 + 8, and with dense groups of 7, against the reference's factors."""
+    import laplace_gnn_b200 as L
+    g = Golden("arxiv_mini_3l")
+    model = build_model(g)
+    for kw, groups in (({}, 3), ({"unit_slabs": False, "rhs_tile_bytes": 2 * g.n * 256 * 4 * 7}, 6)):
+        la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs=kw)
+        la.fit(loader_for(g))
+        check_against_golden(g, la.loss, la.H_facs.kfacs, la.log_marginal_likelihood())
+        assert la.backend.last_stats["n_groups"] == groups
+        assert (la.backend.last_stats["unit_slabs"] > 0) == (not kw)
+
+
 def test_bench_clock_sampler_keeps_the_timed_region(monkeypatch):
     """bench.ClockSampler: nvidia-smi lines stamped outside the timed region are dropped, throttle reasons
     inside it are reported, an unparsable stamp keeps the sample."""

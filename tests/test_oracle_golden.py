@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import Golden, GOLDEN_SMALL, max_rel_err
+from conftest import Golden, GOLDEN_KERNEL_SHAPES, GOLDEN_SMALL, max_rel_err
 from oracle import gcn_kfac_oracle as O
 
 
@@ -41,6 +41,22 @@ def test_factors_loss_marglik_match_reference(golden, dtype, tol):
             assert max_rel_err(h.numpy(), ref) <= tol
     assert abs(float(loss) - g.loss) <= 1e-5 * abs(g.loss)
     assert abs(float(ml) - g.marglik) <= 1e-5 * abs(g.marglik)
+
+
+@pytest.mark.parametrize("name", GOLDEN_KERNEL_SHAPES)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_factors_loss_marglik_match_reference_at_kernel_shapes(name, dtype):
+    """3 layers, h = 256, C = 40 — the shapes the fused GEMM, the tcgen05 SYRK and the unit-compacted slabs
+    take on the GPU — against the reference's own fit (O2 tier)."""
+    g = Golden(name)
+    loss, kfacs, ml = O.fit_and_marglik(_graph(g), g.x, g.Ws, g.bs, g.idx, g.y, 1.0, "reference", dtype)
+    for blk, ref_blk in zip(kfacs, g.kfacs):
+        for h, ref in zip(blk, ref_blk):
+            assert max_rel_err(h.numpy(), ref) <= 5e-6
+    assert abs(float(loss) - g.loss) <= 1e-5 * abs(g.loss)
+    assert abs(float(ml) - g.marglik) <= 1e-5 * abs(g.marglik)
+    hs, ps = O.forward(_graph(g), g.x, g.Ws, g.bs)
+    assert max_rel_err(ps[-1][torch.from_numpy(g.idx)].numpy(), g.z["logits"]) <= 1e-5
 
 
 def test_logits_match_reference(golden_small):

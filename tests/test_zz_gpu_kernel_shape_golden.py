@@ -1,0 +1,43 @@
+"""GPU: the whole fit on the shapes the headline kernels take (3 layers, h = 256, C = 40: fused tcgen05 GEMM +
+relu' mask, tcgen05 SYRK at n = 256, unit-compacted slabs in column groups 16 + 16 + 8) against the REFERENCE's own
+factors, loss and log marginal likelihood (tests/golden/arxiv_mini_3l.npz, oracle/make_golden.py tier O2).
+North-star tolerances: factors <= 1e-4 rel, marglik <= 1e-3 rel.  (File name: sorts after the per-kernel tests.)"""
+import pytest
+import torch
+
+from conftest import Golden, max_rel_err
+from helpers import build_model, check_against_golden, loader_for
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("kw", [
+    {},                                                        # the default path of bench.py
+    {"unit_slabs": False},                                     # dense slabs, fused GEMM with the mask epilogue
+    {"fused_gemm": False, "syrk_impl": "simt"},                # cuBLAS + mask kernel, CUDA-core SYRK
+    {"hess_sqrt": "reference", "rhs_tile_bytes": 2 * 1200 * 256 * 4 * 12},   # column groups of 12
+], ids=["default", "dense-slabs", "two-step-simt", "groups-of-12"])
+def test_fit_matches_the_reference_at_kernel_shapes(kw):
+    import laplace_gnn_b200 as L
+    g = Golden("arxiv_mini_3l")
+    model = build_model(g, DEV)
+    la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs=kw)
+    la.fit(loader_for(g, DEV))
+    ml = la.log_marginal_likelihood()
+    check_against_golden(g, la.loss, la.H_facs.kfacs, ml)
+    st = la.backend.last_stats
+    assert (st["unit_slabs"] > 0) == kw.get("unit_slabs", True)
+    if "rhs_tile_bytes" in kw:
+        assert st["group"] == 12 and st["n_groups"] == 4
+
+
+def test_logits_match_the_reference_at_kernel_shapes():
+    g = Golden("arxiv_mini_3l")
+    model = build_model(g, DEV)
+    model.eval()
+    with torch.no_grad():
+        out = model(torch.from_numpy(g.idx).to(DEV))
+    # three GEMM + SpMM layers deep: the per-kernel 1e-5 (tests/test_gpu_parity.py) compounds
+    assert max_rel_err(out.cpu().numpy(), g.z["logits"]) <= 5e-5
