@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--dense-slabs", action="store_true", help="keep the slabs below the output layer dense (no unit compaction)")
     ap.add_argument("--unit-even-groups", action="store_true",
                     help="lab: column groups of any even width (csrc/spmm_units_even.cu) instead of multiples of 4")
+    ap.add_argument("--shard-eigh", action="store_true",
+                    help="lab, multi-GPU: spread the factor eigendecompositions over the ranks (kron.Kron.decompose)")
     ap.add_argument("--rhs-tile-gb", type=float, default=None,
                     help="HBM budget of the two multi-RHS slabs (sizes the column groups; default: 40 %% of HBM)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -261,6 +263,7 @@ def main():
         bk["process_group"] = pg
         bk["backward_parallel"] = args.backward_parallel
         bk["overlap"] = not args.no_overlap
+        bk["shard_eigh"] = args.shard_eigh
     loader = L.TensorBatchLoader(idx, y)      # one full batch, no per-sample collation
 
     def step(mdl, ldr):

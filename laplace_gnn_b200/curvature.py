@@ -167,7 +167,7 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=True, unit_hub_split=False):
+                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -210,8 +210,8 @@ class _B200KFAC:
         # owns 6 of the products shape's 47 columns and would otherwise carry 8.  OFF by default until those
         # kernels have been run against the dense SpMM on a B200 (tests/test_gpu_parity.py, LGNN_LAB=1)
         self.unit_even_groups = bool(unit_even_groups)
-        # with a process group the stand-in KronLaplace spreads the factor eigendecompositions over the ranks
-        # (kron.Kron.decompose); False keeps them replicated
+        # with a process group the stand-in KronLaplace can spread the factor eigendecompositions over the ranks
+        # (kron.Kron.decompose); OFF (replicated) until the all-gather has run over NCCL (gloo-tested only)
         self.shard_eigh = bool(shard_eigh)
         # power-law graphs: the unit SpMM gives one warp group a whole row, so graphs with rows beyond
         # unit_row_limit non-zeros keep dense slabs — unless unit_hub_split cuts those rows into pieces
@@ -596,7 +596,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=True, unit_hub_split=False):
+                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:

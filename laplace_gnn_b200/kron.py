@@ -374,7 +374,7 @@ class KronLaplace(_ParametricLaplaceLite):
         self.H_facs = self.H
         # multi-GPU pass: the factors are all-reduced, the eigendecompositions are spread over the ranks
         pg = getattr(self.backend, "process_group", None)
-        shard = pg is not None and getattr(self.backend, "shard_eigh", True)
+        shard = pg is not None and getattr(self.backend, "shard_eigh", False)
         self.H = self.H_facs.decompose(process_group=pg) if shard else self.H_facs.decompose()
 
     @property

@@ -36,7 +36,8 @@ def _worker(rank, world, port, name, mode, out):
         model = build_model(g)
         la = L.Laplace(model, "classification", backend=L.B200GGN,
                        backend_kwargs={"process_group": dist.group.WORLD, "backward_parallel": mode,
-                                       "rhs_tile_bytes": 40_000})       # several column groups
+                                       "rhs_tile_bytes": 40_000,        # several column groups
+                                       "shard_eigh": mode == "columns"})  # eigh spread over the ranks / replicated
         la.fit(loader_for(g))
         ml = la.log_marginal_likelihood()
         check_against_golden(g, la.loss, la.H_facs.kfacs, ml)
