@@ -58,6 +58,25 @@ class Golden:
         self.h = self.Ws[0].shape[0]
 
 
+class GgnGolden:
+    """tests/golden/ggn_<name>.npz: the reference's classes with upstream curvlinops' ``.detach()`` on the
+    Hessian-sqrt input restored at run time (oracle/make_golden_ggn.py) — what pins ``hess_sqrt="ggn"``.
+    Inputs and weights are those of <name>.npz."""
+
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, f"ggn_{name}.npz"))
+        self.name = name
+        self.loss, self.marglik = float(z["loss"]), float(z["marglik"])
+        self.fork_marglik = float(z["fork_marglik"])
+        self.kfacs = []
+        for b in range(int(z["n_blocks"])):
+            blk, j = [], 0
+            while f"kfac_{b}_{j}" in z.files:
+                blk.append(z[f"kfac_{b}_{j}"])
+                j += 1
+            self.kfacs.append(blk)
+
+
 @pytest.fixture(params=GOLDEN_SMALL)
 def golden_small(request):
     return Golden(request.param)

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import Golden, max_rel_err
+from conftest import GgnGolden, Golden, max_rel_err
 from helpers import build_model, check_against_golden, loader_for
 
 
@@ -343,6 +343,22 @@ def test_hub_rows_are_split_for_the_unit_spmm(fake_ops, limit):
     assert split_hub_rows(graph.ahat_t, 10 ** 6) is None
     be.kron(idx, y, N=300)                                          # second call: the split is cached on the graph
     assert graph.meta["_split_t"][limit] is sp
+
+
+def test_backend_ggn_mode_matches_upstream_curvlinops_goldens(golden_small, fake_ops):
+    """hess_sqrt="ggn" through the backend and the Laplace driver (multi-batch case included) against the goldens
+    of oracle/make_golden_ggn.py."""
+    import laplace_gnn_b200 as L
+    g, gg = golden_small, GgnGolden(golden_small.name)
+    la = L.Laplace(build_model(g), "classification", backend=L.B200GGN, backend_kwargs={"hess_sqrt": "ggn"})
+    la.fit(loader_for(g))
+    ml = la.log_marginal_likelihood()
+    for blk, ref_blk in zip(la.H_facs.kfacs, gg.kfacs):
+        for h, ref in zip(blk, ref_blk):
+            assert max_rel_err(h.numpy(), ref) <= 1e-4
+    assert abs(float(la.loss) - gg.loss) <= 1e-4 * abs(gg.loss)
+    assert abs(float(ml) - gg.marglik) <= 1e-3 * abs(gg.marglik)
+    assert abs(float(ml) - g.marglik) > 1e-4 * abs(g.marglik)          # and it is not the fork's value
 
 
 def test_backend_matches_reference_at_kernel_shapes(fake_ops):

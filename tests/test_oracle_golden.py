@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import Golden, GOLDEN_KERNEL_SHAPES, GOLDEN_SMALL, max_rel_err
+from conftest import GgnGolden, Golden, GOLDEN_KERNEL_SHAPES, GOLDEN_SMALL, max_rel_err
 from oracle import gcn_kfac_oracle as O
 
 
@@ -77,6 +77,24 @@ def test_ggn_mode_differs_from_fork_and_matches_textbook(golden_small):
     p = torch.softmax(O.forward(G, g.x, g.Ws, g.bs, torch.float64)[1][-1][torch.from_numpy(g.idx)], 1)
     lam = torch.diag_embed(p) - p.unsqueeze(2) * p.unsqueeze(1)
     assert torch.allclose(torch.einsum("nck,ncj->nkj", V, V), lam, atol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64])
+def test_ggn_mode_matches_upstream_curvlinops_arithmetic(golden_small, dtype):
+    """hess_sqrt="ggn" pinned: the reference's own classes run with upstream curvlinops' ``out.detach()`` restored
+    on the Hessian-sqrt input (the one expression the fork changed, curvlinops/kfac.py:631-642) — factors, loss and
+    marglik of that run (oracle/make_golden_ggn.py), multi-batch case included."""
+    g = golden_small
+    gg = GgnGolden(g.name)
+    assert abs(gg.fork_marglik - g.marglik) <= 1e-6 * abs(g.marglik) and gg.marglik != g.marglik
+    bs = None if g.batch_size == len(g.idx) else g.batch_size
+    loss, kfacs, ml = O.fit_and_marglik(_graph(g), g.x, g.Ws, g.bs, g.idx, g.y, 1.0, "ggn", dtype, bs)
+    assert len(kfacs) == len(gg.kfacs)
+    for blk, ref_blk in zip(kfacs, gg.kfacs):
+        for h, ref in zip(blk, ref_blk):
+            assert max_rel_err(h.numpy(), ref) <= 2e-6
+    assert abs(float(loss) - gg.loss) <= 1e-5 * abs(gg.loss)
+    assert abs(float(ml) - gg.marglik) <= 1e-5 * abs(gg.marglik)
 
 
 @pytest.mark.parametrize("name", [n for n in GOLDEN_SMALL if n.startswith("tiny")])

@@ -5,7 +5,7 @@ North-star tolerances: factors <= 1e-4 rel, marglik <= 1e-3 rel.  (File name: so
 import pytest
 import torch
 
-from conftest import Golden, max_rel_err
+from conftest import GOLDEN_SMALL, GgnGolden, Golden, max_rel_err
 from helpers import build_model, check_against_golden, loader_for
 
 pytestmark = pytest.mark.gpu
@@ -41,3 +41,19 @@ def test_logits_match_the_reference_at_kernel_shapes():
         out = model(torch.from_numpy(g.idx).to(DEV))
     # three GEMM + SpMM layers deep: the per-kernel 1e-5 (tests/test_gpu_parity.py) compounds
     assert max_rel_err(out.cpu().numpy(), g.z["logits"]) <= 5e-5
+
+
+@pytest.mark.parametrize("name", GOLDEN_SMALL)
+def test_ggn_mode_matches_upstream_curvlinops_goldens(name):
+    """hess_sqrt="ggn" on the device against the reference's classes run with upstream curvlinops' detach restored
+    (oracle/make_golden_ggn.py): factors <= 1e-4 rel, marglik <= 1e-3 rel."""
+    import laplace_gnn_b200 as L
+    g, gg = Golden(name), GgnGolden(name)
+    la = L.Laplace(build_model(g, DEV), "classification", backend=L.B200GGN, backend_kwargs={"hess_sqrt": "ggn"})
+    la.fit(loader_for(g, DEV))
+    ml = la.log_marginal_likelihood()
+    for blk, ref_blk in zip(la.H_facs.kfacs, gg.kfacs):
+        for h, ref in zip(blk, ref_blk):
+            assert max_rel_err(h.cpu().numpy(), ref) <= 1e-4
+    assert abs(float(la.loss) - gg.loss) <= 1e-4 * abs(gg.loss)
+    assert abs(float(ml) - gg.marglik) <= 1e-3 * abs(gg.marglik)
