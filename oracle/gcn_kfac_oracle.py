@@ -8,10 +8,12 @@ classes (``/root/reference`` through ``oracle/ref_loader.py``) on small graphs
 and on the Cora-/Pubmed-shaped configs and stores inputs + outputs under
 ``tests/golden/``; ``tests/test_oracle_golden.py`` checks every function here
 against those files (factors <= 1e-5 rel, marglik <= 1e-5 rel in fp32; tighter
-in fp64).  The ``hess_sqrt="ggn"`` mode has no runnable reference
-implementation here (asdl / backpack are not installed) — for that mode:
-parity unpinned; it is pinned only to the textbook identity G = J^T Λ J on
-tiny dense cases.
+in fp64).  The ``hess_sqrt="ggn"`` mode is pinned on upstream curvlinops'
+arithmetic: ``oracle/make_golden_ggn.py`` runs the same reference classes with
+upstream's ``out.detach()`` restored at run time on the Hessian-sqrt input (the
+one expression the fork changed, curvlinops/kfac.py:631-642) and stores
+``tests/golden/ggn_*.npz``.  The alternate backends the north star names
+(asdl, backpack) are not installed: against those, parity unpinned.
 
 Integer / index work is numpy (bit-exact contract).  Floating-point work uses
 torch CPU tensors (fp32 like the reference, or fp64) because the reference's
