@@ -210,6 +210,22 @@ int lgnn_hess_rhs_pitched_f32(const float* logits, int64_t ld, int32_t C, const 
                               int32_t c0, int32_t ncols, int32_t ldc, int64_t ld_delta, int mode,
                               float* delta, lgnn_stream_t stream);
 
+/* The same right-hand sides generated inside the output-layer SpMM instead of being materialised
+ * (csrc/spmm_hess.cu).  v_{m,c} is a closed form of the node's softmax:
+ *   v_c[k] = -(A_c P_k + S_c Q_k) (k != c),  V_c (k == c);   P = p, Q = p*(f - fbar), S_c = sqrt(p_c),
+ *   A_c = sqrt(p_c)(1 + (f_c - fbar)/2)          (GGN mode: A = S, Q = 0)
+ *   lgnn_hess_stats_f32   stats[idx[m]] = [P | Q | A | S | V], five vectors of Cp = roundup4(C) floats per node
+ *                         (ld_stats >= 5*Cp, zeroed by the caller; A, S, V accumulate for duplicate idx);
+ *   lgnn_spmm_hess_f32    Y[i, c*Cp + k] = sum_j val[ij] * v_{col[ij], c0+c}[k]  for c < ncols, zero for
+ *                         ncols <= c < width; gathers 2*Cp + 3*ncols floats per edge instead of width*Cp.
+ *                         C <= 64, width <= 16 (lgnn_spmm_hess_supported); rows are walked whole by one warp. */
+int lgnn_spmm_hess_supported(int64_t C, int64_t width);
+int lgnn_hess_stats_f32(const float* logits, int64_t ld, int32_t C, const int64_t* idx, int64_t m, int mode,
+                        float* stats, int64_t ld_stats, lgnn_stream_t stream);
+int lgnn_spmm_hess_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr, const int32_t* col, const float* val,
+                       const float* stats, int64_t ld_stats, int32_t C, int32_t c0, int32_t ncols, int32_t width,
+                       float* y, int64_t ldy, lgnn_stream_t stream);
+
 /* out[k] = keep[col[k]] ? val[k] : 0 for the nnz entries of a CSR.  The right-hand sides injected at
  * the logits are zero outside the batch's train nodes (curvlinops/kfac.py:653-661 back-propagates
  * through model(X)[idx]); with the edges into those rows zeroed, the output-layer SpMM of the KFAC

@@ -132,6 +132,7 @@ class _Whole:
         self.communicates = False
         self.csr_t_top = None        # Â^T with the edges from non-train rows zeroed (set per kron call)
         self.split_t = None          # Â^T with its hub rows cut into pieces (graph.SplitCSR), for the unit SpMM
+        self.hess_stats = None       # softmax statistics for the on-the-fly output-layer SpMM (set per kron call)
 
     def gather(self, slab):
         pass
@@ -150,6 +151,7 @@ class _Rows:
         self.communicates = True
         self.csr_t_top = None
         self.split_t = None
+        self.hess_stats = None
 
     def gather(self, slab):
         self.part.all_gather_slab(slab)
@@ -167,7 +169,7 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False):
+                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -218,6 +220,10 @@ class _B200KFAC:
         # (graph.split_hub_rows; the pieces are summed by a small SpMM afterwards).  OFF by default until the
         # R-MAT sweep has run with it on a B200 (tools/rmat_sweep.py --hub-split)
         self.unit_hub_split = bool(unit_hub_split)
+        # output-layer SpMM with its Hessian-sqrt right-hand sides rebuilt per edge from five softmax vectors per
+        # node (csrc/spmm_hess.cu): 576 instead of 3072 gathered bytes per edge at g = 16, C = 47, and no
+        # lgnn_hess_rhs_f32 pass.  OFF by default until the kernel has run on a B200 (LGNN_LAB=1 tests)
+        self.fused_hess_spmm = bool(fused_hess_spmm)
         self.unit_row_limit = 4096
         # A_0 = X^T X does not depend on the weights: with cache_input_factor the raw Gram matrix of
         # this rank's feature rows is kept (per backend, or in a dict shared across backends by the
@@ -331,9 +337,11 @@ class _B200KFAC:
         P, Q = buf_a, buf_b                             # P: SpMM input, Q: SpMM output
         slab = P[: n_in * gq * c_pad].view(n_in, gq * c_pad)
         delta = slab[slot0:slot0 + n_loc]
-        with ops.timed("hess_rhs", gc):
-            delta.zero_()
-            ops.hess_rhs(logits, idx, c0, gc, delta, c_pad, self.hess_sqrt)
+        on_the_fly = lay.hess_stats is not None and ops.spmm_hess_supported(C, gq)
+        if not on_the_fly:
+            with ops.timed("hess_rhs", gc):
+                delta.zero_()
+                ops.hess_rhs(logits, idx, c0, gc, delta, c_pad, self.hess_sqrt)
         width, ld = C, c_pad
         packed = units = None
         for l in range(L - 1, -1, -1):
@@ -349,6 +357,10 @@ class _B200KFAC:
                 self._n_unit_spmm += 1
             elif packed is not None:
                 ops.spmm_packed(lay.csr_t, packed, out=gz)
+            elif l == L - 1 and on_the_fly:
+                # output layer, right-hand sides rebuilt per edge from the nodes' softmax statistics: no slab
+                ops.spmm_hess(lay.csr_t_top if lay.csr_t_top is not None else lay.csr_t, lay.hess_stats, C, c0, gc,
+                              gq, out=gz)
             else:
                 with ops.timed("allgather", gq * ld, 4.0 * n_in * gq * ld):
                     lay.gather(slab)
@@ -528,7 +540,17 @@ class _B200KFAC:
             keep = torch.zeros(g.n, dtype=torch.uint8, device=dev)
             keep[idx] = 1
             whole.csr_t_top = ops.csr_with_masked_sources(g.ahat_t, keep)
+        mx_row = g.ahat_t.max_row_nnz
+        if (self.fused_hess_spmm and (part is None or self.backward_parallel == "columns") and
+                ops.spmm_hess_supported(C, 1) and mx_row is not None and mx_row <= self.unit_row_limit):
+            self._want_hess_stats = True
+        else:
+            self._want_hess_stats = False
         if part is None:
+            if self._want_hess_stats:
+                cp = (C + 3) // 4 * 4
+                whole.hess_stats = ops.hess_stats(logits, idx, self.hess_sqrt, C,
+                                                  out=_slab(dev, 2000, 0, g.n * 5 * cp).view(g.n, 5 * cp))
             grp, n_groups = self._backward_columns(whole, logits, idx, Hs, Ws, (0, C), G)
         elif self.backward_parallel == "rows":
             grp, n_groups = self._backward_columns(_Rows(part), logits, idx_loc, Hs, Ws, (0, C), G)
@@ -546,6 +568,10 @@ class _B200KFAC:
                     full_logits = full
                 else:
                     full_H.append(full)
+            if self._want_hess_stats:
+                cp = (C + 3) // 4 * 4
+                whole.hess_stats = ops.hess_stats(full_logits, idx, self.hess_sqrt, C,
+                                                  out=_slab(dev, 2000, 0, g.n * 5 * cp).view(g.n, 5 * cp))
             grp, n_groups = self._backward_columns(whole, full_logits, idx, full_H, Ws,
                                                    column_share(C, part.rank, part.world), G)
         if part is not None:
@@ -596,7 +622,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False):
+                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -607,7 +633,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
                          backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs,
-                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split)
+                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split, fused_hess_spmm)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

@@ -399,6 +399,64 @@ def hess_rhs(logits: torch.Tensor, idx: torch.Tensor, c0: int, ncols: int, delta
     return delta
 
 
+def spmm_hess_supported(C: int, width: int) -> bool:
+    return bool(_lib.load().lgnn_spmm_hess_supported(int(C), int(width)))
+
+
+def hess_stats(logits: torch.Tensor, idx: torch.Tensor, mode: str = "reference", C: int | None = None,
+               out: torch.Tensor | None = None) -> torch.Tensor:
+    """[n_nodes, 5*Cp] softmax statistics of the batch's train nodes (zero rows elsewhere) from which
+    ``spmm_hess`` rebuilds the Hessian-sqrt right-hand sides on the fly (csrc/spmm_hess.cu)."""
+    lib = _lib.load()
+    _f32c(logits, "logits")
+    C = int(logits.shape[1]) if C is None else int(C)
+    m = {"reference": _lib.HESS_REFERENCE, "ggn": _lib.HESS_GGN}.get(mode)
+    if m is None:
+        raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {mode!r}")
+    cp = (C + 3) // 4 * 4
+    n = int(logits.shape[0])
+    if out is None:
+        out = torch.empty(n, 5 * cp, dtype=torch.float32, device=logits.device)
+    _f32c(out, "stats")
+    if out.shape[0] < n or out.shape[1] < 5 * cp:
+        raise ValueError("hess_stats: out too small")
+    idx = idx.contiguous()
+    with _Timed("hess_rhs", C):
+        out.zero_()
+        check(lib.lgnn_hess_stats_f32(ptr(logits), logits.stride(0), C, ptr(idx), idx.numel(), m, ptr(out),
+                                      out.stride(0), stream()), "lgnn_hess_stats_f32")
+    _lib.count_launches(1)
+    return out
+
+
+def spmm_hess(a: CSR, stats: torch.Tensor, C: int, c0: int, ncols: int, width: int,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """Y[i, c*Cp + k] = sum_j A[i, j] v_{j, c0+c}[k] for c < ncols (zero columns up to ``width``): the output-layer
+    SpMM of a column group with its Hessian-sqrt right-hand sides rebuilt from ``stats`` per edge."""
+    lib = _lib.load()
+    _f32c(stats, "stats")
+    cp = (int(C) + 3) // 4 * 4
+    if stats.shape[0] < a.n_cols:
+        raise ValueError("spmm_hess: fewer stats rows than matrix columns")
+    d = int(width) * cp
+    if out is None:
+        out = torch.empty(a.n_rows, d, dtype=torch.float32, device=stats.device)
+    _f32c(out, "out")
+    if out.shape[0] < a.n_rows or out.shape[1] < d:
+        raise ValueError("spmm_hess: out too small")
+    # bytes asked of HBM: (col, val), rowptr, per gathered edge P and Q (2 Cp floats) and the group's A, S, V,
+    # the output; the same launch priced as the materialised slab goes into dense_bytes
+    per_edge = (2 * cp + 3 * int(ncols)) * 4
+    work = (lambda: a.nnz * 8 + (a.n_rows + 1) * 8 + a.nnz_gathered * per_edge + a.n_rows * d * 4) \
+        if a.masked else (a.nnz * 8 + (a.n_rows + 1) * 8 + a.nnz * per_edge + a.n_rows * d * 4)
+    with _Timed("spmm_hess", d, work):
+        check(lib.lgnn_spmm_hess_f32(a.n_rows, a.nnz, ptr(a.rowptr), ptr(a.col), ptr(a.val), ptr(stats),
+                                     stats.stride(0), int(C), int(c0), int(ncols), int(width), ptr(out),
+                                     out.stride(0), stream()), "lgnn_spmm_hess_f32")
+    _lib.count_launches(1)
+    return out
+
+
 def csr_with_masked_sources(a: CSR, keep: torch.Tensor) -> CSR:
     """Same pattern, edge values zeroed where the source row (column index) is not flagged in
     ``keep`` (uint8 [n_cols]): SpMM then skips the gathers of rows known to be all zero."""

@@ -86,6 +86,23 @@ def hess_rhs(logits, idx, c0, ncols, delta, ldc, mode="reference", C=None):
     return delta
 
 
+def spmm_hess_supported(C, width):
+    return 1 <= C <= 64 and 1 <= width <= 16
+
+
+def hess_stats(logits, idx, mode="reference", C=None, out=None):
+    """CPU double: keeps what spmm_hess needs (logits, batch indices, mode) in place of the five vectors."""
+    C = logits.shape[1] if C is None else C
+    return {"logits": logits, "idx": idx, "mode": mode, "C": C}
+
+
+def spmm_hess(a, stats, C, c0, ncols, width, out=None):
+    cp = (C + 3) // 4 * 4
+    delta = torch.zeros(a.n_cols, width * cp, dtype=torch.float32)
+    hess_rhs(stats["logits"], stats["idx"], c0, ncols, delta, cp, stats["mode"], C)
+    return spmm(a, delta, out=out)
+
+
 def relu_mask_mul(inp, act, group, out=None, d=None):
     d = inp.shape[1] if d is None else d
     out = inp if out is None else out
@@ -161,5 +178,5 @@ def gemm_mask_supported(k, n):
     return False          # the CPU double keeps the two-step path (torch.mm + relu_mask_mul)
 
 
-ALL = ["sddmm", "unit_slabs_supported", "unit_pack", "spmm_units", "gemm_mask_supported", "pack_rows_pitch", "pack_rows", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
+ALL = ["spmm_hess_supported", "hess_stats", "spmm_hess", "sddmm", "unit_slabs_supported", "unit_pack", "spmm_units", "gemm_mask_supported", "pack_rows_pitch", "pack_rows", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
        "halo_columns", "csr_slice_remap", "spmm", "softmax_ce_sum", "hess_rhs", "relu_mask_mul", "syrk"]

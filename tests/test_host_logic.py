@@ -375,6 +375,41 @@ def test_backend_matches_reference_at_kernel_shapes(fake_ops):
         assert (la.backend.last_stats["unit_slabs"] > 0) == (not kw)
 
 
+@pytest.mark.parametrize("mode", ["reference", "ggn"])
+def test_on_the_fly_hessian_sqrt_spmm_gives_the_same_factors(fake_ops, mode):
+    """fused_hess_spmm: the output-layer SpMM fed by per-node softmax statistics instead of the materialised
+    right-hand sides (csrc/spmm_hess.cu) — same factors, no lgnn_hess_rhs pass; a batch with a repeated node."""
+    import laplace_gnn_b200 as L
+    model, idx, y = _synthetic_model(400, 1600, 12, 64, 10, 3)
+    idx = torch.cat([idx, idx[:5]])
+    y = torch.cat([y, y[:5]])
+    calls = {"rhs": 0, "fly": 0}
+    rhs, fly = fake_ops.hess_rhs, fake_ops.spmm_hess
+    import laplace_gnn_b200.ops as ops
+
+    def count_rhs(*a, **k):
+        calls["rhs"] += 1
+        return rhs(*a, **k)
+
+    def count_fly(*a, **k):
+        calls["fly"] += 1
+        return fly(*a, **k)
+    ops.hess_rhs, ops.spmm_hess = count_rhs, count_fly
+    try:
+        be1 = L.B200GGN(model, "classification", hess_sqrt=mode, unit_min_width=0, fused_hess_spmm=True)
+        l1, k1 = be1.kron(idx, y, N=len(y))
+        assert calls["fly"] == be1.last_stats["n_groups"] and calls["rhs"] == 0
+        be2 = L.B200GGN(model, "classification", hess_sqrt=mode, unit_min_width=0)
+        l2, k2 = be2.kron(idx, y, N=len(y))
+        assert calls["rhs"] == be2.last_stats["n_groups"]
+    finally:
+        ops.hess_rhs, ops.spmm_hess = rhs, fly
+    assert float(l1) == float(l2)
+    for fa, fb in zip(k1.kfacs, k2.kfacs):
+        for a, b in zip(fa, fb):
+            assert max_rel_err(a.numpy(), b.numpy()) <= 1e-5
+
+
 def test_bench_clock_sampler_keeps_the_timed_region(monkeypatch):
     """bench.ClockSampler: nvidia-smi lines stamped outside the timed region are dropped, throttle reasons
     inside it are reported, an unparsable stamp keeps the sample."""
