@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(SH_THREADS) hess_stats_kernel(
 }
 
 template <int G, int KH>
-__global__ void __launch_bounds__(SH_THREADS, 2) spmm_hess_kernel(
+__global__ void __launch_bounds__(SH_THREADS, 3) spmm_hess_kernel(
     int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     const float* __restrict__ val, const float* __restrict__ stats, int64_t lds, int Cp, int c0, int ncols,
     int width, float* __restrict__ y, int64_t ldy) {
