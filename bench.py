@@ -389,6 +389,10 @@ def main():
         # secondary, tensor-bound kernels: useful TFLOP/s (3xTF32 issues 3x that) against the TF32 dense
         # peak taken as half the measured bf16 GEMM figure (MEASURED_PEAKS.json has no tf32 entry)
         tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
+        try:        # a measured TF32 GEMM rate, once tools/tf32_peak.py has been run on the pool's B200
+            tf32_peak = float(json.load(open(os.path.join(ROOT, "profiles", "tf32_peak.json")))["tf32_tflops_sustained"])
+        except Exception:
+            pass
         tens = []
         for (k, dd), v in sorted(groups.items()):
             if k in ("syrk", "gemm_mask") and v["ms"] > 0 and v["bytes"] > 0:

@@ -7,6 +7,8 @@ set -u
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/gpu.txt
 run() { local name=$1 t=$2; shift 2; local S=$(date +%s); timeout "$t" "$@" > gpurun_out/$name.log 2>gpurun_out/$name.err; echo "$name rc=$? in $(( $(date +%s) - S )) s"; }
+run tf32_peak 60 python tools/tf32_peak.py
+cat gpurun_out/tf32_peak.log
 run r2_tests_default 600 python -m pytest tests -m gpu -q -x
 tail -2 gpurun_out/r2_tests_default.log | cut -c1-200
 LGNN_LAB=1 run r2_tests_lab 600 python -m pytest tests/test_gpu_lab.py -q
