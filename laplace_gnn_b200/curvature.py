@@ -169,7 +169,7 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False):
+                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, syrk_stack_narrow=False):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -224,6 +224,9 @@ class _B200KFAC:
         # node (csrc/spmm_hess.cu): 576 instead of 3072 gathered bytes per edge at g = 16, C = 47, and no
         # lgnn_hess_rhs_f32 pass.  OFF by default until the kernel has run on a B200 (LGNN_LAB=1 tests)
         self.fused_hess_spmm = bool(fused_hess_spmm)
+        # G of the output layer (n = C): SYRK of the slab viewed [K/s, s*ld] instead of [K, ld] (ops.syrk_stacked);
+        # OFF until n = s*ld (240 at C = 47) has been timed on a B200
+        self.syrk_stack_narrow = bool(syrk_stack_narrow)
         self.unit_row_limit = 4096
         # A_0 = X^T X does not depend on the weights: with cache_input_factor the raw Gram matrix of
         # this rank's feature rows is kept (per backend, or in a dict shared across backends by the
@@ -367,7 +370,10 @@ class _B200KFAC:
                 # output layer: the slab is zero outside the batch's train rows -> no gather for those edges
                 ops.spmm(lay.csr_t_top if (l == L - 1 and lay.csr_t_top is not None) else lay.csr_t, slab, out=gz)
             gz_rows = gz.view(n_loc * gq, ld)
-            ops.syrk(gz_rows, n=width, alpha=1.0, beta=1.0, out=G[l], impl=self._impl(width))
+            if self.syrk_stack_narrow and ld <= 128 and gz_rows.is_contiguous():
+                ops.syrk_stacked(gz_rows, width, G[l], impl=self._impl(width))
+            else:
+                ops.syrk(gz_rows, n=width, alpha=1.0, beta=1.0, out=G[l], impl=self._impl(width))
             if self._layer_hook is not None:
                 self._layer_hook(l, gz, gq, ld, width)
             if l > 0:
@@ -622,7 +628,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False):
+                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, syrk_stack_narrow=False):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -633,7 +639,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
                          backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs,
-                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split, fused_hess_spmm)
+                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split, fused_hess_spmm, syrk_stack_narrow)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

@@ -184,3 +184,17 @@ def test_fused_hess_spmm_gives_the_same_factors(h, C, layers):
         for fa, fb in zip(k1.kfacs, k2.kfacs):
             for a, b in zip(fa, fb):
                 assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("k,ld,n", [(100_003, 48, 47), (50_000, 40, 40), (7, 48, 47), (20_000, 12, 10), (9_999, 128, 128)])
+def test_syrk_stacked_matches_fp64(k, ld, n):
+    """ops.syrk_stacked (the slab viewed s rows side by side, tcgen05 SYRK at n = s*ld) against float64."""
+    from laplace_gnn_b200 import ops
+    x = torch.randn(k, ld, device=DEV)
+    x[:, n:] = 0
+    ref = x[:, :n].double().T @ x[:, :n].double()
+    out = torch.zeros(n, n, device=DEV)
+    ops.syrk_stacked(x, n, out)
+    assert max_rel_err(out.cpu().numpy(), ref.cpu().numpy()) <= 1e-5
+    ops.syrk_stacked(x, n, out)
+    assert max_rel_err(out.cpu().numpy(), (2 * ref).cpu().numpy()) <= 1e-5

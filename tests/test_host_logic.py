@@ -410,6 +410,23 @@ def test_on_the_fly_hessian_sqrt_spmm_gives_the_same_factors(fake_ops, mode):
             assert max_rel_err(a.numpy(), b.numpy()) <= 1e-5
 
 
+def test_stacked_narrow_syrk_gives_the_same_factors(fake_ops):
+    """syrk_stack_narrow: the output-layer G from the slab viewed s rows side by side (diagonal blocks of the wide
+    product), remainder rows included (K = 400 * 12 rows, s = 256 // 12 = 21)."""
+    import laplace_gnn_b200 as L
+    model, idx, y = _synthetic_model(400, 1600, 12, 64, 10, 3)
+    l1, k1 = L.B200GGN(model, "classification", syrk_stack_narrow=True).kron(idx, y, N=len(y))
+    l2, k2 = L.B200GGN(model, "classification").kron(idx, y, N=len(y))
+    for fa, fb in zip(k1.kfacs, k2.kfacs):
+        for a, b in zip(fa, fb):
+            assert max_rel_err(a.numpy(), b.numpy()) <= 1e-5
+    x = torch.randn(1003, 12)
+    x[:, 10:] = 0
+    out = torch.ones(10, 10)
+    fake_ops.syrk_stacked(x, 10, out)
+    assert max_rel_err(out.numpy(), (1 + x[:, :10].T @ x[:, :10]).numpy()) <= 1e-5
+
+
 def test_bench_clock_sampler_keeps_the_timed_region(monkeypatch):
     """bench.ClockSampler: nvidia-smi lines stamped outside the timed region are dropped, throttle reasons
     inside it are reported, an unparsable stamp keeps the sample."""
