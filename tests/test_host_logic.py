@@ -427,6 +427,23 @@ def test_stacked_narrow_syrk_gives_the_same_factors(fake_ops):
     assert max_rel_err(out.numpy(), (1 + x[:, :10].T @ x[:, :10]).numpy()) <= 1e-5
 
 
+def test_all_lab_switches_compose(fake_ops):
+    """Every opt-in path of DESIGN.md §6c at once (even column groups, hub split, on-the-fly output-layer SpMM,
+    stacked narrow SYRK) through the Laplace driver: the marglik of the plain dense path."""
+    import laplace_gnn_b200 as L
+    model, idx, y = _synthetic_model(300, 1200, 10, 64, 7, 3)
+    kw = {"unit_min_width": 0, "unit_even_groups": True, "fused_hess_spmm": True, "syrk_stack_narrow": True,
+          "unit_hub_split": True}
+    la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs=kw)
+    la.backend.unit_row_limit = 8
+    la.fit(L.TensorBatchLoader(idx, y))
+    assert la.backend.last_stats["unit_slabs"] > 0 and la.backend.last_stats["group"] == 8
+    ref = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs={"unit_slabs": False})
+    ref.fit(L.TensorBatchLoader(idx, y))
+    a, b = float(la.log_marginal_likelihood()), float(ref.log_marginal_likelihood())
+    assert abs(a - b) <= 1e-6 * abs(b)
+
+
 def test_bench_clock_sampler_keeps_the_timed_region(monkeypatch):
     """bench.ClockSampler: nvidia-smi lines stamped outside the timed region are dropped, throttle reasons
     inside it are reported, an unparsable stamp keeps the sample."""
