@@ -427,6 +427,37 @@ def test_stacked_narrow_syrk_gives_the_same_factors(fake_ops):
     assert max_rel_err(out.numpy(), (1 + x[:, :10].T @ x[:, :10]).numpy()) <= 1e-5
 
 
+@pytest.mark.parametrize("n,U,F,h,C,layers,M,dup", [
+    (30, 60, 5, 8, 3, 1, 10, False),      # a single layer: no hidden slab, no GEMM step
+    (30, 60, 5, 8, 2, 2, 1, False),       # one train node
+    (30, 60, 5, 8, 1, 2, 10, False),      # one class: softmax == 1, every Hessian-sqrt column is zero
+    (30, 0, 5, 8, 3, 2, 30, False),       # no edges (self loops only), every node in the batch
+    (30, 60, 5, 8, 3, 3, 10, True),       # a node listed twice in the batch
+])
+def test_edge_case_shapes_match_the_oracle(fake_ops, n, U, F, h, C, layers, M, dup):
+    import laplace_gnn_b200 as L
+    from oracle import gcn_kfac_oracle as O
+    ei = O.synthetic_edges(n, U, seed=1)
+    graph = L.Graph.from_edge_index(torch.from_numpy(ei), n)
+    gen = torch.Generator().manual_seed(0)
+    torch.manual_seed(0)
+    X = torch.randn(n, F, generator=gen)
+    model = L.SparseGCN(F, h, C, layers, X, graph)
+    idx = torch.randperm(n, generator=gen)[:M].sort().values
+    if dup:
+        idx = torch.cat([idx, idx[:1]])
+    y = torch.randint(0, C, (idx.numel(),), generator=gen)
+    la = L.Laplace(model, "classification", backend=L.B200GGN)
+    la.fit(L.TensorBatchLoader(idx, y))
+    Ws = [c.lin.weight.detach().numpy() for c in model.convs]
+    bs = [c.lin.bias.detach().numpy() for c in model.convs]
+    _, kfacs, ml = O.fit_and_marglik(O.build_graph(ei, n), X.numpy(), Ws, bs, idx.numpy(), y.numpy())
+    assert abs(float(la.log_marginal_likelihood()) - float(ml)) <= 1e-5 * abs(float(ml))
+    for blk, ref_blk in zip(la.H_facs.kfacs, kfacs):
+        for a, b in zip(blk, ref_blk):
+            assert float((a - b).abs().max()) <= 1e-5 * max(float(b.abs().max()), 1e-6)
+
+
 def test_all_lab_switches_compose(fake_ops):
     """Every opt-in path of DESIGN.md §6c at once (even column groups, hub split, on-the-fly output-layer SpMM,
     stacked narrow SYRK) through the Laplace driver: the marglik of the plain dense path."""
