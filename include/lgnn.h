@@ -218,13 +218,14 @@ int lgnn_hess_rhs_pitched_f32(const float* logits, int64_t ld, int32_t C, const 
  *                         (ld_stats >= 5*Cp, zeroed by the caller; A, S, V accumulate for duplicate idx);
  *   lgnn_spmm_hess_f32    Y[i, c*Cp + k] = sum_j val[ij] * v_{col[ij], c0+c}[k]  for c < ncols, zero for
  *                         ncols <= c < width; gathers 2*Cp + 3*ncols floats per edge instead of width*Cp.
- *                         C <= 64, width <= 16 (lgnn_spmm_hess_supported); rows are walked whole by one warp. */
+ *                         C <= 64, width <= 16 (lgnn_spmm_hess_supported); rows are walked whole by one warp.
+ *                         flags 0x100: the staged kernel (records copied through a cp.async ring; c0 % 4 == 0). */
 int lgnn_spmm_hess_supported(int64_t C, int64_t width);
 int lgnn_hess_stats_f32(const float* logits, int64_t ld, int32_t C, const int64_t* idx, int64_t m, int mode,
                         float* stats, int64_t ld_stats, lgnn_stream_t stream);
 int lgnn_spmm_hess_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr, const int32_t* col, const float* val,
                        const float* stats, int64_t ld_stats, int32_t C, int32_t c0, int32_t ncols, int32_t width,
-                       float* y, int64_t ldy, lgnn_stream_t stream);
+                       float* y, int64_t ldy, int flags, lgnn_stream_t stream);
 
 /* out[k] = keep[col[k]] ? val[k] : 0 for the nnz entries of a CSR.  The right-hand sides injected at
  * the logits are zero outside the batch's train nodes (curvlinops/kfac.py:653-661 back-propagates

@@ -49,7 +49,7 @@ PROTOTYPES = {
     "lgnn_hess_rhs_pitched_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, _i64, C.c_int, _vp, _vp]),
     "lgnn_spmm_hess_supported": (C.c_int, [_i64, _i64]),
     "lgnn_hess_stats_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i64, C.c_int, _vp, _i64, _vp]),
-    "lgnn_spmm_hess_f32": (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, _vp]),
+    "lgnn_spmm_hess_f32": (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64, C.c_int, _vp]),
     "lgnn_mask_edge_values": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _vp]),
     "lgnn_relu_mask_mul_f32": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i64, _vp]),
     "lgnn_gemm_mask_supported": (C.c_int, [_i64, _i64]),

@@ -205,6 +205,144 @@ int launch_spmm_hess(int64_t n_rows, const int64_t* rowptr, const int32_t* col, 
   return LGNN_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Staged variant (flags bit 8).  The kernel above keeps ONE neighbour's operands in flight per warp (they travel
+// through registers); at 24 warps per SM that is ~28 KB of gathers in flight, short of what the HBM latency asks
+// for.  Here a neighbour's record — P | Q (2 Cp floats, contiguous in the stats row) and the group's slices of
+// A, S, V (3 * G floats) — is copied by cp.async (16 bytes per lane) into a per-warp ring of U slots, U - 1
+// neighbours in flight without holding registers, the pattern of spmm_units_staged_kernel.  The lanes then read
+// P, Q at their classes, A and S as broadcast 128-bit loads, V at their column, and scale P, Q by the edge value.
+// Needs c0 % 4 == 0 (16-byte aligned slices).  Columns >= ncols may read stale ring bytes: their accumulators are
+// discarded at the store.
+__device__ __forceinline__ void sh_cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void sh_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void sh_cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int G, int KH, int U>
+__global__ void __launch_bounds__(SH_THREADS, 3) spmm_hess_staged_kernel(
+    int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+    const float* __restrict__ val, const float* __restrict__ stats, int64_t lds, int Cp, int c0, int ncols,
+    int width, float* __restrict__ y, int64_t ldy) {
+  extern __shared__ __align__(16) uint8_t sh_ring_[];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int64_t row = ((int64_t)blockIdx.x * SH_THREADS + threadIdx.x) >> 5;
+  if (row >= n_rows) return;
+  const int slot_floats = 2 * Cp + 3 * G;                       // multiple of 4
+  float* ring = reinterpret_cast<float*>(sh_ring_) + (size_t)wi * U * slot_floats;
+  const uint32_t ring_addr = smem_addr(ring);
+  const int pq_pieces = Cp >> 1;                                // 2 Cp floats / 4
+  constexpr int GP = G / 4;                                     // pieces per A / S / V slice
+
+  float acc[G][KH];
+#pragma unroll
+  for (int c = 0; c < G; ++c)
+#pragma unroll
+    for (int h = 0; h < KH; ++h) acc[c][h] = 0.f;
+  float dacc = 0.f;
+
+  const int64_t beg = __ldg(rowptr + row), end = __ldg(rowptr + row + 1);
+  for (int64_t k0 = beg; k0 < end; k0 += 32) {
+    const int cnt = (int)((end - k0) < 32 ? (end - k0) : 32);
+    float my_a = 0.f;
+    int32_t my_c = 0;
+    if (lane < cnt) {
+      my_c = __ldg(col + k0 + lane);
+      my_a = __ldg(val + k0 + lane);
+    }
+    int slot_i = 0, slot_c = 0;
+    auto issue = [&](int j) {
+      if (j < cnt) {
+        const float a = __shfl_sync(0xffffffffu, my_a, j);
+        const int32_t cj = __shfl_sync(0xffffffffu, my_c, j);
+        if (a != 0.f) {                                         // masked edges copy nothing
+          const float* sp = stats + (int64_t)cj * lds;
+          const uint32_t dst = ring_addr + (uint32_t)(slot_i * slot_floats) * 4u;
+          if (lane < pq_pieces) sh_cp_async16(dst + 16u * lane, sp + 4 * lane);
+          if (lane < 3 * GP) {
+            const int sl = lane / GP, pc = lane - sl * GP;
+            if (c0 + 4 * pc < Cp)
+              sh_cp_async16(dst + 4u * (uint32_t)(2 * Cp + sl * G + 4 * pc), sp + (2 + sl) * Cp + c0 + 4 * pc);
+          }
+        }
+      }
+      sh_cp_async_commit();
+      slot_i = (slot_i + 1 == U) ? 0 : slot_i + 1;
+    };
+#pragma unroll
+    for (int j = 0; j < U - 1; ++j) issue(j);
+#pragma unroll 1
+    for (int j = 0; j < cnt; ++j) {
+      issue(j + U - 1);
+      sh_cp_async_wait<U - 1>();
+      __syncwarp();
+      const float a = __shfl_sync(0xffffffffu, my_a, j);
+      if (a != 0.f) {                                           // uniform across the warp
+        const float* rec = ring + slot_c * slot_floats;
+        float Pa[KH], Qa[KH];
+#pragma unroll
+        for (int h = 0; h < KH; ++h) {
+          const int k = lane + 32 * h;
+          Pa[h] = (k < Cp) ? a * rec[k] : 0.f;
+          Qa[h] = (k < Cp) ? a * rec[Cp + k] : 0.f;
+        }
+        if (lane < ncols) dacc = fmaf(a, rec[2 * Cp + 2 * G + lane], dacc);
+#pragma unroll
+        for (int c4 = 0; c4 < GP; ++c4) {
+          const float4 A4 = *reinterpret_cast<const float4*>(rec + 2 * Cp + 4 * c4);
+          const float4 S4 = *reinterpret_cast<const float4*>(rec + 2 * Cp + G + 4 * c4);
+          const float Av[4] = {A4.x, A4.y, A4.z, A4.w};
+          const float Sv[4] = {S4.x, S4.y, S4.z, S4.w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int h = 0; h < KH; ++h) {
+              acc[4 * c4 + i][h] = fmaf(Av[i], Pa[h], acc[4 * c4 + i][h]);
+              acc[4 * c4 + i][h] = fmaf(Sv[i], Qa[h], acc[4 * c4 + i][h]);
+            }
+        }
+      }
+      __syncwarp();                                             // the slot is rewritten by the copy issued next iteration
+      slot_c = (slot_c + 1 == U) ? 0 : slot_c + 1;
+    }
+  }
+
+  float* yr = y + row * ldy;
+#pragma unroll
+  for (int c = 0; c < G; ++c) {
+    const float d = __shfl_sync(0xffffffffu, dacc, c);
+    if (c < width) {
+#pragma unroll
+      for (int h = 0; h < KH; ++h) {
+        const int k = lane + 32 * h;
+        if (k < Cp) {
+          float o = 0.f;
+          if (c < ncols) o = (k == c0 + c) ? d : -acc[c][h];
+          yr[c * Cp + k] = o;
+        }
+      }
+    }
+  }
+}
+
+template <int G, int KH>
+int launch_spmm_hess_staged(int64_t n_rows, const int64_t* rowptr, const int32_t* col, const float* val,
+                            const float* stats, int64_t lds, int Cp, int c0, int ncols, int width, float* y,
+                            int64_t ldy, cudaStream_t st) {
+  constexpr int U = 4;
+  const int64_t blocks = (n_rows + SH_THREADS / 32 - 1) / (SH_THREADS / 32);
+  if (blocks > 0x7fffffffLL) return fail(LGNN_E_UNSUPPORTED, "spmm_hess: grid too large");
+  const int smem = (SH_THREADS / 32) * U * (2 * Cp + 3 * G) * 4;
+  spmm_hess_staged_kernel<G, KH, U><<<(unsigned)blocks, SH_THREADS, smem, st>>>(n_rows, rowptr, col, val, stats, lds, Cp,
+                                                                              c0, ncols, width, y, ldy);
+  LGNN_LAUNCH_CHECK("spmm_hess_staged_kernel");
+  return LGNN_OK;
+}
+
 bool spmm_hess_shape_ok(int64_t C, int64_t width) { return C >= 1 && C <= 64 && width >= 1 && width <= 16; }
 
 }  // namespace
@@ -236,7 +374,8 @@ extern "C" int lgnn_hess_stats_f32(const float* logits, int64_t ld, int32_t C, c
 
 extern "C" int lgnn_spmm_hess_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr, const int32_t* col,
                                   const float* val, const float* stats, int64_t ld_stats, int32_t C, int32_t c0,
-                                  int32_t ncols, int32_t width, float* y, int64_t ldy, lgnn_stream_t stream) {
+                                  int32_t ncols, int32_t width, float* y, int64_t ldy, int flags,
+                                  lgnn_stream_t stream) {
   if (n_rows < 0 || nnz < 0) return fail(LGNN_E_BADARG, "spmm_hess: negative size");
   if (!spmm_hess_shape_ok(C, width)) return fail(LGNN_E_UNSUPPORTED, "spmm_hess: C must be 1 .. 64 and the group at most 16 columns wide (C=%d width=%d)", (int)C, (int)width);
   const int Cp = (C + 3) / 4 * 4;
@@ -247,6 +386,18 @@ extern "C" int lgnn_spmm_hess_f32(int64_t n_rows, int64_t nnz, const int64_t* ro
   if (nnz > 0 && (!col || !val)) return fail(LGNN_E_BADARG, "spmm_hess: null col / val");
   cudaStream_t st = as_stream(stream);
   const int g4 = (width + 3) / 4;
+  // flags bit 8: the staged kernel (cp.async ring); needs 16-byte aligned rows and column slices
+  if ((flags & 0x100) && c0 % 4 == 0 && ld_stats % 4 == 0 && (reinterpret_cast<uintptr_t>(stats) & 15) == 0) {
+#define LGNN_SHS(G_) (Cp <= 32 ? launch_spmm_hess_staged<G_, 1>(n_rows, rowptr, col, val, stats, ld_stats, Cp, c0, ncols, width, y, ldy, st) \
+                               : launch_spmm_hess_staged<G_, 2>(n_rows, rowptr, col, val, stats, ld_stats, Cp, c0, ncols, width, y, ldy, st))
+    switch (g4) {
+      case 1: return LGNN_SHS(4);
+      case 2: return LGNN_SHS(8);
+      case 3: return LGNN_SHS(12);
+      default: return LGNN_SHS(16);
+    }
+#undef LGNN_SHS
+  }
 #define LGNN_SH(G_) (Cp <= 32 ? launch_spmm_hess<G_, 1>(n_rows, rowptr, col, val, stats, ld_stats, Cp, c0, ncols, width, y, ldy, st) \
                               : launch_spmm_hess<G_, 2>(n_rows, rowptr, col, val, stats, ld_stats, Cp, c0, ncols, width, y, ldy, st))
   switch (g4) {

@@ -429,8 +429,11 @@ def hess_stats(logits: torch.Tensor, idx: torch.Tensor, mode: str = "reference",
     return out
 
 
+SPMM_HESS_STAGED = True      # lab switch: the cp.async-ring kernel of csrc/spmm_hess.cu instead of the register one
+
+
 def spmm_hess(a: CSR, stats: torch.Tensor, C: int, c0: int, ncols: int, width: int,
-              out: torch.Tensor | None = None) -> torch.Tensor:
+              out: torch.Tensor | None = None, staged: bool | None = None) -> torch.Tensor:
     """Y[i, c*Cp + k] = sum_j A[i, j] v_{j, c0+c}[k] for c < ncols (zero columns up to ``width``): the output-layer
     SpMM of a column group with its Hessian-sqrt right-hand sides rebuilt from ``stats`` per edge."""
     lib = _lib.load()
@@ -452,7 +455,8 @@ def spmm_hess(a: CSR, stats: torch.Tensor, C: int, c0: int, ncols: int, width: i
     with _Timed("spmm_hess", d, work):
         check(lib.lgnn_spmm_hess_f32(a.n_rows, a.nnz, ptr(a.rowptr), ptr(a.col), ptr(a.val), ptr(stats),
                                      stats.stride(0), int(C), int(c0), int(ncols), int(width), ptr(out),
-                                     out.stride(0), stream()), "lgnn_spmm_hess_f32")
+                                     out.stride(0), 0x100 if (SPMM_HESS_STAGED if staged is None else staged) else 0,
+                                     stream()), "lgnn_spmm_hess_f32")
     _lib.count_launches(1)
     return out
 

@@ -96,7 +96,7 @@ def hess_stats(logits, idx, mode="reference", C=None, out=None):
     return {"logits": logits, "idx": idx, "mode": mode, "C": C}
 
 
-def spmm_hess(a, stats, C, c0, ncols, width, out=None):
+def spmm_hess(a, stats, C, c0, ncols, width, out=None, staged=None):
     cp = (C + 3) // 4 * 4
     delta = torch.zeros(a.n_cols, width * cp, dtype=torch.float32)
     hess_rhs(stats["logits"], stats["idx"], c0, ncols, delta, cp, stats["mode"], C)

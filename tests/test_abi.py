@@ -63,10 +63,10 @@ def test_bad_arguments_are_rejected_before_any_launch():
     assert lib.lgnn_spmm_hess_supported(47, 16) == 1 and lib.lgnn_spmm_hess_supported(64, 1) == 1
     assert lib.lgnn_spmm_hess_supported(65, 4) == 0 and lib.lgnn_spmm_hess_supported(47, 17) == 0
     assert lib.lgnn_hess_stats_f32(None, 48, 47, None, 10, 0, None, 240, None) == -1
-    assert lib.lgnn_spmm_hess_f32(5, 10, None, None, None, None, 240, 47, 40, 8, 8, None, 384, None) == -1   # c0 + ncols > C
-    assert lib.lgnn_spmm_hess_f32(5, 10, None, None, None, None, 239, 47, 0, 8, 8, None, 384, None) == -1    # stats pitch < 5 Cp
-    assert lib.lgnn_spmm_hess_f32(5, 10, None, None, None, None, 240, 47, 0, 8, 20, None, 960, None) == -5   # group too wide
-    assert lib.lgnn_spmm_hess_f32(0, 0, None, None, None, None, 240, 47, 0, 8, 8, None, 384, None) == 0
+    assert lib.lgnn_spmm_hess_f32(5, 10, None, None, None, None, 240, 47, 40, 8, 8, None, 384, 0, None) == -1   # c0 + ncols > C
+    assert lib.lgnn_spmm_hess_f32(5, 10, None, None, None, None, 239, 47, 0, 8, 8, None, 384, 0, None) == -1    # stats pitch < 5 Cp
+    assert lib.lgnn_spmm_hess_f32(5, 10, None, None, None, None, 240, 47, 0, 8, 20, None, 960, 0, None) == -5   # group too wide
+    assert lib.lgnn_spmm_hess_f32(0, 0, None, None, None, None, 240, 47, 0, 8, 8, None, 384, 0x100, None) == 0
 
 
 def test_missing_library_fails_loudly(tmp_path):

@@ -154,8 +154,9 @@ def test_spmm_hess_matches_materialised_path(C, mode):
             ops.hess_rhs(lg, ix, c0, ncols, delta, cp, mode, C)
             want = ops.spmm(masked, delta)
             for a in (masked, G.ahat_t):
-                got = ops.spmm_hess(a, stats, C, c0, ncols, gq)
-                assert max_rel_err(got.cpu().numpy(), want.cpu().numpy()) <= 1e-5, (width, c0)
+                for staged in (False, True):          # register kernel / cp.async-ring kernel (c0 % 4 == 0 only)
+                    got = ops.spmm_hess(a, stats, C, c0, ncols, gq, staged=staged)
+                    assert max_rel_err(got.cpu().numpy(), want.cpu().numpy()) <= 1e-5, (width, c0, staged)
             d64 = torch.zeros(n, gq, cp, dtype=torch.float64)
             d64[:, :ncols, :C].index_add_(0, idx, Vref[:, c0:c0 + ncols, :])
             ref = O.spmm(R, d64.reshape(n, gq * cp).numpy(), transpose=True, dtype=torch.float64).numpy()

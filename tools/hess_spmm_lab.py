@@ -39,11 +39,12 @@ for gg in [int(a) for a in sys.argv[1:]] or [16, 8, 6]:
         delta.zero_(); ops.hess_rhs(logits, idx, 0, gg, delta, cp, "reference", C); ops.spmm(masked, delta, out=y)
     t_rhs = timed(lambda: (delta.zero_(), ops.hess_rhs(logits, idx, 0, gg, delta, cp, "reference", C)))
     t_old = timed(materialised)
-    t_new = timed(lambda: ops.spmm_hess(masked, stats, C, 0, gg, gq, out=y2))
+    t_reg = timed(lambda: ops.spmm_hess(masked, stats, C, 0, gg, gq, out=y2, staged=False))
+    t_new = timed(lambda: ops.spmm_hess(masked, stats, C, 0, gg, gq, out=y2, staged=True))
     by_old = g.nnz * 8 + (n + 1) * 8 + live * gq * cp * 4 + n * gq * cp * 4
     by_new = g.nnz * 8 + (n + 1) * 8 + live * (2 * cp + 3 * gg) * 4 + n * gq * cp * 4
     err = float((y2 - y).abs().max() / y.abs().max())
     print(f"g={gg}: materialised {t_old:7.2f} ms (rhs {t_rhs:5.2f} + spmm {t_old - t_rhs:6.2f}: {by_old / (t_old - t_rhs) / 1e6:5.0f} GB/s)"
-          f" | on the fly {t_new:7.2f} ms ({by_new / t_new / 1e6:5.0f} GB/s of its own bytes, {by_new / t_new / 1e6 / peak:4.2f} of peak)"
+          f" | on the fly: register kernel {t_reg:7.2f} ms, staged {t_new:7.2f} ms ({by_new / t_new / 1e6:5.0f} GB/s of its own bytes, {by_new / t_new / 1e6 / peak:4.2f} of peak)"
           f" | speed-up {t_old / t_new:4.2f}x | max rel diff {err:.1e}", flush=True)
     del delta, y, y2
