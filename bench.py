@@ -56,6 +56,8 @@ def parse_args():
                     help="lab: output-layer SpMM with its Hessian-sqrt right-hand sides rebuilt per edge (csrc/spmm_hess.cu)")
     ap.add_argument("--syrk-stack-narrow", action="store_true",
                     help="lab: output-layer G through the wide view of the slab (ops.syrk_stacked)")
+    ap.add_argument("--overlap-groups", action="store_true",
+                    help="lab: two column groups in flight on two streams (SYRK / GEMM of one under the SpMM of the other)")
     ap.add_argument("--shard-eigh", action="store_true",
                     help="lab, multi-GPU: spread the factor eigendecompositions over the ranks (kron.Kron.decompose)")
     ap.add_argument("--rhs-tile-gb", type=float, default=None,
@@ -261,7 +263,8 @@ def main():
         del edge_index
     bk = {"hess_sqrt": args.hess_sqrt, "syrk_impl": args.syrk, "fused_gemm": not args.no_fused_gemm,
           "unit_slabs": not args.dense_slabs, "unit_even_groups": args.unit_even_groups,
-          "fused_hess_spmm": args.fused_hess_spmm, "syrk_stack_narrow": args.syrk_stack_narrow}
+          "fused_hess_spmm": args.fused_hess_spmm, "syrk_stack_narrow": args.syrk_stack_narrow,
+          "overlap_groups": args.overlap_groups}
     if args.rhs_tile_gb is not None:
         bk["rhs_tile_bytes"] = int(args.rhs_tile_gb * 1e9)
     if pg is not None:

@@ -28,6 +28,7 @@ curvlinops / asdl / backpack.  Returned tensors are fresh, detached, fp32, on th
 """
 from __future__ import annotations
 
+import contextlib
 import sys
 from typing import Any
 
@@ -169,7 +170,7 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, syrk_stack_narrow=False):
+                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, syrk_stack_narrow=False, overlap_groups=False):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -227,6 +228,10 @@ class _B200KFAC:
         # G of the output layer (n = C): SYRK of the slab viewed [K/s, s*ld] instead of [K, ld] (ops.syrk_stacked);
         # OFF until n = s*ld (240 at C = 47) has been timed on a B200
         self.syrk_stack_narrow = bool(syrk_stack_narrow)
+        # single GPU / column-parallel backward: two column groups in flight on two streams (half-size slabs each),
+        # so that the tensor-bound SYRK / GEMM of one group can run under the HBM-bound SpMM of the other.
+        # An experiment for the first GPU pass of round 2 (whether the block scheduler co-schedules them): OFF
+        self.overlap_groups = bool(overlap_groups)
         self.unit_row_limit = 4096
         # A_0 = X^T X does not depend on the weights: with cache_input_factor the raw Gram matrix of
         # this rank's feature rows is kept (per backend, or in a dict shared across backends by the
@@ -425,7 +430,10 @@ class _B200KFAC:
         c_first, c_count = cols
         dev = logits.device
         n_loc, n_in = lay.n_local, lay.total_rows
-        lanes = 2 if (self.overlap and lay.communicates and dev.type == "cuda") else 1
+        # two column groups in flight: always worthwhile when a group waits for collectives (rows layout); with
+        # overlap_groups also when every row is local, so that one group's tensor-bound SYRK / GEMM can share the
+        # device with the other's HBM-bound SpMM (the groups' chains are independent)
+        lanes = 2 if ((self.overlap and lay.communicates and dev.type == "cuda") or self.overlap_groups) else 1
         room = self._group_size(lanes * n_in, lanes * n_loc, dmax, 1 << 30, dev)   # columns the HBM budget allows
         grp = min(room, C)
         hidden = max(dims[:-1]) if len(dims) > 1 else 0
@@ -436,7 +444,8 @@ class _B200KFAC:
         # unit-compacted slabs want groups of 4, 8, 12 or 16 columns (any even count with unit_even_groups):
         # the last group of a pass is padded with all-zero right-hand sides (47 classes -> 16 + 16 + 15(+1))
         q = 2 if self.unit_even_groups else 4
-        cand = min(room // q * q, 16, (max(c_count, 1) + q - 1) // q * q)
+        per_lane = (max(c_count, 1) + lanes - 1) // lanes         # = c_count with one group in flight
+        cand = min(room // q * q, 16, (per_lane + q - 1) // q * q)
         pad4 = (self._units_possible(lay) and not can_pack and cand >= q and
                 any(self._can_unit(lay, cand, h) for h in dims[:-1]))
         if pad4:
@@ -446,6 +455,7 @@ class _B200KFAC:
         groups = [(c0, min(grp, c_first + c_count - c0)) for c0 in range(c_first, c_first + c_count, grp)]
         width_of = (lambda gc: (gc + q - 1) // q * q) if pad4 else (lambda gc: gc)
         hdr = torch.empty(n_in, max(max(dims[:-1]) // 32, 1), 2, dtype=torch.int32, device=dev) if pad4 else None
+        hdrs = [hdr, torch.empty_like(hdr) if (hdr is not None and lanes > 1) else None]
         # W_l [d_l, d_{l-1}] as resident tensor-core operands, once per pass
         Wp = [None] + [ops.gemm_mask_prepare(Ws[l]) if self.fused_gemm and dev.type == "cuda" and
                        ops.gemm_mask_supported(Ws[l].shape[0], Ws[l].shape[1]) else None
@@ -466,26 +476,30 @@ class _B200KFAC:
             return grp, len(groups)
         # two column groups in flight, each on its own stream with its own buffers and factor
         # accumulators: while one waits for its all-gather the other runs its SpMM / SYRK / GEMM
-        main = torch.cuda.current_stream(dev)
-        streams = _lane_streams(dev, lanes)
+        on_device = dev.type == "cuda"           # the CPU double walks the same interleaving without streams
+        main = torch.cuda.current_stream(dev) if on_device else None
+        streams = _lane_streams(dev, lanes) if on_device else [None] * lanes
         G_lane = [G] + [[torch.zeros_like(t) for t in G] for _ in range(lanes - 1)]
         for st in streams:
-            st.wait_stream(main)
+            if st is not None:
+                st.wait_stream(main)
         pending = list(groups)
         active = [None] * lanes
         while pending or any(a is not None for a in active):
             for i in range(lanes):
-                with torch.cuda.stream(streams[i]):
+                with (torch.cuda.stream(streams[i]) if on_device else contextlib.nullcontext()):
                     if active[i] is None and pending:
                         c0, gc = pending.pop(0)
-                        active[i] = self._chain(lay, logits, idx, Hs, Ws, Wp, c0, gc, gc, bufs[i][0], bufs[i][1], G_lane[i])
+                        active[i] = self._chain(lay, logits, idx, Hs, Ws, Wp, c0, gc, width_of(gc), bufs[i][0],
+                                                bufs[i][1], G_lane[i], hdrs[i])
                     if active[i] is not None:
                         try:
                             next(active[i])
                         except StopIteration:
                             active[i] = None
         for st in streams:
-            main.wait_stream(st)
+            if st is not None:
+                main.wait_stream(st)
         for extra in G_lane[1:]:
             for t, e in zip(G, extra):
                 t += e
@@ -628,7 +642,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, syrk_stack_narrow=False):
+                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, syrk_stack_narrow=False, overlap_groups=False):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -639,7 +653,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
                          backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs,
-                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split, fused_hess_spmm, syrk_stack_narrow)
+                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split, fused_hess_spmm, syrk_stack_narrow, overlap_groups)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

@@ -458,17 +458,36 @@ def test_edge_case_shapes_match_the_oracle(fake_ops, n, U, F, h, C, layers, M, d
             assert float((a - b).abs().max()) <= 1e-5 * max(float(b.abs().max()), 1e-6)
 
 
+@pytest.mark.parametrize("units", [True, False])
+def test_two_column_groups_in_flight_give_the_same_factors(fake_ops, units):
+    """overlap_groups: two column groups interleaved layer by layer, each with its own slabs, unit headers and
+    factor accumulators (summed at the end) — the CPU double walks the same interleaving without streams."""
+    import laplace_gnn_b200 as L
+    model, idx, y = _synthetic_model(400, 1600, 12, 64, 10, 3)
+    budget = 400 * 64 * 4 * 2 * 2 * 4                                   # room for 4 columns per lane
+    be = L.B200GGN(model, "classification", overlap_groups=True, unit_slabs=units, unit_min_width=0,
+                   rhs_tile_bytes=budget)
+    l1, k1 = be.kron(idx, y, N=len(y))
+    assert be.last_stats["n_groups"] == 3 and be.last_stats["group"] == 4
+    assert (be.last_stats["unit_slabs"] > 0) == units
+    l2, k2 = L.B200GGN(model, "classification", unit_slabs=False).kron(idx, y, N=len(y))
+    assert float(l1) == float(l2)
+    for fa, fb in zip(k1.kfacs, k2.kfacs):
+        for a, b in zip(fa, fb):
+            assert max_rel_err(a.numpy(), b.numpy()) <= 1e-5
+
+
 def test_all_lab_switches_compose(fake_ops):
     """Every opt-in path of DESIGN.md §6c at once (even column groups, hub split, on-the-fly output-layer SpMM,
     stacked narrow SYRK) through the Laplace driver: the marglik of the plain dense path."""
     import laplace_gnn_b200 as L
     model, idx, y = _synthetic_model(300, 1200, 10, 64, 7, 3)
     kw = {"unit_min_width": 0, "unit_even_groups": True, "fused_hess_spmm": True, "syrk_stack_narrow": True,
-          "unit_hub_split": True}
+          "unit_hub_split": True, "overlap_groups": True}
     la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs=kw)
     la.backend.unit_row_limit = 8
     la.fit(L.TensorBatchLoader(idx, y))
-    assert la.backend.last_stats["unit_slabs"] > 0 and la.backend.last_stats["group"] == 8
+    assert la.backend.last_stats["unit_slabs"] > 0 and la.backend.last_stats["group"] == 4    # 7 classes, two lanes
     ref = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs={"unit_slabs": False})
     ref.fit(L.TensorBatchLoader(idx, y))
     a, b = float(la.log_marginal_likelihood()), float(ref.log_marginal_likelihood())

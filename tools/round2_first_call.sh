@@ -21,7 +21,8 @@ B="python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline"
 run r2_bench_base 300 $B
 run r2_bench_hess 300 $B --fused-hess-spmm
 run r2_bench_stack 300 $B --syrk-stack-narrow
-for f in r2_bench_base r2_bench_hess r2_bench_stack; do python - "$f" <<'PY'
+run r2_bench_overlap 300 $B --overlap-groups
+for f in r2_bench_base r2_bench_hess r2_bench_stack r2_bench_overlap; do python - "$f" <<'PY'
 import json, sys
 try:
     d = json.loads(open(f"gpurun_out/{sys.argv[1]}.log").read().strip().splitlines()[-1])
