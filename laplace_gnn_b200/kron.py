@@ -21,17 +21,26 @@ import torch
 from torch.nn.utils import parameters_to_vector
 
 
-def _eigh_psd(m: torch.Tensor):
-    """symeig of the reference (laplace/utils/utils.py:193-226): eigh(UPLO="U"), eigenvalues clamped
-    at 0, NaN -> 0.  On the device the decomposition itself runs in float64 for n <= 1024 and is cast
-    back: cusolver's double-precision path is 2-3x FASTER than the Jacobi solver torch picks for small
-    fp32 matrices (B200: n = 256: 2.4 vs 5.3 ms, n = 500: 5.5 vs 15.6 ms; profiles/r1f_eigh_lab.txt) and
-    its eigenvalues are exact to fp32 rounding."""
+def _eigh(m: torch.Tensor):
     if m.is_cuda and m.dtype == torch.float32 and m.shape[-1] <= 1024:
         lam, q = torch.linalg.eigh(m.double(), UPLO="U")
-        lam, q = lam.to(m.dtype), q.to(m.dtype)
-    else:
-        lam, q = torch.linalg.eigh(m, UPLO="U")
+        return lam.to(m.dtype), q.to(m.dtype)
+    return torch.linalg.eigh(m, UPLO="U")
+
+
+def _eigh_psd(m: torch.Tensor):
+    """symeig of the reference (laplace/utils/utils.py:193-226): eigh(UPLO="U"); when the solver does not
+    converge (rank-deficient factors with many repeated tiny eigenvalues do that to LAPACK's / cusolver's fp32
+    divide-and-conquer) the reference's jitter fallback, W L W^T + I = W (L + I) W^T: decompose M + I and take 1
+    off the eigenvalues; then eigenvalues clamped at 0, NaN -> 0.  On the device the decomposition itself runs in
+    float64 for n <= 1024 and is cast back: cusolver's double-precision path is 2-3x FASTER than the Jacobi solver
+    torch picks for small fp32 matrices (B200: n = 256: 2.4 vs 5.3 ms, n = 500: 5.5 vs 15.6 ms;
+    profiles/r1f_eigh_lab.txt) and its eigenvalues are exact to fp32 rounding."""
+    try:
+        lam, q = _eigh(m)
+    except RuntimeError:               # did not converge (torch's LinAlgError is a RuntimeError)
+        lam, q = _eigh(m + torch.eye(m.shape[-1], device=m.device, dtype=m.dtype))
+        lam = lam - 1.0
     return torch.nan_to_num(lam.clamp(min=0.0)), torch.nan_to_num(q)
 
 

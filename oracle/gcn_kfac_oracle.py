@@ -269,8 +269,13 @@ def kron_factors(g: NormAdj, x, weights, biases, idx, y, n_data: int,
 
 
 def symeig(m: torch.Tensor):
-    """utils.py:193-226: eigh(UPLO='U'), eigenvalues clamped >= 0, NaN -> 0."""
-    lam, q = torch.linalg.eigh(m, UPLO="U")
+    """utils.py:193-226: eigh(UPLO='U'); if the solver does not converge, the reference's jitter fallback
+    (decompose M + I, take 1 off the eigenvalues, :209-216); eigenvalues clamped >= 0, NaN -> 0."""
+    try:
+        lam, q = torch.linalg.eigh(m, UPLO="U")
+    except RuntimeError:
+        lam, q = torch.linalg.eigh(m + torch.eye(m.shape[0], dtype=m.dtype), UPLO="U")
+        lam = lam - 1.0
     return torch.nan_to_num(lam.clamp(min=0.0)), torch.nan_to_num(q)
 
 

@@ -47,6 +47,8 @@ CASES = {
     # the arxiv / products kernel shapes at a size the reference finishes in seconds: 3 layers, h = 256 (fused
     # tcgen05 GEMM, tcgen05 SYRK n = 256, unit-compacted slabs), C = 40 (column groups 16 + 16 + 8)
     "arxiv_mini_3l": dict(n=1200, U=8000, F=128, C=40, h=256, L=3, directed=False, tier="O2", feat="normal"),
+    # the products shape in small: 47 classes (logits pitch padded to 48, column groups 16 + 16 + 15(+1)), F = 100
+    "products_mini_3l": dict(n=1000, U=12000, F=100, C=47, h=256, L=3, directed=False, tier="O2", feat="normal"),
 }
 
 

@@ -14,7 +14,7 @@ GOLDEN_SMALL = ["tiny_undirected_2l", "tiny_directed_3l", "tiny_directed_dups_2l
                 "tiny_symmetrised_2l", "small_multibatch_2l"]
 GOLDEN_ALL = GOLDEN_SMALL + ["cora_shape", "pubmed_shape"]
 # the headline kernels' shapes (3 layers, h = 256, C = 40) at a size the reference finishes in seconds
-GOLDEN_KERNEL_SHAPES = ["arxiv_mini_3l"]
+GOLDEN_KERNEL_SHAPES = ["arxiv_mini_3l", "products_mini_3l"]
 
 
 # kernels that have not yet run on a B200 keep their GPU tests behind LGNN_LAB=1, so that the default

@@ -361,13 +361,14 @@ def test_backend_ggn_mode_matches_upstream_curvlinops_goldens(golden_small, fake
     assert abs(float(ml) - g.marglik) > 1e-4 * abs(g.marglik)          # and it is not the fork's value
 
 
-def test_backend_matches_reference_at_kernel_shapes(fake_ops):
-    """arxiv_mini_3l (3 layers, h = 256, C = 40; reference O2 fit): the backend's orchestration with unit-compacted
-    slabs and column groups 16 + 16 + 8, and with dense groups of 7, against the reference's factors."""
+@pytest.mark.parametrize("name,dense_groups", [("arxiv_mini_3l", 6), ("products_mini_3l", 7)])
+def test_backend_matches_reference_at_kernel_shapes(fake_ops, name, dense_groups):
+    """3 layers, h = 256, C = 40 / 47 (reference O2 fits): the backend's orchestration with unit-compacted slabs and
+    column groups 16 + 16 + 8 resp. 16 + 16 + 15(+1), and with dense groups of 7, against the reference's factors."""
     import laplace_gnn_b200 as L
-    g = Golden("arxiv_mini_3l")
+    g = Golden(name)
     model = build_model(g)
-    for kw, groups in (({}, 3), ({"unit_slabs": False, "rhs_tile_bytes": 2 * g.n * 256 * 4 * 7}, 6)):
+    for kw, groups in (({}, 3), ({"unit_slabs": False, "rhs_tile_bytes": 2 * g.n * 256 * 4 * 7}, dense_groups)):
         la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs=kw)
         la.fit(loader_for(g))
         check_against_golden(g, la.loss, la.H_facs.kfacs, la.log_marginal_likelihood())
@@ -475,6 +476,49 @@ def test_two_column_groups_in_flight_give_the_same_factors(fake_ops, units):
     for fa, fb in zip(k1.kfacs, k2.kfacs):
         for a, b in zip(fa, fb):
             assert max_rel_err(a.numpy(), b.numpy()) <= 1e-5
+
+
+def test_symeig_jitter_fallback_like_the_reference():
+    """laplace/utils/utils.py:209-216: when eigh does not converge the reference decomposes M + I and takes 1 off
+    the eigenvalues.  The G factor of the products-shaped mini fixture (rank-deficient, many repeated tiny
+    eigenvalues) makes LAPACK's fp32 divide-and-conquer give up; the stand-in and the oracle must survive it like
+    the reference did when it produced that fixture."""
+    from laplace_gnn_b200.kron import _eigh_psd
+    from oracle import gcn_kfac_oracle as O
+    g = Golden("products_mini_3l")
+    M = torch.from_numpy(g.kfacs[2][0])
+    try:
+        torch.linalg.eigh(M, UPLO="U")
+        converges = True
+    except RuntimeError:
+        converges = False
+    for fn in (_eigh_psd, O.symeig):
+        lam, q = fn(M)
+        assert bool(torch.isfinite(lam).all()) and bool(torch.isfinite(q).all()) and float(lam.min()) >= 0.0
+        rec = (q * lam[None, :]) @ q.T
+        assert float((rec - M).abs().max()) <= 1e-5 * float(M.abs().max())
+    if not converges:            # the fallback really ran: eigenvalues carry the fp32 resolution of 1 + lambda
+        assert float(_eigh_psd(M)[0].max()) > 0.0
+
+    class Flaky:                 # a solver that fails on the first call: the jittered retry must be used
+        calls = 0
+    import laplace_gnn_b200.kron as K
+    real = K._eigh
+
+    def flaky(m):
+        Flaky.calls += 1
+        if Flaky.calls == 1:
+            raise RuntimeError("linalg.eigh: The algorithm failed to converge")
+        return real(m)
+    K._eigh = flaky
+    try:
+        A = torch.randn(20, 6)
+        S = A @ A.T                                   # rank 6
+        lam, q = K._eigh_psd(S)
+    finally:
+        K._eigh = real
+    assert Flaky.calls == 2
+    assert float(((q * lam[None, :]) @ q.T - S).abs().max()) <= 1e-5 * float(S.abs().max())
 
 
 def test_all_lab_switches_compose(fake_ops):

@@ -1,11 +1,12 @@
 """GPU: the whole fit on the shapes the headline kernels take (3 layers, h = 256, C = 40: fused tcgen05 GEMM +
 relu' mask, tcgen05 SYRK at n = 256, unit-compacted slabs in column groups 16 + 16 + 8) against the REFERENCE's own
-factors, loss and log marginal likelihood (tests/golden/arxiv_mini_3l.npz, oracle/make_golden.py tier O2).
+factors, loss and log marginal likelihood (tests/golden/arxiv_mini_3l.npz and products_mini_3l.npz — 47 classes, logits
+pitch padded to 48, groups 16 + 16 + 15(+1) — oracle/make_golden.py tier O2).
 North-star tolerances: factors <= 1e-4 rel, marglik <= 1e-3 rel.  (File name: sorts after the per-kernel tests.)"""
 import pytest
 import torch
 
-from conftest import GOLDEN_SMALL, GgnGolden, Golden, max_rel_err
+from conftest import GOLDEN_KERNEL_SHAPES, GOLDEN_SMALL, GgnGolden, Golden, max_rel_err
 from helpers import build_model, check_against_golden, loader_for
 
 pytestmark = pytest.mark.gpu
@@ -19,9 +20,12 @@ DEV = "cuda:0"
     {"fused_gemm": False, "syrk_impl": "simt"},                # cuBLAS + mask kernel, CUDA-core SYRK
     {"hess_sqrt": "reference", "rhs_tile_bytes": 2 * 1200 * 256 * 4 * 12},   # column groups of 12
 ], ids=["default", "dense-slabs", "two-step-simt", "groups-of-12"])
-def test_fit_matches_the_reference_at_kernel_shapes(kw):
+@pytest.mark.parametrize("name", GOLDEN_KERNEL_SHAPES)
+def test_fit_matches_the_reference_at_kernel_shapes(name, kw):
     import laplace_gnn_b200 as L
-    g = Golden("arxiv_mini_3l")
+    g = Golden(name)
+    if "rhs_tile_bytes" in kw:
+        kw = dict(kw, rhs_tile_bytes=2 * g.n * 256 * 4 * 12)
     model = build_model(g, DEV)
     la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs=kw)
     la.fit(loader_for(g, DEV))
@@ -30,11 +34,12 @@ def test_fit_matches_the_reference_at_kernel_shapes(kw):
     st = la.backend.last_stats
     assert (st["unit_slabs"] > 0) == kw.get("unit_slabs", True)
     if "rhs_tile_bytes" in kw:
-        assert st["group"] == 12 and st["n_groups"] == 4
+        assert st["group"] == 12 and st["n_groups"] == 4          # 40 = 12 + 12 + 12 + 4, 47 = 12 + 12 + 12 + 11(+1)
 
 
-def test_logits_match_the_reference_at_kernel_shapes():
-    g = Golden("arxiv_mini_3l")
+@pytest.mark.parametrize("name", GOLDEN_KERNEL_SHAPES)
+def test_logits_match_the_reference_at_kernel_shapes(name):
+    g = Golden(name)
     model = build_model(g, DEV)
     model.eval()
     with torch.no_grad():
