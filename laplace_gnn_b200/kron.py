@@ -342,6 +342,38 @@ class _ParametricLaplaceLite:
         self.n_outputs = getattr(self.backend, "n_outputs", self.n_outputs)
         self.n_data += N
 
+    # ---- checkpoint / resume (baselaplace.py:1314-1374, :1664-1676)
+    def state_dict(self) -> dict:
+        if self.H is None:
+            raise AttributeError("Laplace not fitted. Run fit() first.")
+        return {"mean": self.mean, "H": self._H_state(), "loss": self.loss, "prior_mean": self.prior_mean,
+                "prior_precision": self.prior_precision, "n_data": self.n_data, "n_outputs": self.n_outputs,
+                "likelihood": self.likelihood, "temperature": self.temperature,
+                "cls_name": self.__class__.__name__}
+
+    def load_state_dict(self, state_dict: dict) -> None:
+        if self.__class__.__name__ != state_dict["cls_name"]:
+            raise ValueError("Loading a wrong Laplace type. Make sure `subset_of_weights` and"
+                             " `hessian_structure` are correct!")
+        if len(state_dict["mean"]) != self.n_params:
+            raise ValueError("Attempting to load Laplace with different number of parameters than the model.")
+        if self.likelihood != state_dict["likelihood"]:
+            raise ValueError("Different likelihoods detected!")
+        self.mean = state_dict["mean"]
+        self.loss = state_dict["loss"]
+        self.prior_mean = state_dict["prior_mean"]
+        self.prior_precision = state_dict["prior_precision"]
+        self.n_data = state_dict["n_data"]
+        self.n_outputs = state_dict["n_outputs"]
+        self.temperature = state_dict["temperature"]
+        self._load_H_state(state_dict["H"])
+
+    def _H_state(self):
+        return self.H
+
+    def _load_H_state(self, H) -> None:
+        self.H = H
+
     def optimize_prior_precision(self, init_prior_prec=1.0, n_steps: int = 100, lr: float = 0.1,
                                  prior_structure: str = "scalar", verbose: bool = False):
         """Marginal-likelihood tuning of the prior precision (baselaplace.py:419-463): Adam on
@@ -375,16 +407,39 @@ class KronLaplace(_ParametricLaplaceLite):
     def _curv_closure(self, X, y, N):
         return self.backend.kron(X, y, N=N)
 
+    @staticmethod
+    def _rescale_factors(kron: Kron, factor: float) -> Kron:
+        for f in kron.kfacs:                      # only the input-side factor carries the 1/N (baselaplace.py:1574-1578)
+            if len(f) == 2:
+                f[1] *= factor
+        return kron
+
     def fit(self, train_loader, override: bool = True) -> None:
+        """``override=False`` continues a fitted posterior with more data the way the reference does
+        (baselaplace.py:1580-1610): the old factors are discounted by n_old / (n_old + n_new), the new ones by
+        n_new / (n_new + n_old), loss and n_data accumulate."""
         if override:
             self.H_facs = None
-        self.H = self.H_facs
+        n_old, n_new = self.n_data, len(train_loader.dataset)
+        if self.H_facs is not None:
+            self.H_facs = self._rescale_factors(self.H_facs, n_old / (n_old + n_new))
+        self.H = None                            # the batches of this call are summed on their own
         super().fit(train_loader, override=override)
-        self.H_facs = self.H
+        if self.H_facs is None:
+            self.H_facs = self.H
+        else:
+            self.H_facs = self.H_facs + self._rescale_factors(self.H, n_new / (n_new + n_old))
         # multi-GPU pass: the factors are all-reduced, the eigendecompositions are spread over the ranks
         pg = getattr(self.backend, "process_group", None)
         shard = pg is not None and getattr(self.backend, "shard_eigh", False)
         self.H = self.H_facs.decompose(process_group=pg) if shard else self.H_facs.decompose()
+
+    def _H_state(self):                          # the reference stores the undecomposed factors (:1664-1668)
+        return self.H_facs.kfacs
+
+    def _load_H_state(self, kfacs) -> None:      # ... and re-decomposes on load (:1670-1676)
+        self.H_facs = Kron(kfacs)
+        self.H = self.H_facs.decompose()
 
     @property
     def posterior_precision(self) -> KronDecomposed:

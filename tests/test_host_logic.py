@@ -201,6 +201,108 @@ print('DROPIN_OK')
     assert "DROPIN_OK" in out.stdout, out.stderr[-3000:]
 
 
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).available(),
+                    reason="reference tree only exists in the dev container")
+def test_continual_fit_and_state_dict_match_the_reference(fake_ops):
+    """fit(override=False) (baselaplace.py:1580-1610: old factors discounted by n_old / (n_old + n_new), new ones
+    by n_new / (n_new + n_old)) and state_dict / load_state_dict (:1314-1374, :1664-1676): the stand-in driven by
+    B200GGN against the UNMODIFIED reference KronLaplace driven by its own CurvlinopsGGN, and a checkpoint of the
+    reference loaded into the stand-in."""
+    import subprocess, sys
+    from conftest import ROOT
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from oracle import ref_loader
+R = ref_loader.load()
+import laplace_gnn_b200 as L
+import laplace_gnn_b200.ops as ops, fake_ops as F
+for n in F.ALL: setattr(ops, n, getattr(F, n))
+from conftest import Golden, max_rel_err
+from helpers import build_model
+from torch.utils.data import DataLoader, TensorDataset
+g = Golden('tiny_directed_3l')
+idx, y = torch.from_numpy(g.idx), torch.from_numpy(g.y)
+h = len(idx) // 3
+first = DataLoader(TensorDataset(idx[:h], y[:h]), batch_size=h)
+second = DataLoader(TensorDataset(idx[h:], y[h:]), batch_size=len(idx))
+# reference: its dense GCN with the fixture's weights, default backend
+import scipy.sparse as sp
+a = sp.coo_matrix((np.ones(g.edge_index.shape[1]), (g.edge_index[0], g.edge_index[1])), shape=(g.n, g.n)).toarray()
+adj = torch.tensor(a, dtype=torch.int64).float(); adj[adj > 1] = 1
+ref_model = R.GCN(g.F, g.h, g.C, g.L, torch.from_numpy(g.x), adj, dropout_p=0.5)
+with torch.no_grad():
+    for l, conv in enumerate(ref_model.convs):
+        conv.lin.weight.copy_(torch.from_numpy(g.Ws[l])); conv.lin.bias.copy_(torch.from_numpy(g.bs[l]))
+ref_model.eval()
+ref = R.Laplace(ref_model, 'classification', subset_of_weights='all', hessian_structure='kron')
+ref.fit(first); ref.fit(second, override=False)
+la = L.Laplace(build_model(g), 'classification', backend=L.B200GGN)
+la.fit(first); la.fit(second, override=False)
+assert la.n_data == ref.n_data == len(idx)
+for fa, fb in zip(la.H_facs.kfacs, ref.H_facs.kfacs):
+    for a_, b_ in zip(fa, fb):
+        assert max_rel_err(a_.numpy(), b_.detach().numpy()) <= 1e-4
+ml, ml_ref = float(la.log_marginal_likelihood()), float(ref.log_marginal_likelihood())
+assert abs(ml - ml_ref) <= 1e-3 * abs(ml_ref) and abs(float(la.loss) - float(ref.loss)) <= 1e-4 * abs(float(ref.loss))
+# a third fit with override=True starts over
+la.fit(first); ref.fit(first)
+assert la.n_data == ref.n_data == h
+assert abs(float(la.log_marginal_likelihood()) - float(ref.log_marginal_likelihood())) <= 1e-3 * abs(ml_ref)
+# checkpoint of the reference -> the stand-in, and the stand-in's own round trip
+ref.fit(first); ref.fit(second, override=False)
+sd = ref.state_dict()
+sd = {k: (v.detach() if torch.is_tensor(v) else v) for k, v in sd.items()}
+sd['H'] = [[t.detach() for t in blk] for blk in sd['H']]
+la2 = L.Laplace(build_model(g), 'classification', backend=L.B200GGN)
+la2.load_state_dict(sd)
+assert abs(float(la2.log_marginal_likelihood()) - ml_ref) <= 1e-5 * abs(ml_ref)
+la3 = L.Laplace(build_model(g), 'classification', backend=L.B200GGN)
+la3.load_state_dict(la.state_dict())
+assert float(la3.log_marginal_likelihood()) == float(la.log_marginal_likelihood())
+try:
+    L.Laplace(build_model(g), 'classification', hessian_structure='diag', backend=L.B200GGN).load_state_dict(sd)
+    raise SystemExit('wrong class accepted')
+except ValueError:
+    pass
+print('CONTINUAL_OK')
+""" % (ROOT, ROOT)
+    out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, timeout=600)
+    assert "CONTINUAL_OK" in out.stdout, out.stderr[-3000:]
+
+
+def test_state_dict_round_trip_and_continual_fit_algebra(fake_ops):
+    """Checkpoint / resume and fit(override=False) of the stand-in without the reference at hand: a loaded
+    checkpoint reproduces the marglik bit for bit; two halves fitted in sequence give the factor algebra of
+    baselaplace.py:1580-1610 (A discounted by the data shares, G summed)."""
+    import laplace_gnn_b200 as L
+    g = Golden("tiny_undirected_2l")
+    idx, y = torch.from_numpy(g.idx), torch.from_numpy(g.y)
+    h = len(idx) // 2
+    la = L.Laplace(build_model(g), "classification", backend=L.B200GGN)
+    with pytest.raises(AttributeError):
+        la.state_dict()
+    la.fit(L.TensorBatchLoader(idx[:h], y[:h]))
+    k1 = [[t.clone() for t in blk] for blk in la.H_facs.kfacs]
+    la.fit(L.TensorBatchLoader(idx[h:], y[h:]), override=False)
+    solo = L.Laplace(build_model(g), "classification", backend=L.B200GGN)
+    solo.fit(L.TensorBatchLoader(idx[h:], y[h:]))
+    n1, n2 = h, len(idx) - h
+    for blk, b1, b2 in zip(la.H_facs.kfacs, k1, solo.H_facs.kfacs):
+        assert max_rel_err(blk[0].numpy(), (b1[0] + b2[0]).numpy()) <= 1e-6
+        if len(blk) == 2:
+            want = b1[1] * (n1 / (n1 + n2)) + b2[1] * (n2 / (n1 + n2))
+            assert max_rel_err(blk[1].numpy(), want.numpy()) <= 1e-6
+    assert la.n_data == len(idx)
+    buf = __import__("io").BytesIO()
+    torch.save(la.state_dict(), buf)
+    buf.seek(0)
+    la2 = L.Laplace(build_model(g), "classification", backend=L.B200GGN)
+    la2.load_state_dict(torch.load(buf, weights_only=False))
+    assert float(la2.log_marginal_likelihood()) == float(la.log_marginal_likelihood())
+    assert torch.equal(la2.sample(3, torch.Generator().manual_seed(0)), la.sample(3, torch.Generator().manual_seed(0)))
+
+
 def test_marglik_training_epoch_loop(fake_ops):
     """the reference's per-epoch train step + fit + marglik + validation forward
     (gnn/marglik_training.py:159-329) on the sparse model; A_0 is cached across epochs."""
