@@ -199,7 +199,9 @@ class KronDecomposed:
         return KronDecomposed(self.eigenvectors, self.eigenvalues, self.deltas + deltas, self.damping)
 
     def __mul__(self, s) -> "KronDecomposed":
-        vals = [[f[0] * s] + list(f[1:]) for f in self.eigenvalues]
+        # spread evenly over the eigenvalue lists of a block, like the reference (matrix.py:347-366): the same
+        # products without damping, the same damped terms with it
+        vals = [[(s ** (1.0 / len(f))) * lam for lam in f] for f in self.eigenvalues]
         return KronDecomposed(self.eigenvectors, vals, self.deltas, self.damping)
 
     __rmul__ = __mul__
