@@ -493,7 +493,9 @@ class DiagLaplace(_ParametricLaplaceLite):
 
 def Laplace(model, likelihood="classification", subset_of_weights="all", hessian_structure="kron",
             **kwargs):
-    """Factory with the reference's signature (laplace/laplace.py:13-47), hot-path subset."""
+    """Factory with the reference's signature (laplace/laplace.py:13-47), hot-path subset.  One deliberate
+    difference: the reference's default is ``subset_of_weights="last_layer"``; only "all" — what every call site of
+    gnn/marglik_training.py passes (:197-201, :261-265, :653-657) — is built here, so it is the default."""
     if subset_of_weights != "all":
         raise NotImplementedError("only subset_of_weights='all' is on the hot path")
     table = {"kron": KronLaplace, "diag": DiagLaplace}
