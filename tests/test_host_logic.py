@@ -271,6 +271,62 @@ print('CONTINUAL_OK')
     assert "CONTINUAL_OK" in out.stdout, out.stderr[-3000:]
 
 
+@pytest.mark.skipif(not __import__("oracle.ref_loader", fromlist=["x"]).available(),
+                    reason="reference tree only exists in the dev container")
+def test_stand_in_driver_algebra_matches_the_reference_driver(fake_ops):
+    """The same backend (B200GGN on the CPU double) under the UNMODIFIED reference KronLaplace and under the
+    stand-in: marglik with a per-layer prior, a temperature, a prior mean; prior-precision tuning (scalar and
+    layerwise, baselaplace.py:419-463); the decomposed posterior's bmm at exponents -1/2 and 1."""
+    import subprocess, sys
+    from conftest import ROOT
+    code = r"""
+import sys, numpy as np, torch
+sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests')
+from oracle import ref_loader
+R = ref_loader.load()
+import laplace_gnn_b200 as L
+from laplace_gnn_b200.kron import Laplace as StandIn
+import laplace_gnn_b200.ops as ops, fake_ops as F
+for n in F.ALL: setattr(ops, n, getattr(F, n))
+from conftest import Golden
+from helpers import build_model, loader_for
+def close(a, b, tol=1e-5):
+    a, b = float(a), float(b)
+    assert abs(a - b) <= tol * abs(b), (a, b)
+for name in ['tiny_directed_3l', 'small_multibatch_2l']:
+    g = Golden(name)
+    n_layers = 2 * g.L
+    for kw in ({}, {'prior_precision': torch.linspace(0.5, 2.0, n_layers)}, {'temperature': 2.0},
+               {'prior_mean': 0.1, 'prior_precision': 3.0}):
+        ref = R.Laplace(build_model(g), 'classification', subset_of_weights='all', hessian_structure='kron',
+                        backend=L.B200GGN, **kw)
+        ref.fit(loader_for(g))
+        la = StandIn(build_model(g), 'classification', backend=L.B200GGN, **kw)
+        la.fit(loader_for(g))
+        close(la.log_marginal_likelihood(), ref.log_marginal_likelihood())
+        close(la.log_det_posterior_precision, ref.log_det_posterior_precision)
+        close(la.scatter, ref.scatter)
+        eps = torch.randn(4, la.n_params, generator=torch.Generator().manual_seed(1))
+        for ex in (-0.5, 1.0):
+            a, b = la.posterior_precision.bmm(eps, exponent=ex), ref.posterior_precision.bmm(eps, exponent=ex)
+            assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max()), (name, kw, ex)
+    for structure in ('scalar', 'layerwise'):
+        ref = R.Laplace(build_model(g), 'classification', subset_of_weights='all', hessian_structure='kron', backend=L.B200GGN)
+        ref.fit(loader_for(g))
+        ref.optimize_prior_precision(pred_type='nn', method='marglik', n_steps=25, lr=0.1, init_prior_prec=0.7,
+                                     prior_structure=structure)
+        la = StandIn(build_model(g), 'classification', backend=L.B200GGN)
+        la.fit(loader_for(g))
+        la.optimize_prior_precision(init_prior_prec=0.7, n_steps=25, lr=0.1, prior_structure=structure)
+        pa, pb = la.prior_precision.reshape(-1), ref.prior_precision.reshape(-1)
+        assert pa.shape == pb.shape and float((pa - pb).abs().max()) <= 1e-4 * float(pb.abs().max()), (structure, pa, pb)
+        close(la.log_marginal_likelihood(), ref.log_marginal_likelihood())
+print('ALGEBRA_OK')
+""" % (ROOT, ROOT)
+    out = subprocess.run([sys.executable, "-W", "ignore", "-c", code], capture_output=True, text=True, timeout=600)
+    assert "ALGEBRA_OK" in out.stdout, out.stderr[-3000:]
+
+
 def test_state_dict_round_trip_and_continual_fit_algebra(fake_ops):
     """Checkpoint / resume and fit(override=False) of the stand-in without the reference at hand: a loaded
     checkpoint reproduces the marglik bit for bit; two halves fitted in sequence give the factor algebra of
