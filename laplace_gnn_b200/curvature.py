@@ -155,7 +155,7 @@ class _Rows:
         self.hess_stats = None
 
     def gather(self, slab):
-        self.part.all_gather_slab(slab)
+        self.part.exchange_for_spmm(slab)
 
     def agree_min(self, value: int) -> int:
         """Collectives need the same column grouping on every rank."""
@@ -170,7 +170,7 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, syrk_stack_narrow=False, overlap_groups=False):
+                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, syrk_stack_narrow=False, overlap_groups=False, sparse_halo=False):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -232,6 +232,10 @@ class _B200KFAC:
         # so that the tensor-bound SYRK / GEMM of one group can run under the HBM-bound SpMM of the other.
         # An experiment for the first GPU pass of round 2 (whether the block scheduler co-schedules them): OFF
         self.overlap_groups = bool(overlap_groups)
+        # row-partitioned passes: when fewer than half of the other ranks' rows are referenced (a graph with
+        # locality, partitioned), exchange only those halo rows (all-to-all) instead of all-gathering whole slabs
+        # (dist.RowPartition.exchange_for_spmm).  OFF until the all-to-all has run over NCCL (gloo-tested)
+        self.sparse_halo = bool(sparse_halo)
         self.unit_row_limit = 4096
         # A_0 = X^T X does not depend on the weights: with cache_input_factor the raw Gram matrix of
         # this rank's feature rows is kept (per backend, or in a dict shared across backends by the
@@ -292,7 +296,7 @@ class _B200KFAC:
                     else:
                         torch.addmm(bs[l], h, Ws[l].t(), out=z)
                 with ops.timed("allgather", d_out, 4.0 * part.total_rows * d_out):
-                    part.all_gather_slab(slab)
+                    part.exchange_for_spmm(slab)          # whole slab, or the halo rows only when the halo is sparse
                 h = ops.spmm(part.ahat, slab, relu=(l < L - 1))
             if l < L - 1:
                 Hs.append(h)
@@ -324,6 +328,7 @@ class _B200KFAC:
             from .dist import RowPartition
             part = RowPartition.build(self.model.graph, self.process_group)
             cache[id(self.process_group)] = part
+        part.sparse_halo_below = 0.5 if self.sparse_halo else 0.0
         return part
 
     def _chain(self, lay, logits, idx, Hs, Ws, Wp, c0, gc, gq, buf_a, buf_b, G, hdr=None):
@@ -642,7 +647,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, syrk_stack_narrow=False, overlap_groups=False):
+                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, syrk_stack_narrow=False, overlap_groups=False, sparse_halo=False):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -653,7 +658,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
                          backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs,
-                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split, fused_hess_spmm, syrk_stack_narrow, overlap_groups)
+                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split, fused_hess_spmm, syrk_stack_narrow, overlap_groups, sparse_halo)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

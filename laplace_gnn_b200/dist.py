@@ -45,6 +45,11 @@ class RowPartition:
     ahat_t: CSR             # rows [lo, hi) of Â^T, columns in padded layout
     graph: object = None    # the full graph (for the lazily evaluated halo statistic)
     _halo_fraction: float | None = None
+    _halo_plan: dict | None = None
+    # below this fraction of the other ranks' rows the SpMM inputs travel as halo rows (all-to-all) instead of
+    # whole slabs (all-gather); a uniformly random graph sits at > 0.99, a partitioned mesh-like graph far below
+    # (0 = never: the switch of B200GGN(sparse_halo=True) sets 0.5)
+    sparse_halo_below: float = 0.0
 
     @property
     def halo_fraction(self) -> float:
@@ -96,6 +101,52 @@ class RowPartition:
         if not slab.is_cuda:           # gloo (CPU tests): no in-place guarantee
             mine = mine.clone()
         return dist.all_gather_into_tensor(flat.view(-1), mine.reshape(-1), group=self.pg, async_op=async_op)
+
+    # ---- halo-only exchange ------------------------------------------------------------
+    @property
+    def sparse_halo(self) -> bool:
+        return self.world > 1 and self.sparse_halo_below > 0.0 and self.halo_fraction < self.sparse_halo_below
+
+    def halo_plan(self) -> dict:
+        """Who sends which rows to whom, built once per (graph, group): this rank's halo = the columns its row
+        slices of Â and Â^T reference outside [lo, hi) (lgnn_halo_mark), grouped by owner; the lists are
+        exchanged so that every rank knows which of its own rows each peer needs."""
+        if self._halo_plan is not None:
+            return self._halo_plan
+        g, dev = self.graph, self.ahat.rowptr.device
+        need = ops.halo_columns(g.ahat, self.lo, self.hi)
+        if g.ahat_t is not g.ahat:
+            need = torch.unique(torch.cat([need, ops.halo_columns(g.ahat_t, self.lo, self.hi)]))
+        need = need.to(torch.int64)
+        bounds = torch.tensor(self.bounds, dtype=torch.int64, device=dev)
+        owner = torch.searchsorted(bounds, need, right=True) - 1
+        recv_counts = torch.bincount(owner, minlength=self.world)
+        send_counts = torch.empty_like(recv_counts)
+        dist.all_to_all_single(send_counts, recv_counts, group=self.pg)
+        rc, sc = recv_counts.tolist(), send_counts.tolist()
+        wanted = torch.empty(int(sum(sc)), dtype=torch.int64, device=dev)      # global ids peers want from me
+        dist.all_to_all_single(wanted, need.contiguous(), output_split_sizes=sc, input_split_sizes=rc, group=self.pg)
+        self._halo_plan = {
+            "send_rows": (wanted - self.lo + self.slot0).contiguous(),          # my rows, positions in the padded slab
+            "recv_rows": (owner * self.pad + (need - bounds[owner])).contiguous(),
+            "send_counts": sc, "recv_counts": rc}
+        return self._halo_plan
+
+    def exchange_for_spmm(self, slab: torch.Tensor):
+        """Make the rows this rank's SpMM reads present in the padded slab: the whole slab (all-gather) when the
+        halo is dense, only the halo rows (one all-to-all of row lists fixed at partition time) when it is
+        sparse.  Rows nobody reads stay whatever they were."""
+        if not self.sparse_halo:
+            return self.all_gather_slab(slab)
+        plan = self.halo_plan()
+        width = slab.shape[1]
+        send = slab.index_select(0, plan["send_rows"])
+        recv = torch.empty(int(sum(plan["recv_counts"])), width, dtype=slab.dtype, device=slab.device)
+        dist.all_to_all_single(recv.view(-1), send.view(-1),
+                               output_split_sizes=[c * width for c in plan["recv_counts"]],
+                               input_split_sizes=[c * width for c in plan["send_counts"]], group=self.pg)
+        slab.index_copy_(0, plan["recv_rows"], recv)
+        return None
 
     def compact(self, slab: torch.Tensor, width: int) -> torch.Tensor:
         """Padded [world*pad, width] -> natural node order [N, width]."""

@@ -173,3 +173,58 @@ def test_eigh_assignment_balances_cubic_cost():
     load = [sum(s ** 3 for s, o in zip(sizes, own) if o == r) for r in range(2)]
     assert abs(load[0] - load[1]) <= 100 ** 3 + 47 ** 3
     assert eigh_assignment(sizes, 1) == [0] * 6 and eigh_assignment([], 4) == []
+
+
+def _halo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import numpy as np
+        import fake_ops as F
+        import laplace_gnn_b200 as L
+        import laplace_gnn_b200.ops as ops
+        for n in F.ALL:
+            setattr(ops, n, getattr(F, n))
+        # a graph with locality: node i is linked to i+1 .. i+3 (directed) -> a contiguous row block reads only a
+        # few rows of its neighbours' blocks
+        n, C = 240, 5
+        src = np.repeat(np.arange(n - 3), 3)
+        dst = src + np.tile(np.arange(1, 4), n - 3)
+        graph = L.Graph.from_edge_index(torch.from_numpy(np.stack([src, dst]).astype(np.int64)), n)
+        gen = torch.Generator().manual_seed(3)
+        torch.manual_seed(3)
+        model = L.SparseGCN(7, 16, C, 3, torch.randn(n, 7, generator=gen), graph)
+        idx = torch.randperm(n, generator=gen)[:150].sort().values
+        y = torch.randint(0, C, (150,), generator=gen)
+        ref_loss, ref = L.B200GGN(model, "classification").kron(idx, y, N=150)
+        for mode in ("rows", "columns"):
+            be = L.B200GGN(model, "classification", process_group=dist.group.WORLD, backward_parallel=mode,
+                           sparse_halo=True, rhs_tile_bytes=60_000)
+            loss, kron = be.kron(idx, y, N=150)
+            part = be.last_stats["partition"]
+            assert part.sparse_halo and part.halo_fraction < 0.1
+            plan = part.halo_plan()
+            assert sum(plan["recv_counts"]) <= 6 and sum(plan["send_counts"]) <= 6      # 3 rows per neighbouring block
+            assert abs(float(loss) - float(ref_loss)) <= 1e-5 * abs(float(ref_loss))
+            for fa, fb in zip(kron.kfacs, ref.kfacs):
+                for a, b in zip(fa, fb):
+                    assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+        # the switch off: the same partition all-gathers whole slabs
+        be = L.B200GGN(model, "classification", process_group=dist.group.WORLD, backward_parallel="rows")
+        be.kron(idx, y, N=150)
+        assert not be.last_stats["partition"].sparse_halo
+        out[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sparse_halo_exchange_matches_the_single_rank_pass(world):
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_halo_worker, args=(world, port, out), nprocs=world, join=True)
+        assert len(out) == world
