@@ -679,6 +679,23 @@ def test_symeig_jitter_fallback_like_the_reference():
     assert float(((q * lam[None, :]) @ q.T - S).abs().max()) <= 1e-5 * float(S.abs().max())
 
 
+def test_saturated_softmax_stays_finite(fake_ops):
+    """A softmax probability that underflows to exactly 0: the reference's autograd through sqrt(p) returns all-NaN
+    G factors there and its symeig then exits the process; the closed form is the continuous
+    extension — finite factors, finite marglik, in both Hessian-sqrt modes."""
+    import laplace_gnn_b200 as L
+    g = Golden("tiny_undirected_2l")
+    model = build_model(g)
+    with torch.no_grad():
+        model.convs[-1].lin.weight.mul_(300.0)
+        assert float(torch.softmax(model(torch.from_numpy(g.idx)), 1).min()) == 0.0
+    for mode in ("reference", "ggn"):
+        la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs={"hess_sqrt": mode})
+        la.fit(loader_for(g))
+        assert all(bool(torch.isfinite(h).all()) for blk in la.H_facs.kfacs for h in blk)
+        assert bool(torch.isfinite(la.log_marginal_likelihood()))
+
+
 def test_all_lab_switches_compose(fake_ops):
     """Every opt-in path of DESIGN.md §6c at once (even column groups, hub split, on-the-fly output-layer SpMM,
     stacked narrow SYRK) through the Laplace driver: the marglik of the plain dense path."""
