@@ -54,6 +54,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=40)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--adjgrad", action="store_true",
+                    help="also compare d marglik / d adj: the reference's STEGCN + (-marglik).backward() against "
+                         "oracle/adj_grad_oracle.py (and the package's marglik_edge_grad with --package)")
     ap.add_argument("--package", action="store_true",
                     help="also run the package's host logic (B200GGN on the CPU test double, tests/fake_ops.py)")
     args = ap.parse_args()
@@ -113,6 +116,34 @@ def main():
                     assert float(np.abs(a.numpy() - b).max() / max(np.abs(b).max(), 1e-30)) <= 5e-5, (tag, "package factor")
             e_p = abs(float(pl.log_marginal_likelihood()) - ml) / max(abs(ml), 1e-30)
             assert e_p <= 1e-5, (tag, "package marglik", e_p)
+        if args.adjgrad and not c["symmetric"]:
+            from gnn.models.models import STEGCN
+            from oracle import adj_grad_oracle as AG
+            ste = STEGCN(c["F"], c["h"], c["C"], c["L"], torch.from_numpy(c["x"]),
+                         dense_adj_from_edges(c["ei"], c["n"]).clone(), dropout_p=0.5)
+            with torch.no_grad():
+                for l, conv in enumerate(ste.convs):
+                    conv.lin.weight.copy_(torch.from_numpy(Ws[l]))
+                    conv.lin.bias.copy_(torch.from_numpy(bs_[l]))
+            ste.eval()
+            ls = R.Laplace(ste, "classification", subset_of_weights="all", hessian_structure="kron")
+            ls.fit(DataLoader(TensorDataset(idx_t, y_t), batch_size=c["bs"], shuffle=False))
+            (-ls.log_marginal_likelihood()).backward()
+            ref_grad = -ste.adj.grad.detach().numpy().astype(np.float64)
+            A01 = AG.dense_adj01(c["ei"], c["n"])
+            ml64, grad = AG.marglik_adj_grad(A01, c["x"], Ws, bs_, c["idx"], c["y"], batch_size=c["bs"])
+            scale = max(np.abs(ref_grad).max(), 1e-30)
+            e_g = np.abs(grad - ref_grad).max() / scale
+            worst["adjgrad"] = max(worst.get("adjgrad", 0.0), float(e_g))
+            assert e_g <= 2e-4, (tag, "adj grad (oracle)", e_g)
+            if args.package:
+                from laplace_gnn_b200.structure import marglik_edge_grad
+                res = marglik_edge_grad(pm, idx_t, y_t, group=2,
+                                        batch_size=None if c["bs"] == len(c["idx"]) else c["bs"])
+                rr, cc = res.rows.numpy(), res.cols.numpy()
+                e_pg = np.abs(res.grad_edges.numpy() - ref_grad[rr, cc]).max() / scale
+                worst["adjgrad_package"] = max(worst.get("adjgrad_package", 0.0), float(e_pg))
+                assert e_pg <= 5e-4, (tag, "adj grad (package)", e_pg)
         print(tag, f"ok (marglik {ml:.5f})", flush=True)
     print("worst relative differences:", worst)
 
