@@ -199,3 +199,50 @@ def test_syrk_stacked_matches_fp64(k, ld, n):
     assert max_rel_err(out.cpu().numpy(), ref.cpu().numpy()) <= 1e-5
     ops.syrk_stacked(x, n, out)
     assert max_rel_err(out.cpu().numpy(), (2 * ref).cpu().numpy()) <= 1e-5
+
+
+# ---------------------------------------------------------------------------------- random small configurations
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_random_small_configurations_match_the_oracle(seed):
+    """The default backend on random small shapes (directed / symmetrised graphs, duplicate and self-loop edges,
+    isolated nodes, 1-4 layers, 2-9 classes, hidden widths 1-96 incl. multiples of 32, uneven batches, repeated
+    train nodes) against the oracle — the GPU leg of oracle/fuzz_against_reference.py.  Behind LGNN_LAB until its
+    first run on a B200; then it joins the default suite."""
+    import laplace_gnn_b200 as L
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(6, 400))
+    directed = bool(rng.integers(0, 2))
+    symmetric = bool(directed and rng.integers(0, 3) == 0)
+    e = int(rng.integers(0, 6 * n))
+    src, dst = rng.integers(0, n, e), rng.integers(0, n, e)
+    if not directed:
+        src, dst = np.concatenate([src, dst]), np.concatenate([dst, src])
+    if rng.integers(0, 2) and e > 0:
+        iso = rng.permutation(n)[: max(1, n // 8)]
+        keep = ~(np.isin(src, iso) | np.isin(dst, iso))
+        src, dst = src[keep], dst[keep]
+    ei = np.stack([src, dst]).astype(np.int64)
+    layers, C, F = int(rng.integers(1, 5)), int(rng.integers(2, 10)), int(rng.integers(1, 40))
+    h = int(rng.choice([1, 3, 8, 32, 33, 64, 96]))
+    m = int(rng.integers(1, n + 1))
+    idx = np.sort(rng.permutation(n)[:m]).astype(np.int64)
+    if rng.integers(0, 4) == 0 and m > 1:
+        idx = np.concatenate([idx, idx[:2]])
+    y = rng.integers(0, C, idx.shape[0]).astype(np.int64)
+    bs = int(idx.shape[0]) if rng.integers(0, 2) else int(rng.integers(1, idx.shape[0] + 1))
+    x = rng.standard_normal((n, F)).astype(np.float32)
+    graph = L.Graph.from_edge_index(torch.from_numpy(ei).to(DEV), n, symmetric=symmetric)
+    torch.manual_seed(seed)
+    model = L.SparseGCN(F, h, C, layers, torch.from_numpy(x).to(DEV), graph).to(DEV)
+    Ws = [c.lin.weight.detach().cpu().numpy() for c in model.convs]
+    bs_ = [c.lin.bias.detach().cpu().numpy() for c in model.convs]
+    from torch.utils.data import DataLoader, TensorDataset
+    la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs={"unit_min_width": 0})
+    la.fit(DataLoader(TensorDataset(torch.from_numpy(idx).to(DEV), torch.from_numpy(y).to(DEV)), batch_size=bs))
+    loss, kfacs, ml = O.fit_and_marglik(O.build_graph(ei, n, symmetric), x, Ws, bs_, idx, y, 1.0, "reference",
+                                        torch.float64, None if bs == len(idx) else bs)
+    for blk, ref_blk in zip(la.H_facs.kfacs, kfacs):
+        for a, b in zip(blk, ref_blk):
+            assert float((a.cpu().double() - b).abs().max()) <= 1e-4 * max(float(b.abs().max()), 1e-12)
+    assert abs(float(la.loss) - float(loss)) <= 1e-4 * abs(float(loss))
+    assert abs(float(la.log_marginal_likelihood()) - float(ml)) <= 1e-3 * abs(float(ml))
