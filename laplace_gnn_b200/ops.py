@@ -4,6 +4,7 @@ only serve as device-memory handles.  No CPU path exists here.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 
 import torch
@@ -49,15 +50,23 @@ def timed(kind: str, d: int = 0, work: float = 0.0):
     return _Timed(kind, d, work)
 
 
+# LGNN_NVTX=1: an NVTX range per launch group ("spmm_units d=4096", "syrk d=256", ...), so that ncu / nsys can
+# filter by stage (ncu --nvtx --nvtx-include "spmm_units d=4096/").  Off by default: no call is made.
+NVTX = os.environ.get("LGNN_NVTX") == "1"
+
+
 class _Timed:
     def __init__(self, kind: str, d: int, work: float):
         self.rec = None
+        self.nvtx = f"{kind} d={d}" if NVTX else None
         if PROFILE is not None:
             self.rec = {"kind": kind, "d": d, "bytes": work,
                         "start": torch.cuda.Event(enable_timing=True),
                         "end": torch.cuda.Event(enable_timing=True)}
 
     def __enter__(self):
+        if self.nvtx is not None:
+            torch.cuda.nvtx.range_push(self.nvtx)
         if self.rec is not None:
             self.rec["start"].record()
         return self
@@ -66,6 +75,8 @@ class _Timed:
         if self.rec is not None:
             self.rec["end"].record()
             PROFILE.append(self.rec)
+        if self.nvtx is not None:
+            torch.cuda.nvtx.range_pop()
         return False
 
 
