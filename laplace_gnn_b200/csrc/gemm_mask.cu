@@ -58,7 +58,21 @@ constexpr int GM_STG_WARP = 32 * GM_STG_PITCH; // per epilogue warp
 constexpr uint32_t GM_TMEM_COLS = 512;         // D: 2 x 64, A: 4 x 64
 constexpr uint32_t GM_TMEM_A0 = 128;
 
+// Ablation switches for the lab copy of this kernel (gemm_mask_lab.cu compiles this file a second time with
+// LGNN_GM_ABLATE defined and every global symbol renamed): which stage paces a tile?  In the product build GM_ABL
+// is the constant false and every guarded statement is what it was.
+//   1: the MMA thread issues no MMA (commits only)      2: only hi.hi of the three products is issued
+//   4: transform warps skip the tcgen05.st of hi / lo    8: epilogue skips the global stores
+#ifdef LGNN_GM_ABLATE
+#define GM_ABL(bit) ((P.ablate & (bit)) != 0)
+#else
+#define GM_ABL(bit) false
+#endif
+
 struct GmParams {
+#ifdef LGNN_GM_ABLATE
+  int ablate;
+#endif
   int64_t m_rows;
   int64_t tiles_total;
   int n_kb;          // k-blocks (K_pad / 32)
@@ -213,9 +227,11 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const uint64_t db_hi = make_smem_desc(bh + off, 0, 1024, 2);
             const uint64_t db_lo = make_smem_desc(bl + off, 0, 1024, 2);
             const uint32_t ca = (uint32_t)(ks * 8);    // 8 tf32 = 8 TMEM columns
-            tc_mma_tf32_ts(d, a_hi + ca, db_hi, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
-            tc_mma_tf32_ts(d, a_hi + ca, db_lo, idesc, 1u);
-            tc_mma_tf32_ts(d, a_lo + ca, db_hi, idesc, 1u);
+            if (!GM_ABL(1)) tc_mma_tf32_ts(d, a_hi + ca, db_hi, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
+            if (!GM_ABL(1) && !GM_ABL(2)) {
+              tc_mma_tf32_ts(d, a_hi + ca, db_lo, idesc, 1u);
+              tc_mma_tf32_ts(d, a_lo + ca, db_hi, idesc, 1u);
+            }
           }
           tc_commit(smem_u32(&ta_empty[s]));
         }
@@ -257,8 +273,10 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       mbar_wait(smem_u32(&ta_empty[ts]), tph ^ 1u);
       tc_fence_after();
       const uint32_t taddr = tmem_base + lane_addr + GM_TMEM_A0 + (uint32_t)(ts * 64);
-      tmem_st_x32(taddr, hi);
-      tmem_st_x32(taddr + 32, lo);
+      if (!GM_ABL(4)) {
+        tmem_st_x32(taddr, hi);
+        tmem_st_x32(taddr + 32, lo);
+      }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
@@ -350,7 +368,7 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             o.y = (kb4 & 2u) ? o.y : 0.f;
             o.z = (kb4 & 4u) ? o.z : 0.f;
             o.w = (kb4 & 8u) ? o.w : 0.f;
-            if (row < P.m_rows) *reinterpret_cast<float4*>(P.out + row * P.ldo + n0 + 16 * p + 4 * sub_c) = o;
+            if (row < P.m_rows && !GM_ABL(8)) *reinterpret_cast<float4*>(P.out + row * P.ldo + n0 + 16 * p + 4 * sub_c) = o;
           }
           __syncwarp();
         }
@@ -434,6 +452,9 @@ int lgnn_gemm_mask_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, c
   cudaStream_t st = as_stream(stream);
   const int k_pad = (int)lgnn_gemm_mask_kpad(k);
   GmParams P;
+#ifdef LGNN_GM_ABLATE
+  P.ablate = LGNN_GM_ABLATE_VALUE;
+#endif
   P.m_rows = m_rows;
   P.tiles_total = (m_rows + GM_BM - 1) / GM_BM;
   P.n_kb = k_pad / GM_BK;

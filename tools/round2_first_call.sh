@@ -15,6 +15,8 @@ LGNN_LAB=1 run r2_tests_lab 600 python -m pytest tests/test_gpu_lab.py -q
 tail -15 gpurun_out/r2_tests_lab.log | cut -c1-220
 run r2_units_lab 300 python tools/units_lab.py 6 8 10 12
 cat gpurun_out/r2_units_lab.log | cut -c1-260
+run r2_gemm_lab 200 python tools/gemm_lab.py
+tail -9 gpurun_out/r2_gemm_lab.log | cut -c1-200
 run r2_hess_spmm_lab 200 python tools/hess_spmm_lab.py 16 8 6
 cat gpurun_out/r2_hess_spmm_lab.log | cut -c1-260
 B="python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline"
