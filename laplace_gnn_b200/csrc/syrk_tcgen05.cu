@@ -80,7 +80,20 @@ static TcGeom tc_geom(int n) {
   return g;
 }
 
+// Ablation switches for the lab copy of this kernel (syrk_tcgen05_lab.cu compiles this file a second time with
+// LGNN_TC_ABLATE defined and the global symbols renamed).  In the product build TC_ABL is the constant false.
+//   1: no MMA issued (commits only)   2: only hi.hi of the three products   4: transform warps skip their
+//   shared-memory stores of hi / lo   8: epilogue skips the red.global adds
+#ifdef LGNN_TC_ABLATE
+#define TC_ABL(bit) ((P.ablate & (bit)) != 0)
+#else
+#define TC_ABL(bit) false
+#endif
+
 struct TcParams {
+#ifdef LGNN_TC_ABLATE
+  int ablate;
+#endif
   int n, np, mb, lbo, op_bytes, raw_bytes, tmem_cols;
   int seg_steps;     // steps per TMEM accumulation segment
   int64_t steps_total;
@@ -176,18 +189,22 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
           {  // M block 0: rows 0..127 x columns 0..np-1
             const uint64_t a_hi = make_smem_desc(hi + koff, lbo, sbo);
             const uint64_t a_lo = make_smem_desc(lo + koff, lbo, sbo);
-            tc_mma_tf32(tmem_base, a_hi, a_hi, idesc0, acc);
-            tc_mma_tf32(tmem_base, a_hi, a_lo, idesc0, 1u);
-            tc_mma_tf32(tmem_base, a_lo, a_hi, idesc0, 1u);
+            if (!TC_ABL(1)) tc_mma_tf32(tmem_base, a_hi, a_hi, idesc0, acc);
+            if (!TC_ABL(1) && !TC_ABL(2)) {
+              tc_mma_tf32(tmem_base, a_hi, a_lo, idesc0, 1u);
+              tc_mma_tf32(tmem_base, a_lo, a_hi, idesc0, 1u);
+            }
           }
           if (P.mb == 2) {  // M block 1: rows 128..255 x columns 128..np-1 (128 rows = 16 groups)
             const uint32_t off = koff + 16u * TC_SBO;
             const uint64_t a_hi = make_smem_desc(hi + off, lbo, sbo);
             const uint64_t a_lo = make_smem_desc(lo + off, lbo, sbo);
             const uint32_t d = tmem_base + (uint32_t)P.np;
-            tc_mma_tf32(d, a_hi, a_hi, idesc1, acc);
-            tc_mma_tf32(d, a_hi, a_lo, idesc1, 1u);
-            tc_mma_tf32(d, a_lo, a_hi, idesc1, 1u);
+            if (!TC_ABL(1)) tc_mma_tf32(d, a_hi, a_hi, idesc1, acc);
+            if (!TC_ABL(1) && !TC_ABL(2)) {
+              tc_mma_tf32(d, a_hi, a_lo, idesc1, 1u);
+              tc_mma_tf32(d, a_lo, a_hi, idesc1, 1u);
+            }
           }
         }
         tc_commit(smem_u32(&empty_op[st]));  // implies fence::before_thread_sync
@@ -232,8 +249,10 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
           l.y = v[j][1] - h.y;
           l.z = v[j][2] - h.z;
           l.w = v[j][3] - h.w;
-          *reinterpret_cast<float4*>(hi + off) = h;
-          *reinterpret_cast<float4*>(lo + off) = l;
+          if (!TC_ABL(4)) {
+            *reinterpret_cast<float4*>(hi + off) = h;
+            *reinterpret_cast<float4*>(lo + off) = l;
+          }
         }
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor-core (async) proxy
@@ -272,7 +291,7 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
           asm volatile("" : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]),
                             "+r"(v[7]), "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]),
                             "+r"(v[13]), "+r"(v[14]), "+r"(v[15]));
-          if (live) {
+          if (live && !TC_ABL(8)) {
             float* dst = out + (size_t)row * P.np + c0;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
@@ -346,6 +365,9 @@ int syrk_tcgen05_launch(const float* x, int64_t ldx, int64_t k_rows, int n, floa
   if (r != CUDA_SUCCESS) return fail(LGNN_E_CUDA, "syrk_tcgen05: cuTensorMapEncodeTiled failed (%d)", (int)r);
 
   TcParams P;
+#ifdef LGNN_TC_ABLATE
+  P.ablate = LGNN_TC_ABLATE_VALUE;
+#endif
   P.n = n; P.np = g.np; P.mb = g.mb; P.lbo = g.lbo; P.op_bytes = g.op_bytes; P.raw_bytes = g.raw_bytes;
   P.tmem_cols = g.tmem_cols;
   P.seg_steps = TC_SEG_STEPS_DEFAULT;

@@ -17,6 +17,8 @@ run r2_units_lab 300 python tools/units_lab.py 6 8 10 12
 cat gpurun_out/r2_units_lab.log | cut -c1-260
 run r2_gemm_lab 200 python tools/gemm_lab.py
 tail -9 gpurun_out/r2_gemm_lab.log | cut -c1-200
+run r2_syrk_lab 200 python tools/syrk_lab.py --n 256 --dist randn --impl tcgen05
+tail -9 gpurun_out/r2_syrk_lab.log | cut -c1-200
 run r2_hess_spmm_lab 200 python tools/hess_spmm_lab.py 16 8 6
 cat gpurun_out/r2_hess_spmm_lab.log | cut -c1-260
 B="python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline"
