@@ -60,6 +60,9 @@ def main():
     ap.add_argument("--ggn", action="store_true",
                     help="compare hess_sqrt='ggn' against the reference run with upstream curvlinops' detach restored "
                          "(the wrapper of oracle/make_golden_ggn.py) instead of the fork's mode")
+    ap.add_argument("--predictive", action="store_true",
+                    help="also compare posterior_precision.bmm(eps, -1/2), pinned samples and the MC predictive "
+                         "(la(idx, pred_type='nn', link_approx='mc')) with the oracle (and the package with --package)")
     ap.add_argument("--diag", action="store_true",
                     help="also compare the exact diagonal GGN (reference DiagLaplace) against oracle.diag_ggn")
     ap.add_argument("--package", action="store_true",
@@ -129,6 +132,33 @@ def main():
                     assert float(np.abs(a.numpy() - b).max() / max(np.abs(b).max(), 1e-30)) <= 5e-5, (tag, "package factor")
             e_p = abs(float(pl.log_marginal_likelihood()) - ml) / max(abs(ml), 1e-30)
             assert e_p <= 1e-5, (tag, "package marglik", e_p)
+        if args.predictive:
+            S = 5
+            eps = torch.randn(S, la.n_params, generator=torch.Generator().manual_seed(case))
+            ref_bmm = la.posterior_precision.bmm(eps, exponent=-0.5).detach()
+            ref_samples = (la.mean.reshape(1, -1) + ref_bmm).detach()
+            eval_idx = torch.from_numpy(np.sort(rng.permutation(c["n"])[: max(1, c["n"] // 3)]).astype(np.int64))
+            orig_sample = la.sample
+            la.sample = lambda n_samples=S, generator=None: ref_samples          # pin the draws
+            with torch.no_grad():
+                ref_py = la(eval_idx, pred_type="nn", link_approx="mc", n_samples=S).detach().numpy()
+            la.sample = orig_sample
+            kf = [[h.detach() for h in blk] for blk in la.H_facs.kfacs]
+            o_bmm = O.kron_bmm(kf, eps, -0.5, 1.0)
+            e_b = float((o_bmm - ref_bmm).abs().max() / ref_bmm.abs().max())
+            shapes = [w.shape for w in Ws]
+            o_py = O.mc_predictive(G, c["x"], ref_samples.numpy(), shapes, eval_idx.numpy())
+            e_y = float(np.abs(o_py.numpy() - ref_py).max() / np.abs(ref_py).max())
+            worst["bmm"], worst["mc_predictive"] = max(worst.get("bmm", 0.0), e_b), max(worst.get("mc_predictive", 0.0), e_y)
+            assert e_b <= 2e-4 and e_y <= 2e-5, (tag, "predictive", e_b, e_y)
+            if args.package:
+                p_bmm = pl.posterior_precision.bmm(eps, exponent=-0.5)
+                e_pb = float((p_bmm - ref_bmm).abs().max() / ref_bmm.abs().max())
+                p_py = pl(eval_idx, pred_type="nn", link_approx="mc", samples=ref_samples)
+                e_py = float(np.abs(p_py.numpy() - ref_py).max() / np.abs(ref_py).max())
+                worst["bmm_package"] = max(worst.get("bmm_package", 0.0), e_pb)
+                worst["mc_predictive_package"] = max(worst.get("mc_predictive_package", 0.0), e_py)
+                assert e_pb <= 5e-4 and e_py <= 2e-5, (tag, "predictive (package)", e_pb, e_py)
         if args.diag and c["n"] <= 24:
             ld = R.Laplace(model, "classification", subset_of_weights="all", hessian_structure="diag")
             ld.fit(DataLoader(TensorDataset(idx_t, y_t), batch_size=len(c["idx"]), shuffle=False))
