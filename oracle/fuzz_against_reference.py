@@ -26,7 +26,7 @@ from oracle import ref_loader  # noqa: E402
 from oracle.make_golden import dense_adj_from_edges  # noqa: E402
 
 
-def random_case(rng):
+def random_case(rng, wide=False):
     n = int(rng.integers(6, 40))
     directed = bool(rng.integers(0, 2))
     symmetric = bool(directed and rng.integers(0, 3) == 0)
@@ -40,6 +40,8 @@ def random_case(rng):
         src, dst = src[keep], dst[keep]
     ei = np.stack([src, dst]).astype(np.int64)
     L, C, h, F = int(rng.integers(1, 5)), int(rng.integers(2, 10)), int(rng.integers(1, 9)), int(rng.integers(1, 7))
+    if wide:                                        # hidden widths the unit-compacted slabs take (multiples of 32)
+        h, C = int(rng.choice([32, 64, 96])), int(rng.integers(2, 20))
     m = int(rng.integers(1, n + 1))
     idx = np.sort(rng.permutation(n)[:m]).astype(np.int64)
     if rng.integers(0, 4) == 0 and m > 1:
@@ -60,6 +62,7 @@ def main():
     ap.add_argument("--ggn", action="store_true",
                     help="compare hess_sqrt='ggn' against the reference run with upstream curvlinops' detach restored "
                          "(the wrapper of oracle/make_golden_ggn.py) instead of the fork's mode")
+    ap.add_argument("--wide", action="store_true", help="hidden widths 32 / 64 / 96 and up to 19 classes")
     ap.add_argument("--predictive", action="store_true",
                     help="also compare posterior_precision.bmm(eps, -1/2), pinned samples and the MC predictive "
                          "(la(idx, pred_type='nn', link_approx='mc')) with the oracle (and the package with --package)")
@@ -87,7 +90,7 @@ def main():
         K.loss_hessian_matrix_sqrt = lambda out, tgt, lf: original(out.detach(), tgt, lf)
         mode = "ggn"
     for case in range(args.cases):
-        c = random_case(rng)
+        c = random_case(rng, args.wide)
         torch.manual_seed(case)
         model = R.GCN(c["F"], c["h"], c["C"], c["L"], torch.from_numpy(c["x"]), dense_adj_from_edges(c["ei"], c["n"]),
                       dropout_p=0.5, symmetric=c["symmetric"])
