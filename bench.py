@@ -61,7 +61,7 @@ def parse_args():
     ap.add_argument("--shard-eigh", action="store_true",
                     help="lab, multi-GPU: spread the factor eigendecompositions over the ranks (kron.Kron.decompose)")
     ap.add_argument("--rhs-tile-gb", type=float, default=None,
-                    help="HBM budget of the two multi-RHS slabs (sizes the column groups; default: 40 %% of HBM)")
+                    help="HBM budget of the two multi-RHS slabs (sizes the column groups; default: 45 %% of HBM)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-div", type=int, default=16,
