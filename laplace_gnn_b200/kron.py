@@ -44,6 +44,23 @@ def _eigh_psd(m: torch.Tensor):
     return torch.nan_to_num(lam.clamp(min=0.0)), torch.nan_to_num(q)
 
 
+def _eigh_cached(h: torch.Tensor):
+    """``_eigh_psd(h)``, except for a factor the backend marked as ``scale * raw`` with ``raw`` held in a cache that
+    outlives the fit (``_eig_of``: the weight-independent input factor A_0 = X^T X / N with
+    ``cache_input_factor``): the raw matrix is decomposed once, later fits scale its eigenvalues."""
+    tag = getattr(h, "_eig_of", None)
+    if tag is None:
+        return _eigh_psd(h)
+    cache, key, scale = tag
+    if key not in cache:                      # the backend replaced its cache entry: decompose what we were given
+        return _eigh_psd(h)
+    ek = ("eig",) + tuple(key)
+    if ek not in cache:
+        cache[ek] = _eigh_psd(cache[key])
+    lam, q = cache[ek]
+    return lam * scale, q
+
+
 def eigh_assignment(sizes: Sequence[int], world: int) -> list[int]:
     """Owner rank of each factor: largest first onto the least-loaded rank (cost ~ n^3), ties to the lower
     rank — a pure function of the sizes, so every rank computes the same table."""
@@ -149,7 +166,7 @@ class Kron:
         if world > 1 and len(distinct) > 1:
             pairs = _sharded_eigh(distinct, process_group)
         else:
-            pairs = [_eigh_psd(h) for h in distinct]
+            pairs = [_eigh_cached(h) for h in distinct]
         vecs, vals = [], []
         for f in self.kfacs:
             vals.append([pairs[owner_of[id(h)]][0] for h in f])

@@ -696,6 +696,49 @@ def test_saturated_softmax_stays_finite(fake_ops):
         assert bool(torch.isfinite(la.log_marginal_likelihood()))
 
 
+def test_cached_input_factor_is_decomposed_once(fake_ops):
+    """cache_input_factor: A_0 = X^T X / N is weight-independent; its eigendecomposition is computed once per
+    feature matrix and rescaled in later fits (a second fit with changed weights and a different batch size runs
+    one eigh fewer), with the marglik of the uncached path."""
+    import laplace_gnn_b200 as L
+    import laplace_gnn_b200.kron as K
+    g = Golden("tiny_directed_3l")
+    model = build_model(g)
+    idx, y = torch.from_numpy(g.idx), torch.from_numpy(g.y)
+    calls = {"n": 0}
+    real = K._eigh
+
+    def counting(m):
+        calls["n"] += 1
+        return real(m)
+    K._eigh = counting
+    try:
+        shared = {}
+        kw = {"cache_input_factor": True, "_shared_cache": shared}
+        la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs=kw)
+        la.fit(L.TensorBatchLoader(idx, y))
+        first = calls["n"]
+        ml1 = float(la.log_marginal_likelihood())
+        with torch.no_grad():
+            for p in model.parameters():
+                p.mul_(1.1)
+        calls["n"] = 0
+        la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs=kw)
+        la.fit(L.TensorBatchLoader(idx[:-3], y[:-3]))
+        assert calls["n"] == first - 1                      # A_0's decomposition came from the cache
+        ml2 = float(la.log_marginal_likelihood())
+        plain = L.Laplace(model, "classification", backend=L.B200GGN)
+        plain.fit(L.TensorBatchLoader(idx[:-3], y[:-3]))
+        assert abs(ml2 - float(plain.log_marginal_likelihood())) <= 1e-6 * abs(ml2) and ml1 != ml2
+        # a multi-batch fit sums factors: the mark is gone, the plain decomposition runs
+        calls["n"] = 0
+        la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs=kw)
+        la.fit(torch.utils.data.DataLoader(torch.utils.data.TensorDataset(idx, y), batch_size=7))
+        assert calls["n"] == first + g.L                    # summed blocks carry no marks: 3 L plain decompositions
+    finally:
+        K._eigh = real
+
+
 def test_all_lab_switches_compose(fake_ops):
     """Every opt-in path of DESIGN.md §6c at once (even column groups, hub split, on-the-fly output-layer SpMM,
     stacked narrow SYRK) through the Laplace driver: the marglik of the plain dense path."""
