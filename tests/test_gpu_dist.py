@@ -71,3 +71,80 @@ def test_nccl_partitioned_fit_matches_single_gpu():
         out = m.dict()
         mp.spawn(_worker, args=(world, _free_port(), out), nprocs=world, join=True)
         assert len(out) == world
+
+
+def _lab_worker(rank, world, port, out):
+    """The multi-GPU switches that have not run over NCCL yet: eigendecompositions spread over the
+    ranks, even column groups in the column-parallel backward, halo-only exchange on a graph with locality."""
+    import numpy as np
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import laplace_gnn_b200 as L
+
+        def fit(model, idx, y, **kw):
+            la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs=kw)
+            la.fit(L.TensorBatchLoader(idx, y))
+            return la, float(la.log_marginal_likelihood())
+
+        def same(la, ref, tag):
+            for blk, rblk in zip(la.H_facs.kfacs, ref.H_facs.kfacs):
+                for a, b in zip(blk, rblk):
+                    assert float((a - b).abs().max() / b.abs().max()) <= 2e-5, tag
+
+        # (1) uniform graph, 10 classes on 2 ranks = 5 columns each: even groups (6) + sharded eigh
+        n, u, f, c, h, layers = 40_000, 300_000, 64, 10, 128, 3
+        gen = torch.Generator(device=dev).manual_seed(0)
+        src = torch.randint(0, n, (u,), device=dev, generator=gen)
+        dst = torch.randint(0, n, (u,), device=dev, generator=gen)
+        ei = torch.stack([torch.cat([src, dst]), torch.cat([dst, src])])
+        X = torch.randn(n, f, device=dev, generator=gen)
+        idx = torch.randperm(n, device=dev, generator=gen)[: int(0.6 * n)].sort().values
+        y = torch.randint(0, c, (idx.numel(),), device=dev, generator=gen)
+        torch.manual_seed(0)
+        model = L.SparseGCN(f, h, c, layers, X, L.Graph.from_edge_index(ei, n)).to(dev)
+        ref, ref_ml = fit(model, idx, y)
+        la, ml = fit(model, idx, y, process_group=dist.group.WORLD, backward_parallel="columns", shard_eigh=True,
+                     unit_even_groups=True)
+        same(la, ref, "even groups + sharded eigh")
+        assert abs(ml - ref_ml) <= 1e-5 * abs(ref_ml)
+        if world == 2:
+            assert la.backend.last_stats["group"] == 6
+        # every rank holds bit-identical eigenpairs
+        flat = torch.cat([t.reshape(-1) for blk in la.H.eigenvalues for t in blk])
+        gathered = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(gathered, flat)
+        assert all(torch.equal(gathered[0], t) for t in gathered)
+        # (2) banded graph: halo-only exchange in both layouts
+        n2 = 60_000
+        s2 = torch.arange(n2 - 3, device=dev).repeat_interleave(3)
+        d2 = s2 + torch.arange(1, 4, device=dev).repeat(n2 - 3)
+        X2 = torch.randn(n2, f, device=dev, generator=gen)
+        torch.manual_seed(1)
+        model2 = L.SparseGCN(f, h, c, layers, X2, L.Graph.from_edge_index(torch.stack([s2, d2]), n2)).to(dev)
+        idx2 = torch.randperm(n2, device=dev, generator=gen)[: int(0.6 * n2)].sort().values
+        y2 = torch.randint(0, c, (idx2.numel(),), device=dev, generator=gen)
+        ref2, ref2_ml = fit(model2, idx2, y2)
+        for mode in ("rows", "columns"):
+            la2, ml2 = fit(model2, idx2, y2, process_group=dist.group.WORLD, backward_parallel=mode, sparse_halo=True)
+            assert la2.backend.last_stats["partition"].sparse_halo
+            same(la2, ref2, f"sparse halo {mode}")
+            assert abs(ml2 - ref2_ml) <= 1e-5 * abs(ref2_ml)
+        out[rank] = ref_ml
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.skipif(os.environ.get("LGNN_LAB") != "1", reason="lab paths, not on the default path: set LGNN_LAB=1 to run")
+def test_nccl_lab_switches_match_single_gpu():
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_lab_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert len(out) == world

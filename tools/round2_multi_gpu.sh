@@ -5,6 +5,9 @@ set -u
 N=${1:-8}
 mkdir -p gpurun_out
 P=29540
+S=$(date +%s)
+LGNN_LAB=1 timeout 600 python -m pytest tests/test_gpu_dist.py -x -q > gpurun_out/r2_n${N}_tests.log 2>&1; echo "multi-GPU tests (incl. lab switches over NCCL) rc=$? in $(( $(date +%s) - S )) s"
+tail -3 gpurun_out/r2_n${N}_tests.log | cut -c1-200
 for flags in "" "--shard-eigh" "--unit-even-groups --shard-eigh" "--unit-even-groups --shard-eigh --fused-hess-spmm"; do
   tag=$(echo "base $flags" | tr -d '-' | tr ' ' '_')
   S=$(date +%s)
