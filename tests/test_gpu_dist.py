@@ -109,7 +109,7 @@ def _lab_worker(rank, world, port, out):
         model = L.SparseGCN(f, h, c, layers, X, L.Graph.from_edge_index(ei, n)).to(dev)
         ref, ref_ml = fit(model, idx, y)
         la, ml = fit(model, idx, y, process_group=dist.group.WORLD, backward_parallel="columns", shard_eigh=True,
-                     unit_even_groups=True)
+                     unit_even_groups=True, unit_min_width=0)
         same(la, ref, "even groups + sharded eigh")
         assert abs(ml - ref_ml) <= 1e-5 * abs(ref_ml)
         if world == 2:
