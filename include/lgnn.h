@@ -137,21 +137,6 @@ int lgnn_spmm_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr, const int3
                   const float* val, const float* x, int64_t ldx, float* y, int64_t ldy, int64_t d,
                   int flags, lgnn_stream_t stream);
 
-/* Zero-compressed slabs.  The right-hand sides below the output layer, delta = (gZ W) * relu'(H), are
- * about half exact zeros; the SpMM that gathers them is HBM-bound, so they are stored compressed
- * (per row: 128-element bitmask blocks, block prefix counts, the non-zeros; see spmm_packed.cu) and
- * the gather moves only len[r] bytes of row r.  d <= 4096.
- *   lgnn_pack_rows_pitch   bytes per packed row slot for width d (the caller allocates n_rows * pitch)
- *   lgnn_pack_rows_f32     X [n_rows, ldx] dense (first d columns) -> packed, len[n_rows] (int32 bytes)
- *   lgnn_spmm_packed_f32   Y[i, 0:d] = sum_k val[k] * unpack(packed row col[k]); same summation order as
- *                          lgnn_spmm_f32 on the dense slab, hence bit-identical; flags: LGNN_SPMM_NO_HUB_ROWS */
-int64_t lgnn_pack_rows_pitch(int64_t d);
-int lgnn_pack_rows_f32(const float* x, int64_t ldx, int64_t n_rows, int64_t d, void* packed, int32_t* len,
-                       lgnn_stream_t stream);
-int lgnn_spmm_packed_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr, const int32_t* col,
-                         const float* val, const void* packed, const int32_t* len, int64_t d, float* y,
-                         int64_t ldy, int flags, lgnn_stream_t stream);
-
 /* Unit-compacted slabs.  delta[n, c, u] = (gZ W)[n, c, u] * 1[H[n, u] > 0] (curvlinops/kfac.py:653-661
  * through the relu of gnn/models/base_gnn.py:150): the g Hessian-sqrt columns of a node share ONE zero
  * pattern, that of the node's hidden units.  The slab row [g][h] of node n is rewritten in place as

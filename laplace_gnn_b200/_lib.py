@@ -37,9 +37,6 @@ PROTOTYPES = {
     "lgnn_halo_mark": (C.c_int, [_vp, _vp, _i64, _i64, _vp, _vp]),
     "lgnn_csr_slice_remap": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "lgnn_spmm_f32": (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, C.c_int, _vp]),
-    "lgnn_pack_rows_pitch": (_i64, [_i64]),
-    "lgnn_pack_rows_f32": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
-    "lgnn_spmm_packed_f32": (C.c_int, [_i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, C.c_int, _vp]),
     "lgnn_unit_slabs_supported": (C.c_int, [_i64, _i64]),
     "lgnn_unit_pack_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "lgnn_spmm_units_f32": (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, C.c_int, _vp]),
@@ -102,7 +99,21 @@ def ptr(t: torch.Tensor | None) -> int | None:
     if not t.is_cuda:
         raise LgnnError("lgnn kernels take CUDA tensors only (there is no CPU fallback); got a "
                         f"{t.device} tensor")
+    if t.device.index != torch.cuda.current_device():
+        # stream() is the current stream of the CURRENT device: launching there with another device's pointers
+        # is an invalid launch at best.  The package's entry points (B200GGN.kron / diag, GCNConvFunction,
+        # Graph.from_edge_index) switch to their tensors' device themselves (on_device_of); direct callers of
+        # ops.* must do the same.
+        raise LgnnError(f"tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}; "
+                        "wrap the call in `with torch.cuda.device(tensor.device):`")
     return t.data_ptr()
+
+
+def on_device_of(t: torch.Tensor):
+    """Context manager making ``t``'s device the current CUDA device (no-op for CPU tensors: the CPU double of
+    the tests drives the same host code)."""
+    import contextlib
+    return torch.cuda.device(t.device) if t.is_cuda else contextlib.nullcontext()
 
 
 def stream() -> int:

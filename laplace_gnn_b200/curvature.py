@@ -198,12 +198,6 @@ class _B200KFAC:
         self.overlap = bool(overlap)
         self.fused_gemm = bool(fused_gemm)
         self.skip_zero_rows = True
-        # zero-compress the relu-masked slabs below the output layer (csrc/spmm_packed.cu).  Correct and
-        # bit-identical, but OFF by default: per-element bitmask decoding in the SpMM consumer costs more
-        # than the halved gather saves (products, d = 3840: 594 ms against 286 ms dense;
-        # profiles/r1g_pack_lab.txt)
-        self.pack_slabs = False
-        self.pack_min_width = 1024
         # unit-compacted slabs below the output layer (csrc/spmm_units.cu): the relu' mask is shared by all
         # columns of a node, so the slab rows keep only their live hidden units and the SpMM gathers about
         # half the bytes.  Column groups are then padded to a multiple of 4 with all-zero right-hand sides.
@@ -268,6 +262,7 @@ class _B200KFAC:
             h = h[part.lo:part.hi]
         Hs = [h]
         L = len(Ws)
+        self._fwd_out = []          # row-partitioned forward: the padded slabs holding this rank's P_l / H_l rows
         for l in range(L):
             d_out = Ws[l].shape[0]
             if part is None:
@@ -288,16 +283,27 @@ class _B200KFAC:
                 out = _slab(h.device, 1000 + l, 1, n_rows * ldz).view(n_rows, ldz)
                 h = ops.spmm(g.ahat, z, relu=(l < L - 1), out=out)[:, :d_out]
             else:
-                slab = torch.empty(part.total_rows, d_out, dtype=torch.float32, device=h.device)
+                # row block of this rank: Z_l goes straight into this rank's slot of the padded all-gather slab,
+                # P_l / H_l into its slot of a second one (the column-parallel backward all-gathers that one in
+                # place).  Both persistent, like the single-device pair above.
+                ldz = (d_out + 3) // 4 * 4
+                slab = _slab(h.device, 1100 + l, 0, part.total_rows * ldz).view(part.total_rows, ldz)
                 z = slab[part.slot0:part.slot0 + part.n_local]
                 with ops.timed("gemm_fwd", d_out, 2.0 * h.shape[0] * Ws[l].numel()):
-                    if bs[l] is None:
-                        torch.mm(h, Ws[l].t(), out=z)
+                    if ldz == d_out:
+                        if bs[l] is None:
+                            torch.mm(h, Ws[l].t(), out=z)
+                        else:
+                            torch.addmm(bs[l], h, Ws[l].t(), out=z)
                     else:
-                        torch.addmm(bs[l], h, Ws[l].t(), out=z)
-                with ops.timed("allgather", d_out, 4.0 * part.total_rows * d_out):
+                        z[:, :d_out] = torch.mm(h, Ws[l].t()) if bs[l] is None else torch.addmm(bs[l], h, Ws[l].t())
+                        z[:, d_out:] = 0
+                with ops.timed("allgather", d_out, 4.0 * part.total_rows * ldz):
                     part.exchange_for_spmm(slab)          # whole slab, or the halo rows only when the halo is sparse
-                h = ops.spmm(part.ahat, slab, relu=(l < L - 1))
+                out_slab = _slab(h.device, 1100 + l, 1, part.total_rows * ldz).view(part.total_rows, ldz)
+                self._fwd_out.append(out_slab)
+                h = ops.spmm(part.ahat, slab, relu=(l < L - 1),
+                             out=out_slab[part.slot0:part.slot0 + part.n_local])[:, :d_out]
             if l < L - 1:
                 Hs.append(h)
         return Hs, h
@@ -341,7 +347,8 @@ class _B200KFAC:
         delta = (gZ W) ⊙ relu' is about half zeros, in a pattern the columns of a node share: when every
         row is local (single GPU, or the column-parallel backward) it is compacted in place to the live
         units of each node (``ops.unit_pack``, which applies the mask itself) and the SpMM gathers only
-        those (``ops.spmm_units``).  ``pack_slabs`` is the older per-element compression (off)."""
+        those (``ops.spmm_units``).  (A per-element compression of the same slabs was 2x slower than the dense
+        gather — profiles/r1g_pack_lab.txt — and has left the tree.)"""
         L = len(Ws)
         C = logits.shape[1]
         dims = [w.shape[0] for w in Ws]                 # d_1 .. d_L (d_L = C)
@@ -356,7 +363,7 @@ class _B200KFAC:
                 delta.zero_()
                 ops.hess_rhs(logits, idx, c0, gc, delta, c_pad, self.hess_sqrt)
         width, ld = C, c_pad
-        packed = units = None
+        units = None
         for l in range(L - 1, -1, -1):
             gz = Q[: n_loc * gq * ld].view(n_loc, gq * ld)
             if units is not None and lay.split_t is not None:
@@ -368,8 +375,6 @@ class _B200KFAC:
             elif units is not None:
                 ops.spmm_units(lay.csr_t, units, out=gz)
                 self._n_unit_spmm += 1
-            elif packed is not None:
-                ops.spmm_packed(lay.csr_t, packed, out=gz)
             elif l == L - 1 and on_the_fly:
                 # output layer, right-hand sides rebuilt per edge from the nodes' softmax statistics: no slab
                 ops.spmm_hess(lay.csr_t_top if lay.csr_t_top is not None else lay.csr_t, lay.hess_stats, C, c0, gc,
@@ -401,12 +406,7 @@ class _B200KFAC:
                         with ops.timed("relu_mask", d_prev, 2.0 * n_loc * gq * d_prev * 4):
                             ops.relu_mask_mul(nxt, act, gq)
                 width, ld = d_prev, d_prev
-                packed = units = None
-                if to_units:
-                    units = ops.unit_pack(slab, Hs[l], gq, hdr=hdr)
-                elif self._can_pack(lay, gq * d_prev):
-                    packed = ops.pack_rows(slab, gq * d_prev, out=Q.view(torch.uint8))   # gZ in Q is dead
-                    P, Q = Q, P            # the packed slab is the next input, the dense one the next output
+                units = ops.unit_pack(slab, Hs[l], gq, hdr=hdr) if to_units else None
             yield
 
     def _units_possible(self, lay) -> bool:
@@ -419,11 +419,6 @@ class _B200KFAC:
     def _can_unit(self, lay, g: int, h: int) -> bool:
         return (self._units_possible(lay) and g * h >= self.unit_min_width and
                 ops.unit_slabs_supported(g, h))
-
-    def _can_pack(self, lay, width: int) -> bool:
-        # narrow slabs stay dense: the ring kernel needs multi-KB copies to reach the HBM roofline
-        return (self.pack_slabs and not lay.communicates and width % 4 == 0 and
-                self.pack_min_width <= width <= ops.PACK_MAX_WIDTH and lay.csr_t.val.is_cuda)
 
     def _backward_columns(self, lay, logits, idx, Hs, Ws, cols, G):
         """Multi-RHS KFAC backward for the Hessian-sqrt columns ``cols = (first, count)`` on the
@@ -441,17 +436,13 @@ class _B200KFAC:
         lanes = 2 if ((self.overlap and lay.communicates and dev.type == "cuda") or self.overlap_groups) else 1
         room = self._group_size(lanes * n_in, lanes * n_loc, dmax, 1 << 30, dev)   # columns the HBM budget allows
         grp = min(room, C)
-        hidden = max(dims[:-1]) if len(dims) > 1 else 0
-        can_pack = self.pack_slabs and not lay.communicates and dev.type == "cuda" and 0 < hidden <= ops.PACK_MAX_WIDTH
-        if can_pack:                       # keep the hidden-layer slabs narrow enough for the packed SpMM
-            grp = min(grp, max(1, ops.PACK_MAX_WIDTH // hidden))
         grp = lay.agree_min(max(1, min(grp, (c_count + lanes - 1) // lanes)))
         # unit-compacted slabs want groups of 4, 8, 12 or 16 columns (any even count with unit_even_groups):
         # the last group of a pass is padded with all-zero right-hand sides (47 classes -> 16 + 16 + 15(+1))
         q = 2 if self.unit_even_groups else 4
         per_lane = (max(c_count, 1) + lanes - 1) // lanes         # = c_count with one group in flight
         cand = min(room // q * q, 16, (per_lane + q - 1) // q * q)
-        pad4 = (self._units_possible(lay) and not can_pack and cand >= q and
+        pad4 = (self._units_possible(lay) and cand >= q and
                 any(self._can_unit(lay, cand, h) for h in dims[:-1]))
         if pad4:
             grp = cand
@@ -467,12 +458,10 @@ class _B200KFAC:
                        for l in range(1, len(Ws))]
         lanes = min(lanes, len(groups))
         n_split = lay.split_t.n_extra if (pad4 and lay.split_t is not None) else 0
-        # two slabs per lane, alternating as SpMM input / output; a packed slab needs its header on top
+        # two slabs per lane, alternating as SpMM input / output
         row_floats = grp * dmax
-        if can_pack:
-            row_floats = max(row_floats, (ops.pack_rows_pitch(grp * hidden) + 3) // 4)
         bufs = [(_slab(dev, i, 0, n_in * row_floats),
-                 _slab(dev, i, 1, max(n_in if can_pack else n_loc + n_split, 1) * row_floats))
+                 _slab(dev, i, 1, max(n_loc + n_split, 1) * row_floats))
                 for i in range(lanes)]
         if lanes == 1:
             for c0, gc in groups:
@@ -514,7 +503,13 @@ class _B200KFAC:
     def kron(self, x: torch.Tensor, y: torch.Tensor, N: int, **kwargs):
         """(loss, Kron) for the batch of train-node indices ``x`` with labels ``y``; ``N`` is the
         size of the whole training set (curvature.py:236-265).  With a ``process_group`` every rank
-        passes the same (x, y) and receives the same (all-reduced) result."""
+        passes the same (x, y) and receives the same (all-reduced) result.  Runs on the MODEL's device,
+        whichever device is current in the calling thread."""
+        from ._lib import on_device_of
+        with on_device_of(self.model.X):
+            return self._kron(x, y, N, **kwargs)
+
+    def _kron(self, x: torch.Tensor, y: torch.Tensor, N: int, **kwargs):
         model = self.model
         g = model.graph
         Ws, bs = self._layers()
@@ -586,14 +581,16 @@ class _B200KFAC:
             grp, n_groups = self._backward_columns(_Rows(part), logits, idx_loc, Hs, Ws, (0, C), G)
         else:                                                  # "columns": full graph, own columns
             from .dist import column_share
+            # every rank needs H_l (relu' masks) and the logits of ALL nodes: in-place all-gather of the padded
+            # slabs the forward wrote its rows into, then into natural node order — persistent buffers, no
+            # allocation per fit
             full_H, full_logits = [self.model.X.float().contiguous()], None
-            for t_loc in Hs[1:] + [logits]:
-                w = t_loc.shape[1]
-                slab = torch.empty(part.total_rows, w, dtype=torch.float32, device=dev)
-                slab[part.slot0:part.slot0 + part.n_local] = t_loc
-                with ops.timed("allgather", w, 4.0 * part.total_rows * w):
+            for l, t_loc in enumerate(Hs[1:] + [logits]):
+                w, slab = t_loc.shape[1], self._fwd_out[l]
+                ldz = slab.shape[1]
+                with ops.timed("allgather", w, 4.0 * part.total_rows * ldz):
                     part.all_gather_slab(slab)
-                full = part.compact(slab, w)
+                full = part.compact(slab, ldz, out=_slab(dev, 1100 + l, 2, g.n * ldz).view(g.n, ldz))[:, :w]
                 if t_loc is logits:
                     full_logits = full
                 else:
@@ -636,11 +633,12 @@ class _B200KFAC:
         ``diag_mode="node_factorised"``: an APPROXIMATION for graphs where that is infeasible:
         sum_c (gZ_c ∘ gZ_c)^T (H ∘ H), one multi-RHS backward like ``kron``; exact when no edge couples
         two nodes."""
-        if self.diag_mode == "node_factorised":
-            from .diag import diag_ggn_node_factorised
-            return diag_ggn_node_factorised(self, x, y)
-        from .diag import diag_ggn_exact
-        return diag_ggn_exact(self, x, y)
+        from ._lib import on_device_of
+        from .diag import diag_ggn_exact, diag_ggn_node_factorised
+        with on_device_of(self.model.X):
+            if self.diag_mode == "node_factorised":
+                return diag_ggn_node_factorised(self, x, y)
+            return diag_ggn_exact(self, x, y)
 
 
 def make_backend(base: type, name: str = "B200GGN") -> type:

@@ -148,10 +148,11 @@ class RowPartition:
         slab.index_copy_(0, plan["recv_rows"], recv)
         return None
 
-    def compact(self, slab: torch.Tensor, width: int) -> torch.Tensor:
-        """Padded [world*pad, width] -> natural node order [N, width]."""
+    def compact(self, slab: torch.Tensor, width: int, out: torch.Tensor | None = None) -> torch.Tensor:
+        """Padded [world*pad, width] -> natural node order [N, width] (into ``out`` when given)."""
         v = slab.view(self.world, self.pad, width)
-        return torch.cat([v[r, : self.bounds[r + 1] - self.bounds[r]] for r in range(self.world)], dim=0)
+        pieces = [v[r, : self.bounds[r + 1] - self.bounds[r]] for r in range(self.world)]
+        return torch.cat(pieces, dim=0) if out is None else torch.cat(pieces, dim=0, out=out)
 
     def all_reduce_sum(self, tensors) -> None:
         """One all-reduce over the concatenation of same-dtype tensors (written back in place)."""

@@ -15,6 +15,7 @@ import torch
 from torch import nn
 
 from . import ops
+from ._lib import on_device_of
 from .graph import Graph
 
 
@@ -25,11 +26,13 @@ class GCNConvFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z: torch.Tensor, graph: Graph) -> torch.Tensor:
         ctx.graph = graph
-        return ops.spmm(graph.ahat, z.contiguous())
+        with on_device_of(z):
+            return ops.spmm(graph.ahat, z.contiguous())
 
     @staticmethod
     def backward(ctx, grad_out: torch.Tensor):
-        return ops.spmm(ctx.graph.ahat_t, grad_out.contiguous()), None
+        with on_device_of(grad_out):
+            return ops.spmm(ctx.graph.ahat_t, grad_out.contiguous()), None
 
 
 class SparseGCNConv(nn.Module):

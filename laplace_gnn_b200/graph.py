@@ -43,6 +43,12 @@ class Graph:
         assume_undirected=True declares that the edge list already contains both directions, so
         Â^T = Â and one CSR serves both (halves graph memory); it is not verified.
         """
+        from ._lib import on_device_of
+        with on_device_of(edge_index):
+            return cls._build(edge_index, num_nodes, symmetric, assume_undirected)
+
+    @classmethod
+    def _build(cls, edge_index, num_nodes, symmetric, assume_undirected) -> "Graph":
         a = ops.csr_from_edge_index(edge_index, num_nodes, symmetric)      # pattern of A  == Â^T
         deg, dis = ops.degree_norm(a)
         a.val = ops.edge_values(a, dis)
@@ -142,7 +148,21 @@ def save_graph(graph: Graph, path: str) -> None:
 
 
 def load_graph(path: str, device) -> Graph:
-    z = torch.load(path, map_location="cpu", weights_only=False)
+    # the payload save_graph writes is dicts / tensors / ints / bools / None only: no pickled code is accepted
+    z = torch.load(path, map_location="cpu", weights_only=True)
+    if not isinstance(z, dict) or not {"n", "deg", "dis", "ahat", "ahat_t", "symmetric_pattern", "meta"} <= set(z):
+        raise ValueError(f"{path}: not a graph cache written by save_graph")
+    for name, dt in (("deg", torch.int64), ("dis", torch.float32)):
+        if not isinstance(z[name], torch.Tensor) or z[name].dtype != dt or z[name].numel() != z["n"]:
+            raise ValueError(f"{path}: field {name!r} has the wrong type or length")
+    for name in ("ahat", "ahat_t"):
+        d = z[name]
+        if d is None and name == "ahat_t":
+            continue
+        if (not isinstance(d, dict) or d["rowptr"].dtype != torch.int64 or d["col"].dtype != torch.int32 or
+                d["rowptr"].numel() != d["n_rows"] + 1 or int(d["rowptr"][-1]) != d["col"].numel() or
+                (d["val"] is not None and (d["val"].dtype != torch.float32 or d["val"].numel() != d["col"].numel()))):
+            raise ValueError(f"{path}: field {name!r} is not a consistent CSR")
 
     def unpack(d):
         return CSR(d["n_rows"], d["n_cols"], d["rowptr"].to(device), d["col"].to(device),

@@ -271,6 +271,16 @@ class _ParametricLaplaceLite:
                  backend=None, backend_kwargs: dict | None = None, **unused):
         if likelihood != "classification":
             raise NotImplementedError("the GCN Laplace hot path is classification only")
+        # reference keywords that would change the result must not be swallowed: only their neutral values pass
+        # (baselaplace.py:94-107: sigma_noise=1, enable_backprop=False; KronLaplace :1520-1540: damping=False)
+        neutral = {"sigma_noise": (1, 1.0), "enable_backprop": (False,), "damping": (False,),
+                   "dict_key_x": ("input_ids",), "dict_key_y": ("labels",), "asdl_fisher_kwargs": (None,)}
+        for key, val in unused.items():
+            if key not in neutral:
+                raise TypeError(f"{type(self).__name__}: unexpected keyword argument {key!r}")
+            if not any(val is ok or val == ok for ok in neutral[key]):
+                raise NotImplementedError(f"{type(self).__name__}: {key}={val!r} is outside the hot path this stand-in "
+                                          "restates; drive B200GGN from the reference's laplace package for it")
         if backend is None:
             from .curvature import B200GGN
             backend = B200GGN

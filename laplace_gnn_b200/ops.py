@@ -24,16 +24,21 @@ class CSR:
     val: torch.Tensor | None = None
     max_row_nnz: int | None = None     # longest row, if known (graph build): lets SpMM skip its hub passes
     masked: bool = False               # some edge values were zeroed on purpose (their gathers are skipped)
-    _nnz_live: int | None = None
+    _nnz_live: torch.Tensor | None = None   # 0-d device count of the live edges (profiling only)
 
-    @property
-    def nnz_gathered(self) -> int:
-        """Non-zeros whose source row is actually read (profiling only: one host sync when masked)."""
+    def nnz_gathered_dev(self) -> torch.Tensor | int:
+        """Non-zeros whose source row is actually read — as an 8-byte DEVICE scalar when masked (enqueued, no
+        host sync), so that a profile record never has to hold the matrix to count them later."""
         if not self.masked:
             return self.nnz
         if self._nnz_live is None:
-            self._nnz_live = int(torch.count_nonzero(self.val))
+            self._nnz_live = torch.count_nonzero(self.val)
         return self._nnz_live
+
+    @property
+    def nnz_gathered(self) -> int:
+        """Host value of the above (one sync when masked; profiling / tests only)."""
+        return int(self.nnz_gathered_dev())
 
     @property
     def nnz(self) -> int:
@@ -41,8 +46,45 @@ class CSR:
 
 
 # bench.py sets PROFILE = [] to collect one record per SpMM / SYRK launch: CUDA events on the
-# launching stream plus the algorithmic bytes (SpMM) or flops (SYRK) of that launch.
+# launching stream plus the algorithmic bytes (SpMM) or flops (SYRK) of that launch.  A record holds NUMBERS
+# only — python scalars, or 0-d device tensors where the count needs a reduction on the device (live edges of a
+# masked matrix, live units gathered by the unit SpMM): a record that kept the slab, the activations or the masked
+# edge values alive pinned ~5.7 GB of HBM per timed step (round-1 scaling runs at 2 and 4 GPUs ran out of memory).
 PROFILE: list | None = None
+_LIVE_GATHER: dict = {}     # (activation ptr, shape, col ptr) -> 0-d int64: sum over edges of the source's live units
+
+
+def profile_begin() -> None:
+    global PROFILE
+    PROFILE = []
+
+
+def profile_end() -> list:
+    """Stop recording; returns the records with every count turned into a python number."""
+    global PROFILE
+    recs, PROFILE = PROFILE or [], None
+    for r in recs:
+        r["bytes"] = _number(r["bytes"])
+    _LIVE_GATHER.clear()
+    return recs
+
+
+def _number(w):
+    if callable(w):
+        w = w()
+    return float(w.item()) if isinstance(w, torch.Tensor) else float(w)
+
+
+def live_gather_sum(act: torch.Tensor, h: int, col: torch.Tensor) -> torch.Tensor:
+    """sum_e k[col[e]], k[j] = live units of node j — the unit SpMM's gathered slots per column, as a 0-d device
+    tensor.  Profiling only; cached per (activation buffer, matrix): the column groups of a pass and — with the
+    activations in the persistent workspace — the steps of a bench run share one evaluation."""
+    key = (act.data_ptr(), tuple(act.shape), h, col.data_ptr(), col.numel())
+    t = _LIVE_GATHER.get(key)
+    if t is None:
+        k = (act[:, :h] > 0).sum(1)
+        t = _LIVE_GATHER[key] = k[col.to(torch.int64)].sum()
+    return t
 
 
 def timed(kind: str, d: int = 0, work: float = 0.0):
@@ -207,75 +249,17 @@ def spmm(a: CSR, x: torch.Tensor, relu: bool = False, out: torch.Tensor | None =
     _f32c(out, "out")
     if out.shape[0] < a.n_rows or out.shape[1] < d:
         raise ValueError("spmm: out too small")
-    # masked edges still stream their (col, val) but pull no source row; counting them needs a host
-    # sync, so the record carries a thunk that bench.py evaluates after the timed region
-    work = (lambda: spmm_algorithmic_bytes(a.n_rows, a.nnz_gathered, d) + (a.nnz - a.nnz_gathered) * 8) \
-        if a.masked else spmm_algorithmic_bytes(a.n_rows, a.nnz, d)
+    # masked edges still stream their (col, val) but pull no source row: nnz*8 + rowptr + output + live*d*4,
+    # the live count a device scalar (no sync here, no reference to the matrix in the record)
+    work = spmm_algorithmic_bytes(a.n_rows, a.nnz, d)
+    if a.masked and PROFILE is not None:
+        work = spmm_algorithmic_bytes(a.n_rows, 0, d) + a.nnz * 8 + a.nnz_gathered_dev() * (d * 4)
     with _Timed("spmm", d, work):
         check(lib.lgnn_spmm_f32(a.n_rows, a.nnz, ptr(a.rowptr), ptr(a.col), ptr(a.val), ptr(x), x.stride(0),
                                 ptr(out), out.stride(0), d,
                                 (_lib.SPMM_RELU if relu else _lib.SPMM_NONE) | _SPMM_IMPL[impl] |
                                 (_lib.SPMM_NO_HUB_ROWS if a.max_row_nnz is not None and a.max_row_nnz <= 4096 else 0),
                                 stream()), "lgnn_spmm_f32")
-    _lib.count_launches(1)
-    return out
-
-
-# ------------------------------------------------------------------------------ zero-compressed slabs
-PACK_MAX_WIDTH = 4096
-
-
-@dataclass
-class PackedRows:
-    """Slab [n_rows, d] with its zeros squeezed out (csrc/spmm_packed.cu): ``data`` holds one slot of
-    ``pitch`` bytes per row, of which the SpMM reads the first ``len[r]``."""
-    n_rows: int
-    d: int
-    pitch: int
-    data: torch.Tensor      # uint8 [>= n_rows * pitch]
-    len: torch.Tensor       # int32 [n_rows]
-
-
-def pack_rows_pitch(d: int) -> int:
-    return int(_lib.load().lgnn_pack_rows_pitch(int(d)))
-
-
-def pack_rows(x: torch.Tensor, d: int | None = None, out: torch.Tensor | None = None) -> PackedRows:
-    """Compress the first d columns of x (row-major fp32).  ``out``: optional uint8 byte buffer."""
-    lib = _lib.load()
-    _f32c(x, "x")
-    d = int(x.shape[1]) if d is None else int(d)
-    n = int(x.shape[0])
-    pitch = pack_rows_pitch(d)
-    if out is None:
-        out = torch.empty(max(n * pitch, 16), dtype=torch.uint8, device=x.device)
-    if out.dtype != torch.uint8 or out.numel() < n * pitch:
-        raise ValueError("pack_rows: out must be a uint8 buffer of at least n_rows * pitch bytes")
-    ln = torch.empty(max(n, 1), dtype=torch.int32, device=x.device)[:n]
-    with _Timed("pack", d, float(n) * d * 4):
-        check(lib.lgnn_pack_rows_f32(ptr(x), x.stride(0), n, d, ptr(out), ptr(ln), stream()), "lgnn_pack_rows_f32")
-    _lib.count_launches(1)
-    return PackedRows(n, d, pitch, out, ln)
-
-
-def spmm_packed(a: CSR, pr: PackedRows, out: torch.Tensor | None = None) -> torch.Tensor:
-    """Y = A @ unpack(pr); bit-identical to ``spmm(a, dense)``."""
-    lib = _lib.load()
-    if pr.n_rows < a.n_cols:
-        raise ValueError("spmm_packed: fewer packed rows than matrix columns")
-    if out is None:
-        out = torch.empty(a.n_rows, pr.d, dtype=torch.float32, device=pr.data.device)
-    _f32c(out, "out")
-    if out.shape[0] < a.n_rows or out.shape[1] < pr.d:
-        raise ValueError("spmm_packed: out too small")
-    # bytes: (col, val, len) per edge, rowptr, the live part of every gathered row, the dense output
-    work = lambda: (a.nnz * 12 + (a.n_rows + 1) * 8 + int(pr.len.to(torch.int64)[a.col.to(torch.int64)].sum())
-                    + a.n_rows * pr.d * 4)
-    with _Timed("spmm_packed", pr.d, work):
-        check(lib.lgnn_spmm_packed_f32(a.n_rows, a.nnz, ptr(a.rowptr), ptr(a.col), ptr(a.val), ptr(pr.data),
-                                       ptr(pr.len), pr.d, ptr(out), out.stride(0),
-                                       _lib.SPMM_NO_HUB_ROWS if a.max_row_nnz is not None and a.max_row_nnz <= 4096 else 0,
-                                       stream()), "lgnn_spmm_packed_f32")
     _lib.count_launches(1)
     return out
 
@@ -338,8 +322,9 @@ def spmm_units(a: CSR, us: UnitSlab, out: torch.Tensor | None = None, variant: i
     # bytes actually asked of HBM: (col, val) + one header row per edge, rowptr, the live units of every
     # gathered row, the dense output
     nblk = us.h // 32
-    work = lambda: (a.nnz * (8 + 8 * nblk) + (a.n_rows + 1) * 8 + a.n_rows * d * 4
-                    + int(us.live_units()[a.col.to(torch.int64)].sum()) * us.g * 4)
+    work = a.nnz * (8 + 8 * nblk) + (a.n_rows + 1) * 8 + a.n_rows * d * 4
+    if PROFILE is not None and us.act is not None:
+        work = work + live_gather_sum(us.act, us.h, a.col) * (us.g * 4)
     with _Timed("spmm_units", d, work) as rec:
         check(lib.lgnn_spmm_units_f32(a.n_rows, us.n_rows, a.nnz, ptr(a.rowptr), ptr(a.col), ptr(a.val), ptr(us.slab),
                                       us.slab.stride(0), ptr(us.hdr), us.g, us.h, ptr(out), out.stride(0),
@@ -461,8 +446,9 @@ def spmm_hess(a: CSR, stats: torch.Tensor, C: int, c0: int, ncols: int, width: i
     # bytes asked of HBM: (col, val), rowptr, per gathered edge P and Q (2 Cp floats) and the group's A, S, V,
     # the output; the same launch priced as the materialised slab goes into dense_bytes
     per_edge = (2 * cp + 3 * int(ncols)) * 4
-    work = (lambda: a.nnz * 8 + (a.n_rows + 1) * 8 + a.nnz_gathered * per_edge + a.n_rows * d * 4) \
-        if a.masked else (a.nnz * 8 + (a.n_rows + 1) * 8 + a.nnz * per_edge + a.n_rows * d * 4)
+    work = a.nnz * 8 + (a.n_rows + 1) * 8 + a.n_rows * d * 4
+    if PROFILE is not None:
+        work = work + a.nnz_gathered_dev() * per_edge
     with _Timed("spmm_hess", d, work):
         check(lib.lgnn_spmm_hess_f32(a.n_rows, a.nnz, ptr(a.rowptr), ptr(a.col), ptr(a.val), ptr(stats),
                                      stats.stride(0), int(C), int(c0), int(ncols), int(width), ptr(out),

@@ -144,18 +144,6 @@ def csr_with_masked_sources(a, keep):
     return CSR(a.n_rows, a.n_cols, a.rowptr, a.col, val, a.max_row_nnz, masked=True)
 
 
-PACK_MAX_WIDTH = 4096
-
-
-def pack_rows_pitch(d):
-    nblk = (d + 127) // 128
-    return nblk * 16 + (nblk * 4 + 15) // 16 * 16 + nblk * 512
-
-
-def pack_rows(x, d=None, out=None):
-    raise AssertionError("the CPU double never packs (B200GGN packs on CUDA devices only)")
-
-
 def unit_slabs_supported(g, h):
     return 2 <= g <= 16 and g % 2 == 0 and 32 <= h <= 1024 and h % 32 == 0
 
@@ -194,5 +182,5 @@ def gemm_mask_supported(k, n):
     return False          # the CPU double keeps the two-step path (torch.mm + relu_mask_mul)
 
 
-ALL = ["syrk_stacked", "spmm_hess_supported", "hess_stats", "spmm_hess", "sddmm", "unit_slabs_supported", "unit_pack", "spmm_units", "gemm_mask_supported", "pack_rows_pitch", "pack_rows", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
+ALL = ["syrk_stacked", "spmm_hess_supported", "hess_stats", "spmm_hess", "sddmm", "unit_slabs_supported", "unit_pack", "spmm_units", "gemm_mask_supported", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
        "halo_columns", "csr_slice_remap", "spmm", "softmax_ce_sum", "hess_rhs", "relu_mask_mul", "syrk"]

@@ -495,57 +495,6 @@ def test_masked_output_layer_spmm_changes_nothing():
     assert torch.equal(masked.val, ref)
 
 
-# ---------------------------------------------------------------------------------- zero-compressed slabs
-@pytest.mark.parametrize("d", [4, 100, 192, 256, 1000, 2048, 3840, 4096])
-@pytest.mark.parametrize("density", [0.0, 0.5, 1.0])
-def test_packed_spmm_is_bit_identical_to_dense(d, density):
-    """pack_rows + spmm_packed against the dense SpMM of the same slab: identical bits (same summation
-    order), for empty, half-full and full rows, widths that end inside a mask block, hub rows."""
-    ops = _ops()
-    n = 6000
-    rng = np.random.Generator(np.random.PCG64(d))
-    base = O.synthetic_edges(n, 30_000, seed=d)
-    star = np.stack([np.zeros(20_000, np.int64), rng.integers(0, n, 20_000)])          # a hub beyond the CTA budget
-    ei = np.concatenate([base, star, star[::-1]], axis=1)
-    G = _dev_graph(ei, n)
-    gen = torch.Generator(device=DEV).manual_seed(d)
-    ld = d + 8
-    x = torch.randn(n, ld, device=DEV, generator=gen)
-    x[:, :d] *= (torch.rand(n, d, device=DEV, generator=gen) < density)
-    x[17] = 0                                                      # an all-zero row
-    pr = ops.pack_rows(x, d)
-    nnz_row = (x[:, :d] != 0).sum(1)
-    nblk = (d + 127) // 128
-    header = nblk * 16 + (nblk * 4 + 15) // 16 * 16
-    assert torch.equal(pr.len.long(), header + (nnz_row * 4 + 15) // 16 * 16)
-    assert pr.pitch == ops.pack_rows_pitch(d) == header + nblk * 512
-    dense = ops.spmm(G.ahat, x, d=d, impl="ldg")
-    y = ops.spmm_packed(G.ahat, pr)
-    hub = int(torch.argmax(G.deg))
-    rows = torch.tensor([r for r in range(n) if r != hub], device=DEV)
-    assert torch.equal(y[rows], dense[rows])                       # plain-store rows: same bits
-    assert float((y[hub] - dense[hub]).abs().max()) <= 1e-4 * max(1.0, float(dense[hub].abs().max()))
-
-
-def test_packed_backward_gives_the_same_factors():
-    import laplace_gnn_b200 as L
-    g = Golden("pubmed_shape")
-    model = build_model(g, DEV)
-    idx, y = torch.from_numpy(g.idx).to(DEV), torch.from_numpy(g.y).to(DEV)
-    be1 = L.B200GGN(model, "classification")
-    be1.pack_slabs = True
-    be1.pack_min_width = 0                                         # pack even the 192-wide slabs of this shape
-    be2 = L.B200GGN(model, "classification")
-    be2.pack_slabs = False
-    l1, k1 = be1.kron(idx, y, N=len(y))
-    l2, k2 = be2.kron(idx, y, N=len(y))
-    assert float(l1) == float(l2)
-    for fa, fb in zip(k1.kfacs, k2.kfacs):
-        for a, b in zip(fa, fb):
-            assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-6
-    check_against_golden(g, l1, k1.kfacs, torch.tensor(g.marglik))
-
-
 # ---------------------------------------------------------------------------------- unit-compacted slabs
 def _masked_slab(n, g, h, density, seed, pitch_extra=0):
     gen = torch.Generator(device=DEV).manual_seed(seed)

@@ -28,10 +28,10 @@ for name in sys.argv[1:] or ["pubmed", "arxiv"]:
         for _ in range(reps): out = fn()
         torch.cuda.synchronize(); return (time.perf_counter() - t0) / reps, out
     t_fit, ml = timed(fit)
-    ops.PROFILE = []
+    ops.profile_begin()
     t_grad, res = timed(lambda: marglik_edge_grad(model, idx, y), reps=1)
     kinds = {}
-    for rec in ops.PROFILE:
+    for rec in list(ops.PROFILE):
         kinds[rec["kind"]] = kinds.get(rec["kind"], 0.0) + rec["start"].elapsed_time(rec["end"])
     ops.PROFILE = None
     print(f"{name}: n={n} nnz={graph.nnz} fit+marglik {1e3 * t_fit:8.1f} ms | marglik + d/dA on {graph.nnz} entries {1e3 * t_grad:8.1f} ms "

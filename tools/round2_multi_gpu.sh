@@ -12,7 +12,7 @@ for flags in "" "--shard-eigh" "--unit-even-groups --shard-eigh" "--unit-even-gr
   tag=$(echo "base $flags" | tr -d '-' | tr ' ' '_')
   S=$(date +%s)
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P \
-      bench.py --gpus $N --steps 3 --warmup 3 --no-e2e $flags > gpurun_out/r2_n${N}_$tag.log 2>gpurun_out/r2_n${N}_$tag.err
+      bench.py --gpus $N --steps 3 --warmup 3 --no-e2e --no-parity $flags > gpurun_out/r2_n${N}_$tag.log 2>gpurun_out/r2_n${N}_$tag.err
   echo "N=$N [$flags] rc=$? in $(( $(date +%s) - S )) s"
   python - "gpurun_out/r2_n${N}_$tag.log" <<'PY'
 import json, sys
