@@ -50,14 +50,10 @@ def parse_args():
     ap.add_argument("--no-overlap", action="store_true", help="rows layout: one column group in flight instead of two")
     ap.add_argument("--no-fused-gemm", action="store_true", help="cuBLAS fp32 GEMM + mask kernel instead of the fused tcgen05 kernel")
     ap.add_argument("--dense-slabs", action="store_true", help="keep the slabs below the output layer dense (no unit compaction)")
-    ap.add_argument("--unit-even-groups", action="store_true",
-                    help="lab: column groups of any even width (csrc/spmm_units_even.cu) instead of multiples of 4")
+    ap.add_argument("--no-unit-even-groups", action="store_true",
+                    help="column groups padded to multiples of 4 (round-1 behaviour) instead of any even width")
     ap.add_argument("--fused-hess-spmm", action="store_true",
                     help="lab: output-layer SpMM with its Hessian-sqrt right-hand sides rebuilt per edge (csrc/spmm_hess.cu)")
-    ap.add_argument("--syrk-stack-narrow", action="store_true",
-                    help="lab: output-layer G through the wide view of the slab (ops.syrk_stacked)")
-    ap.add_argument("--overlap-groups", action="store_true",
-                    help="lab: two column groups in flight on two streams (SYRK / GEMM of one under the SpMM of the other)")
     ap.add_argument("--shard-eigh", action="store_true",
                     help="lab, multi-GPU: spread the factor eigendecompositions over the ranks (kron.Kron.decompose)")
     ap.add_argument("--rhs-tile-gb", type=float, default=None,
@@ -266,9 +262,8 @@ def main():
     if args.no_e2e:
         del edge_index
     bk = {"hess_sqrt": args.hess_sqrt, "syrk_impl": args.syrk, "fused_gemm": not args.no_fused_gemm,
-          "unit_slabs": not args.dense_slabs, "unit_even_groups": args.unit_even_groups,
-          "fused_hess_spmm": args.fused_hess_spmm, "syrk_stack_narrow": args.syrk_stack_narrow,
-          "overlap_groups": args.overlap_groups}
+          "unit_slabs": not args.dense_slabs, "unit_even_groups": not args.no_unit_even_groups,
+          "fused_hess_spmm": args.fused_hess_spmm}
     if args.rhs_tile_gb is not None:
         bk["rhs_tile_bytes"] = int(args.rhs_tile_gb * 1e9)
     if pg is not None:
@@ -531,7 +526,7 @@ def main():
                    "nodes": n, "nnz": nnz, "features": f, "classes": c, "train_nodes": int(idx.numel()),
                    "hess_sqrt": args.hess_sqrt, "syrk": args.syrk, "scale": args.scale,
                    "slabs": "dense" if args.dense_slabs else "unit-compacted below the output layer" +
-                   (", even column groups" if args.unit_even_groups else ""),
+                   ("" if args.no_unit_even_groups else ", even column groups"),
                    "l2": "inputs (>= 10 GB per SpMM) far exceed the 126 MB L2; no explicit flush",
                    "parallelism": "single GPU" if world == 1 else
                    f"row-partitioned x{world} (halo all-gather), backward over {args.backward_parallel}"},

@@ -68,24 +68,33 @@ __device__ __forceinline__ void fma2(float2& a, float v, const float2& x) {
   a.y = fmaf(v, x.y, a.y);
 }
 
-// The structure of spmm_units_staged_kernel (spmm_units.cu): a group of nblk warps owns `rpg` consecutive rows,
+// The structure of spmm_units_staged_kernel (spmm_units.cu): a group of warps owns `rpg` consecutive rows,
 // walks their (col, val) run in batches of 32 with the next batch's headers and the one after's (col, val) in
 // flight, and copies every neighbour's run into a per-warp ring of U slots with cp.async.
-template <int G2, int U, int MINB>
+//
+// NB = unit blocks per warp (1 or 2).  The cost of one (warp, neighbour) iteration — shuffles, the copy issue,
+// the wait, two warp syncs — does not depend on g, so narrow groups move few bytes per iteration: at g = 6 a
+// warp's run is 16 live units x 24 bytes = 384 bytes and the kernel reached 0.67 of the copy rate against 0.88
+// at g = 12 (profiles/r2a_units_lab.txt).  With NB = 2 a lane owns the units 32(2w) + L and 32(2w+1) + L: the
+// runs of two consecutive blocks are adjacent in the row (block 2w+1 starts where block 2w's slots, rounded up
+// to even, end), so the warp copies ONE run of twice the length per neighbour and reads both header words
+// with one 16-byte load — g = 6 then moves what g = 12 moves per iteration.
+template <int G2, int NB, int U, int MINB>
 __global__ void __launch_bounds__(EVEN_THREADS, MINB) spmm_units_even_kernel(
     int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
     const float* __restrict__ val, const float* __restrict__ slab, int64_t lds, const uint2* __restrict__ hdr,
     int nblk, float* __restrict__ y, int64_t ldy, int rpg) {
   extern __shared__ __align__(16) uint8_t units_even_smem_[];
-  constexpr int SLOT = 256 * G2;                       // bytes: 32 live units x g floats
-  constexpr int PIECES = (16 * G2 + 31) / 32;          // 16-byte pieces per lane for a full run
+  constexpr int SLOT = 256 * G2 * NB;                  // bytes: NB x 32 live units x g floats
+  constexpr int PIECES = (16 * G2 * NB + 31) / 32;     // 16-byte pieces per lane for a full run
   const int lane = threadIdx.x & 31;
   const uint32_t ring = smem_addr(units_even_smem_) + (threadIdx.x >> 5) * (U * SLOT);
   const int64_t warp = ((int64_t)blockIdx.x * EVEN_THREADS + threadIdx.x) >> 5;
-  const int64_t grp = warp / nblk;
+  const int wpr = nblk / NB;                           // warps per row group
+  const int64_t grp = warp / wpr;
   const int64_t r0 = grp * rpg;
   if (r0 >= n_rows) return;
-  const int w = (int)(warp - grp * nblk);
+  const int w = (int)(warp - grp * wpr);
   const int nr = (int)((n_rows - r0) < rpg ? (n_rows - r0) : rpg);
   const uint32_t lt = (1u << lane) - 1u;
   const int h = nblk * 32;
@@ -96,13 +105,15 @@ __global__ void __launch_bounds__(EVEN_THREADS, MINB) spmm_units_even_kernel(
   const int k_end = __shfl_sync(0xffffffffu, my_rp, nr);
   col += k_beg;
   val += k_beg;
-  hdr += w;
-  float* yb = y + r0 * ldy + 32 * w + lane;
+  hdr += w * NB;
+  float* yb = y + r0 * ldy + 32 * NB * w + lane;
   const float4* slab4 = reinterpret_cast<const float4*>(slab);
 
-  float2 acc[G2];
+  float2 acc[NB][G2];
 #pragma unroll
-  for (int t = 0; t < G2; ++t) acc[t] = make_float2(0.f, 0.f);
+  for (int b = 0; b < NB; ++b)
+#pragma unroll
+    for (int t = 0; t < G2; ++t) acc[b][t] = make_float2(0.f, 0.f);
 
   auto load_cv = [&](int k0, int32_t& c, float& v) {
     const int k = k0 + lane;
@@ -114,23 +125,35 @@ __global__ void __launch_bounds__(EVEN_THREADS, MINB) spmm_units_even_kernel(
     }
   };
   // slab position of a neighbour's run in 16-byte units: the block's first slot is even, a slot is G2 half-pieces
-  auto load_hdr = [&](int32_t c, uint32_t& m, uint32_t& p) {
-    m = 0u;
+  auto load_hdr = [&](int32_t c, uint32_t (&m)[NB], uint32_t& p) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b) m[b] = 0u;
     p = 0u;
     if (c >= 0) {
-      const uint2 hd = __ldg(hdr + (int64_t)c * nblk);
-      m = hd.x;
-      p = (uint32_t)(((int64_t)c * lds) >> 2) + (hd.y >> 1) * G2;
+      uint32_t first;
+      if (NB == 2) {
+        const uint4 hd = __ldg(reinterpret_cast<const uint4*>(hdr + (int64_t)c * nblk));   // blocks 2w and 2w+1
+        m[0] = hd.x;
+        first = hd.y;
+        m[NB - 1] = hd.z;
+      } else {
+        const uint2 hd = __ldg(hdr + (int64_t)c * nblk);
+        m[0] = hd.x;
+        first = hd.y;
+      }
+      p = (uint32_t)(((int64_t)c * lds) >> 2) + (first >> 1) * G2;
     }
   };
   int row = 0;
   auto flush = [&]() {
 #pragma unroll
-    for (int t = 0; t < G2; ++t) {
-      yb[(2 * t + 0) * h] = acc[t].x;
-      yb[(2 * t + 1) * h] = acc[t].y;
-      acc[t] = make_float2(0.f, 0.f);
-    }
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+      for (int t = 0; t < G2; ++t) {
+        yb[32 * b + (2 * t + 0) * h] = acc[b][t].x;
+        yb[32 * b + (2 * t + 1) * h] = acc[b][t].y;
+        acc[b][t] = make_float2(0.f, 0.f);
+      }
     yb += ldy;
     ++row;
   };
@@ -138,7 +161,7 @@ __global__ void __launch_bounds__(EVEN_THREADS, MINB) spmm_units_even_kernel(
   int32_t c_a;                 // batch b+1: (col, val) loaded, header not yet
   float v_a;
   float my_v;                  // batch b: everything loaded
-  uint32_t my_m, my_p;
+  uint32_t my_m[NB], my_p;
   load_cv(0, c_a, v_a);
   my_v = v_a;
   load_hdr(c_a, my_m, my_p);
@@ -146,7 +169,7 @@ __global__ void __launch_bounds__(EVEN_THREADS, MINB) spmm_units_even_kernel(
   int row_end = __shfl_sync(0xffffffffu, my_rp, 1);
 
   for (int k0 = 0; k0 < k_end; k0 += 32) {
-    uint32_t m_n, p_n;
+    uint32_t m_n[NB], p_n;
     const float v_n = v_a;
     load_hdr(c_a, m_n, p_n);
     load_cv(k0 + 64, c_a, v_a);
@@ -155,9 +178,10 @@ __global__ void __launch_bounds__(EVEN_THREADS, MINB) spmm_units_even_kernel(
     uint32_t slot_i = ring, slot_c = ring;             // ring slot of the next copy / of the next neighbour read
     auto issue = [&](int jj) {
       if (jj < cnt) {
-        const uint32_t m = __shfl_sync(0xffffffffu, my_m, jj);
         const uint32_t p = __shfl_sync(0xffffffffu, my_p, jj);
-        const int n16 = (__popc(m) * G2 + 1) >> 1;     // 16-byte pieces covering the run (the last may be half stale)
+        int slots = __popc(__shfl_sync(0xffffffffu, my_m[0], jj));
+        if (NB == 2) slots = ((slots + 1) & ~1) + __popc(__shfl_sync(0xffffffffu, my_m[NB - 1], jj));
+        const int n16 = (slots * G2 + 1) >> 1;         // 16-byte pieces covering the run (the last may be half stale)
 #pragma unroll
         for (int t = 0; t < PIECES; ++t) {
           const int idx = lane + 32 * t;
@@ -178,33 +202,42 @@ __global__ void __launch_bounds__(EVEN_THREADS, MINB) spmm_units_even_kernel(
         flush();
         row_end = __shfl_sync(0xffffffffu, my_rp, row + 1);
       }
-      const uint32_t m = __shfl_sync(0xffffffffu, my_m, j);
       const float v = __shfl_sync(0xffffffffu, my_v, j);
-      if ((m >> lane) & 1u) {
-        const uint32_t at = slot_c + 8u * (uint32_t)(__popc(m & lt) * G2);
+      const uint32_t m0 = __shfl_sync(0xffffffffu, my_m[0], j);
+      if ((m0 >> lane) & 1u) {
+        const uint32_t at = slot_c + 8u * (uint32_t)(__popc(m0 & lt) * G2);
 #pragma unroll
-        for (int t = 0; t < G2; ++t) fma2(acc[t], v, lds_f2(at + 8u * t));
+        for (int t = 0; t < G2; ++t) fma2(acc[0][t], v, lds_f2(at + 8u * t));
+      }
+      if (NB == 2) {
+        const uint32_t m1 = __shfl_sync(0xffffffffu, my_m[NB - 1], j);
+        if ((m1 >> lane) & 1u) {
+          const uint32_t at = slot_c + 8u * (uint32_t)((((__popc(m0) + 1) & ~1) + __popc(m1 & lt)) * G2);
+#pragma unroll
+          for (int t = 0; t < G2; ++t) fma2(acc[NB - 1][t], v, lds_f2(at + 8u * t));
+        }
       }
       __syncwarp();                         // the slot is rewritten by the copy issued next iteration
       slot_c = (slot_c + SLOT == ring + U * SLOT) ? ring : slot_c + SLOT;
     }
     my_v = v_n;
-    my_m = m_n;
+#pragma unroll
+    for (int b = 0; b < NB; ++b) my_m[b] = m_n[b];
     my_p = p_n;
   }
   while (row < nr) flush();
 }
 
-template <int G2, int U, int MINB>
+template <int G2, int NB, int U, int MINB>
 int launch_even(int64_t n_rows, const int64_t* rowptr, const int32_t* col, const float* val, const float* slab,
                 int64_t lds, const uint2* hdr, int nblk, float* y, int64_t ldy, int rpg, cudaStream_t st) {
-  const int64_t warps = (n_rows + rpg - 1) / rpg * nblk;
+  const int64_t warps = (n_rows + rpg - 1) / rpg * (nblk / NB);
   const int64_t blocks = (warps + EVEN_THREADS / 32 - 1) / (EVEN_THREADS / 32);
   if (blocks > 0x7fffffffLL) return fail(LGNN_E_UNSUPPORTED, "spmm_units: grid too large");
-  const int smem = (EVEN_THREADS / 32) * U * 256 * G2;
-  LGNN_CUDA_TRY(cudaFuncSetAttribute(spmm_units_even_kernel<G2, U, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  spmm_units_even_kernel<G2, U, MINB><<<(unsigned)blocks, EVEN_THREADS, smem, st>>>(n_rows, rowptr, col, val, slab, lds,
-                                                                                   hdr, nblk, y, ldy, rpg);
+  const int smem = (EVEN_THREADS / 32) * U * 256 * G2 * NB;
+  LGNN_CUDA_TRY(cudaFuncSetAttribute(spmm_units_even_kernel<G2, NB, U, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  spmm_units_even_kernel<G2, NB, U, MINB><<<(unsigned)blocks, EVEN_THREADS, smem, st>>>(n_rows, rowptr, col, val, slab,
+                                                                                       lds, hdr, nblk, y, ldy, rpg);
   LGNN_LAUNCH_CHECK("spmm_units_even_kernel");
   return LGNN_OK;
 }
@@ -225,30 +258,38 @@ int unit_pack_even(float* slab, int64_t lds, const float* act, int64_t lda, int6
   return LGNN_OK;
 }
 
-// variant: 0 / 8..11 = 4 rows per group, 12..15 = 8 rows per group; the low two bits pick the ring depth
+// variant: 0 / 8..11 = 4 rows per group, 12..15 = 8 rows per group; the low two bits pick the ring depth; bit 4
+// (16..31) forces one unit block per warp where the default is two (g = 2, 6 with an even number of blocks)
 int spmm_units_even(int64_t n_rows, const int64_t* rowptr, const int32_t* col, const float* val, const float* slab,
                     int64_t lds, const uint2* hdr, int g, int nblk, float* y, int64_t ldy, int variant,
                     cudaStream_t st) {
   const int rpg = 4 << ((variant >> 2) & 1);
   const int cfg = variant & 3;
-#define LGNN_EVEN(G2_, U_, MINB_) launch_even<G2_, U_, MINB_>(n_rows, rowptr, col, val, slab, lds, hdr, nblk, y, ldy, rpg, st)
+  const bool pair = (nblk % 2 == 0) && !(variant & 16) && (reinterpret_cast<uintptr_t>(hdr) & 15) == 0;
+#define LGNN_EVEN(G2_, NB_, U_, MINB_) launch_even<G2_, NB_, U_, MINB_>(n_rows, rowptr, col, val, slab, lds, hdr, nblk, y, ldy, rpg, st)
   switch (g) {
-    case 2: return LGNN_EVEN(1, 8, 3);
+    case 2: return pair ? LGNN_EVEN(1, 2, 8, 3) : LGNN_EVEN(1, 1, 8, 3);
     case 6:
+      if (pair) switch (cfg) {
+        case 1: return LGNN_EVEN(3, 2, 4, 3);
+        case 2: return LGNN_EVEN(3, 2, 8, 2);
+        case 3: return LGNN_EVEN(3, 2, 5, 3);
+        default: return LGNN_EVEN(3, 2, 6, 3);
+      }
       switch (cfg) {
-        case 1: return LGNN_EVEN(3, 8, 4);
-        case 2: return LGNN_EVEN(3, 4, 4);
-        default: return LGNN_EVEN(3, 6, 4);
+        case 1: return LGNN_EVEN(3, 1, 8, 4);
+        case 2: return LGNN_EVEN(3, 1, 4, 4);
+        default: return LGNN_EVEN(3, 1, 6, 4);
       }
     case 10:
       switch (cfg) {
-        case 1: return LGNN_EVEN(5, 6, 3);
-        default: return LGNN_EVEN(5, 4, 3);
+        case 1: return LGNN_EVEN(5, 1, 6, 3);
+        default: return LGNN_EVEN(5, 1, 4, 3);
       }
     case 14:
       switch (cfg) {
-        case 1: return LGNN_EVEN(7, 6, 2);
-        default: return LGNN_EVEN(7, 4, 3);
+        case 1: return LGNN_EVEN(7, 1, 6, 2);
+        default: return LGNN_EVEN(7, 1, 4, 3);
       }
     default: return fail(LGNN_E_UNSUPPORTED, "spmm_units: g = %d is not 2, 6, 10 or 14", g);
   }

@@ -170,7 +170,7 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, syrk_stack_narrow=False, overlap_groups=False, sparse_halo=False):
+                    unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, sparse_halo=False):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -204,8 +204,8 @@ class _B200KFAC:
         self.unit_slabs = bool(unit_slabs)
         self.unit_min_width = int(unit_min_width)   # narrower slabs stay dense (one row is a few hundred bytes anyway)
         # column groups of 2, 6, 10 or 14 as well (csrc/spmm_units_even.cu): a rank of the 8-GPU column split
-        # owns 6 of the products shape's 47 columns and would otherwise carry 8.  OFF by default until those
-        # kernels have been run against the dense SpMM on a B200 (tests/test_gpu_parity.py, LGNN_LAB=1)
+        # owns 6 of the products shape's 47 columns and would otherwise carry 8 (g = 6: 93.7 ms against 111 ms per
+        # hidden layer, profiles/r2a_units_lab.txt; bit-identical to the dense SpMM, tests/test_gpu_units_even.py)
         self.unit_even_groups = bool(unit_even_groups)
         # with a process group the stand-in KronLaplace can spread the factor eigendecompositions over the ranks
         # (kron.Kron.decompose); OFF (replicated) until the all-gather has run over NCCL (gloo-tested only)
@@ -219,13 +219,6 @@ class _B200KFAC:
         # node (csrc/spmm_hess.cu): 576 instead of 3072 gathered bytes per edge at g = 16, C = 47, and no
         # lgnn_hess_rhs_f32 pass.  OFF by default until the kernel has run on a B200 (LGNN_LAB=1 tests)
         self.fused_hess_spmm = bool(fused_hess_spmm)
-        # G of the output layer (n = C): SYRK of the slab viewed [K/s, s*ld] instead of [K, ld] (ops.syrk_stacked);
-        # OFF until n = s*ld (240 at C = 47) has been timed on a B200
-        self.syrk_stack_narrow = bool(syrk_stack_narrow)
-        # single GPU / column-parallel backward: two column groups in flight on two streams (half-size slabs each),
-        # so that the tensor-bound SYRK / GEMM of one group can run under the HBM-bound SpMM of the other.
-        # An experiment for the first GPU pass of round 2 (whether the block scheduler co-schedules them): OFF
-        self.overlap_groups = bool(overlap_groups)
         # row-partitioned passes: when fewer than half of the other ranks' rows are referenced (a graph with
         # locality, partitioned), exchange only those halo rows (all-to-all) instead of all-gathering whole slabs
         # (dist.RowPartition.exchange_for_spmm).  OFF until the all-to-all has run over NCCL (gloo-tested)
@@ -385,10 +378,7 @@ class _B200KFAC:
                 # output layer: the slab is zero outside the batch's train rows -> no gather for those edges
                 ops.spmm(lay.csr_t_top if (l == L - 1 and lay.csr_t_top is not None) else lay.csr_t, slab, out=gz)
             gz_rows = gz.view(n_loc * gq, ld)
-            if self.syrk_stack_narrow and ld <= 128 and gz_rows.is_contiguous():
-                ops.syrk_stacked(gz_rows, width, G[l], impl=self._impl(width))
-            else:
-                ops.syrk(gz_rows, n=width, alpha=1.0, beta=1.0, out=G[l], impl=self._impl(width))
+            ops.syrk(gz_rows, n=width, alpha=1.0, beta=1.0, out=G[l], impl=self._impl(width))
             if self._layer_hook is not None:
                 self._layer_hook(l, gz, gq, ld, width)
             if l > 0:
@@ -430,10 +420,11 @@ class _B200KFAC:
         c_first, c_count = cols
         dev = logits.device
         n_loc, n_in = lay.n_local, lay.total_rows
-        # two column groups in flight: always worthwhile when a group waits for collectives (rows layout); with
-        # overlap_groups also when every row is local, so that one group's tensor-bound SYRK / GEMM can share the
-        # device with the other's HBM-bound SpMM (the groups' chains are independent)
-        lanes = 2 if ((self.overlap and lay.communicates and dev.type == "cuda") or self.overlap_groups) else 1
+        # two column groups in flight when a group waits for collectives (rows layout).  (With every row local the
+        # same interleaving — one group's SYRK / GEMM under the other's SpMM — was measured 10 % SLOWER than one
+        # group at a time, 1,972 against 1,786 ms per products fit: the persistent tensor-core CTAs and the SpMM's
+        # CTAs time-slice the SMs instead of sharing them; profiles/r2a_lab_switches.txt.)
+        lanes = 2 if (self.overlap and lay.communicates and dev.type == "cuda") else 1
         room = self._group_size(lanes * n_in, lanes * n_loc, dmax, 1 << 30, dev)   # columns the HBM budget allows
         grp = min(room, C)
         grp = lay.agree_min(max(1, min(grp, (c_count + lanes - 1) // lanes)))
@@ -441,7 +432,11 @@ class _B200KFAC:
         # the last group of a pass is padded with all-zero right-hand sides (47 classes -> 16 + 16 + 15(+1))
         q = 2 if self.unit_even_groups else 4
         per_lane = (max(c_count, 1) + lanes - 1) // lanes         # = c_count with one group in flight
-        cand = min(room // q * q, 16, (per_lane + q - 1) // q * q)
+        cap = min(room // q * q, 16)
+        # equal groups instead of full ones plus a narrow rest: 24 columns (a rank of the 2-GPU split) travel as
+        # 12 + 12, not 16 + 8 — the unit SpMM runs at 0.88 of the copy rate at g = 12 against 0.75 at g = 8
+        n_eq = (per_lane + cap - 1) // cap if cap > 0 else 1
+        cand = min(cap, ((per_lane + n_eq - 1) // n_eq + q - 1) // q * q)
         pad4 = (self._units_possible(lay) and cand >= q and
                 any(self._can_unit(lay, cand, h) for h in dims[:-1]))
         if pad4:
@@ -650,7 +645,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact", unit_even_groups=False, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, syrk_stack_narrow=False, overlap_groups=False, sparse_halo=False):
+                 unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, sparse_halo=False):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -661,7 +656,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
                          backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs,
-                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split, fused_hess_spmm, syrk_stack_narrow, overlap_groups, sparse_halo)
+                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split, fused_hess_spmm, sparse_halo)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

@@ -417,7 +417,7 @@ def hess_stats(logits: torch.Tensor, idx: torch.Tensor, mode: str = "reference",
     if out.shape[0] < n or out.shape[1] < 5 * cp:
         raise ValueError("hess_stats: out too small")
     idx = idx.contiguous()
-    with _Timed("hess_rhs", C):
+    with _Timed("hess_rhs", C, 0.0):
         out.zero_()
         check(lib.lgnn_hess_stats_f32(ptr(logits), logits.stride(0), C, ptr(idx), idx.numel(), m, ptr(out),
                                       out.stride(0), stream()), "lgnn_hess_stats_f32")
@@ -573,26 +573,4 @@ def syrk(x: torch.Tensor, n: int | None = None, alpha: float = 1.0, beta: float 
         check(lib.lgnn_syrk_f32(ptr(x), x.stride(0), k_rows, n, float(alpha), float(beta), ptr(out),
                                 out.stride(0), ptr(ws), ws.numel(), code, stream()), "lgnn_syrk_f32")
     _lib.count_launches(2)
-    return out
-
-
-def syrk_stacked(x: torch.Tensor, n: int, out: torch.Tensor, impl: str = "auto") -> torch.Tensor:
-    """out += X[:, :n]^T X[:, :n] for a NARROW contiguous X ([K, ld], ld <= 128, columns n .. ld zero), computed as
-    the SYRK of the same memory viewed [K/s, s*ld] (s = 256 // ld consecutive rows side by side): the diagonal
-    ld x ld blocks of that s*ld-square product add up to X^T X.  The tensor-core SYRK is paced by its TMA boxes at
-    small n (n = 48: 9.5 useful TFLOP/s against 133 at n = 256); the wide view does 5x the flops at 14x the rate."""
-    _f32c(x, "x")
-    K, ld = int(x.shape[0]), int(x.shape[1])
-    s = 256 // ld if ld > 0 else 0
-    if s < 2 or x.stride(0) != ld or K < 4 * s:
-        return syrk(x, n=n, alpha=1.0, beta=1.0, out=out, impl=impl)
-    k_main = K // s * s
-    wide = syrk(x[:k_main].view(k_main // s, s * ld), impl=impl)            # [s*ld, s*ld]
-    blocks = wide.view(s, ld, s, ld)
-    acc = blocks[0, :n, 0, :n].clone()
-    for b in range(1, s):
-        acc += blocks[b, :n, b, :n]
-    out[:n, :n] += acc
-    if k_main < K:
-        syrk(x[k_main:], n=n, alpha=1.0, beta=1.0, out=out, impl=impl)
     return out

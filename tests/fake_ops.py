@@ -123,22 +123,6 @@ def syrk(x, n=None, alpha=1.0, beta=0.0, out=None, impl="auto", k_rows=None):
     return out
 
 
-def syrk_stacked(x, n, out, impl="auto"):
-    """Same wide-view algebra as ops.syrk_stacked, on the CPU double's syrk."""
-    K, ld = x.shape
-    s_ = 256 // ld if ld > 0 else 0
-    if s_ < 2 or x.stride(0) != ld or K < 4 * s_:
-        return syrk(x, n=n, alpha=1.0, beta=1.0, out=out)
-    k_main = K // s_ * s_
-    wide = syrk(x[:k_main].view(k_main // s_, s_ * ld))
-    blocks = wide.view(s_, ld, s_, ld)
-    for b in range(s_):
-        out[:n, :n] += blocks[b, :n, b, :n]
-    if k_main < K:
-        syrk(x[k_main:], n=n, alpha=1.0, beta=1.0, out=out)
-    return out
-
-
 def csr_with_masked_sources(a, keep):
     val = a.val * keep[a.col.to(torch.int64)].to(a.val.dtype)
     return CSR(a.n_rows, a.n_cols, a.rowptr, a.col, val, a.max_row_nnz, masked=True)
@@ -182,5 +166,5 @@ def gemm_mask_supported(k, n):
     return False          # the CPU double keeps the two-step path (torch.mm + relu_mask_mul)
 
 
-ALL = ["syrk_stacked", "spmm_hess_supported", "hess_stats", "spmm_hess", "sddmm", "unit_slabs_supported", "unit_pack", "spmm_units", "gemm_mask_supported", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
+ALL = ["spmm_hess_supported", "hess_stats", "spmm_hess", "sddmm", "unit_slabs_supported", "unit_pack", "spmm_units", "gemm_mask_supported", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
        "halo_columns", "csr_slice_remap", "spmm", "softmax_ce_sum", "hess_rhs", "relu_mask_mul", "syrk"]

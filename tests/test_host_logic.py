@@ -432,7 +432,8 @@ def test_unit_compacted_groups_give_the_same_factors(fake_ops, C, layers, budget
     csrc/spmm_units.cu) against the dense slabs: 10 classes -> groups 8 + 2(+2) or 4 + 4 + 2(+2)."""
     import laplace_gnn_b200 as L
     model, idx, y = _synthetic_model(600, 2400, 12, 64, C, layers)
-    be1 = L.B200GGN(model, "classification", unit_slabs=True, rhs_tile_bytes=budget, unit_min_width=0)
+    be1 = L.B200GGN(model, "classification", unit_slabs=True, rhs_tile_bytes=budget, unit_min_width=0,
+                    unit_even_groups=False)
     be2 = L.B200GGN(model, "classification", unit_slabs=False, rhs_tile_bytes=budget)
     l1, k1 = be1.kron(idx, y, N=len(y))
     l2, k2 = be2.kron(idx, y, N=len(y))
@@ -447,11 +448,11 @@ def test_unit_compacted_groups_give_the_same_factors(fake_ops, C, layers, budget
 @pytest.mark.parametrize("C,want_group", [(6, 6), (5, 6), (10, 10), (7, 8), (47, 16)])
 def test_even_column_groups_take_what_the_rank_owns(fake_ops, C, want_group):
     """unit_even_groups: groups of any even width (csrc/spmm_units_even.cu) — the 6 (or 5) columns a rank of the
-    8-GPU column split owns travel as 6, not 8; the default keeps multiples of 4."""
+    8-GPU column split owns travel as 6, not 8 (the default); unit_even_groups=False keeps multiples of 4."""
     import laplace_gnn_b200 as L
     model, idx, y = _synthetic_model(400, 1600, 12, 64, C, 3)
     be1 = L.B200GGN(model, "classification", unit_min_width=0, unit_even_groups=True)
-    be2 = L.B200GGN(model, "classification", unit_min_width=0)
+    be2 = L.B200GGN(model, "classification", unit_min_width=0, unit_even_groups=False)
     be3 = L.B200GGN(model, "classification", unit_slabs=False)
     l1, k1 = be1.kron(idx, y, N=len(y))
     l2, k2 = be2.kron(idx, y, N=len(y))
@@ -569,23 +570,6 @@ def test_on_the_fly_hessian_sqrt_spmm_gives_the_same_factors(fake_ops, mode):
             assert max_rel_err(a.numpy(), b.numpy()) <= 1e-5
 
 
-def test_stacked_narrow_syrk_gives_the_same_factors(fake_ops):
-    """syrk_stack_narrow: the output-layer G from the slab viewed s rows side by side (diagonal blocks of the wide
-    product), remainder rows included (K = 400 * 12 rows, s = 256 // 12 = 21)."""
-    import laplace_gnn_b200 as L
-    model, idx, y = _synthetic_model(400, 1600, 12, 64, 10, 3)
-    l1, k1 = L.B200GGN(model, "classification", syrk_stack_narrow=True).kron(idx, y, N=len(y))
-    l2, k2 = L.B200GGN(model, "classification").kron(idx, y, N=len(y))
-    for fa, fb in zip(k1.kfacs, k2.kfacs):
-        for a, b in zip(fa, fb):
-            assert max_rel_err(a.numpy(), b.numpy()) <= 1e-5
-    x = torch.randn(1003, 12)
-    x[:, 10:] = 0
-    out = torch.ones(10, 10)
-    fake_ops.syrk_stacked(x, 10, out)
-    assert max_rel_err(out.numpy(), (1 + x[:, :10].T @ x[:, :10]).numpy()) <= 1e-5
-
-
 @pytest.mark.parametrize("n,U,F,h,C,layers,M,dup", [
     (30, 60, 5, 8, 3, 1, 10, False),      # a single layer: no hidden slab, no GEMM step
     (30, 60, 5, 8, 2, 2, 1, False),       # one train node
@@ -615,25 +599,6 @@ def test_edge_case_shapes_match_the_oracle(fake_ops, n, U, F, h, C, layers, M, d
     for blk, ref_blk in zip(la.H_facs.kfacs, kfacs):
         for a, b in zip(blk, ref_blk):
             assert float((a - b).abs().max()) <= 1e-5 * max(float(b.abs().max()), 1e-6)
-
-
-@pytest.mark.parametrize("units", [True, False])
-def test_two_column_groups_in_flight_give_the_same_factors(fake_ops, units):
-    """overlap_groups: two column groups interleaved layer by layer, each with its own slabs, unit headers and
-    factor accumulators (summed at the end) — the CPU double walks the same interleaving without streams."""
-    import laplace_gnn_b200 as L
-    model, idx, y = _synthetic_model(400, 1600, 12, 64, 10, 3)
-    budget = 400 * 64 * 4 * 2 * 2 * 4                                   # room for 4 columns per lane
-    be = L.B200GGN(model, "classification", overlap_groups=True, unit_slabs=units, unit_min_width=0,
-                   rhs_tile_bytes=budget)
-    l1, k1 = be.kron(idx, y, N=len(y))
-    assert be.last_stats["n_groups"] == 3 and be.last_stats["group"] == 4
-    assert (be.last_stats["unit_slabs"] > 0) == units
-    l2, k2 = L.B200GGN(model, "classification", unit_slabs=False).kron(idx, y, N=len(y))
-    assert float(l1) == float(l2)
-    for fa, fb in zip(k1.kfacs, k2.kfacs):
-        for a, b in zip(fa, fb):
-            assert max_rel_err(a.numpy(), b.numpy()) <= 1e-5
 
 
 def test_symeig_jitter_fallback_like_the_reference():
@@ -740,16 +705,15 @@ def test_cached_input_factor_is_decomposed_once(fake_ops):
 
 
 def test_all_lab_switches_compose(fake_ops):
-    """Every opt-in path of DESIGN.md §6c at once (even column groups, hub split, on-the-fly output-layer SpMM,
-    stacked narrow SYRK) through the Laplace driver: the marglik of the plain dense path."""
+    """Every opt-in path at once (even column groups, hub split, on-the-fly output-layer SpMM) through the
+    Laplace driver: the marglik of the plain dense path."""
     import laplace_gnn_b200 as L
     model, idx, y = _synthetic_model(300, 1200, 10, 64, 7, 3)
-    kw = {"unit_min_width": 0, "unit_even_groups": True, "fused_hess_spmm": True, "syrk_stack_narrow": True,
-          "unit_hub_split": True, "overlap_groups": True}
+    kw = {"unit_min_width": 0, "unit_even_groups": True, "fused_hess_spmm": True, "unit_hub_split": True}
     la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs=kw)
     la.backend.unit_row_limit = 8
     la.fit(L.TensorBatchLoader(idx, y))
-    assert la.backend.last_stats["unit_slabs"] > 0 and la.backend.last_stats["group"] == 4    # 7 classes, two lanes
+    assert la.backend.last_stats["unit_slabs"] > 0 and la.backend.last_stats["group"] == 8    # 7 classes (+1 zero column)
     ref = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs={"unit_slabs": False})
     ref.fit(L.TensorBatchLoader(idx, y))
     a, b = float(la.log_marginal_likelihood()), float(ref.log_marginal_likelihood())
