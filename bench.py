@@ -52,8 +52,9 @@ def parse_args():
     ap.add_argument("--dense-slabs", action="store_true", help="keep the slabs below the output layer dense (no unit compaction)")
     ap.add_argument("--no-unit-even-groups", action="store_true",
                     help="column groups padded to multiples of 4 (round-1 behaviour) instead of any even width")
-    ap.add_argument("--fused-hess-spmm", action="store_true",
-                    help="lab: output-layer SpMM with its Hessian-sqrt right-hand sides rebuilt per edge (csrc/spmm_hess.cu)")
+    ap.add_argument("--no-fused-hess-spmm", action="store_true",
+                    help="materialise the Hessian-sqrt right-hand sides (round-1 path) instead of rebuilding them per edge "
+                         "inside the output-layer SpMM (csrc/spmm_hess.cu)")
     ap.add_argument("--shard-eigh", action="store_true",
                     help="lab, multi-GPU: spread the factor eigendecompositions over the ranks (kron.Kron.decompose)")
     ap.add_argument("--rhs-tile-gb", type=float, default=None,
@@ -263,7 +264,7 @@ def main():
         del edge_index
     bk = {"hess_sqrt": args.hess_sqrt, "syrk_impl": args.syrk, "fused_gemm": not args.no_fused_gemm,
           "unit_slabs": not args.dense_slabs, "unit_even_groups": not args.no_unit_even_groups,
-          "fused_hess_spmm": args.fused_hess_spmm}
+          "fused_hess_spmm": not args.no_fused_hess_spmm}
     if args.rhs_tile_gb is not None:
         bk["rhs_tile_bytes"] = int(args.rhs_tile_gb * 1e9)
     if pg is not None:

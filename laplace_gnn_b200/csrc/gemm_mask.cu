@@ -96,16 +96,6 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
         "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
-// D[tmem] (+)= A[tmem] . B[smem]^T
-__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
-                                               uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t cta) {
   uint32_t remote;
@@ -135,7 +125,7 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   uint64_t* acc_empty = acc_full + 2;              // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)warp_uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int cl = P.cl;
   const uint32_t rank = cl > 1 ? cluster_ctarank() : 0u;
   const int64_t cluster_id = blockIdx.x / cl;
@@ -177,7 +167,7 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_a) : "memory");
       // resident weights: this CTA's 64 rows of W^T, hi and lo, all k-blocks
       mbar_arrive_expect_tx(smem_u32(b_full), (uint32_t)(2 * P.n_kb * GM_B_TILE));
@@ -202,40 +192,45 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // the WHOLE warp walks the loop (uniform control flow, uniform operands), one elected lane issues each MMA /
+    // commit (tc_common.cuh: tc_mma_tf32_ts_e)
+    {
+      const uint32_t tb = warp_uniform(tmem_base);
       const uint32_t idesc = make_idesc_tf32(GM_BM, GM_BN);
+      const uint32_t bh0 = smem_u32(b_hi), bl0 = smem_u32(b_lo);
       mbar_wait(smem_u32(b_full), 0);
       for (int64_t t = 0; t < n_tiles; ++t) {
         const int as = (int)(t & 1);
         const uint32_t aph = (uint32_t)((t >> 1) & 1);
         mbar_wait(smem_u32(&acc_empty[as]), aph ^ 1u);
         tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(as * GM_BN);
+        const uint32_t d = tb + (uint32_t)(as * GM_BN);
         for (int kb = 0; kb < P.n_kb; ++kb) {
           const int64_t it = t * P.n_kb + kb;
           const int s = (int)(it % GM_TM_STAGES);
           const uint32_t ph = (uint32_t)((it / GM_TM_STAGES) & 1);
           mbar_wait(smem_u32(&ta_full[s]), ph);
           tc_fence_after();
-          const uint32_t a_hi = tmem_base + GM_TMEM_A0 + (uint32_t)(s * 64);   // 32 columns hi, 32 columns lo
+          const uint32_t a_hi = tb + GM_TMEM_A0 + (uint32_t)(s * 64);   // 32 columns hi, 32 columns lo
           const uint32_t a_lo = a_hi + 32;
-          const uint32_t bh = smem_u32(b_hi + (size_t)kb * GM_B_TILE);
-          const uint32_t bl = smem_u32(b_lo + (size_t)kb * GM_B_TILE);
+          const uint32_t bh = bh0 + (uint32_t)kb * GM_B_TILE;
+          const uint32_t bl = bl0 + (uint32_t)kb * GM_B_TILE;
           const int ksteps = (kb == P.n_kb - 1) ? P.last_ksteps : GM_BK / 8;
+#pragma unroll 4
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint32_t off = (uint32_t)ks * 32u;   // 8 tf32 = 32 bytes inside the 128-byte swizzle row
             const uint64_t db_hi = make_smem_desc(bh + off, 0, 1024, 2);
             const uint64_t db_lo = make_smem_desc(bl + off, 0, 1024, 2);
             const uint32_t ca = (uint32_t)(ks * 8);    // 8 tf32 = 8 TMEM columns
-            if (!GM_ABL(1)) tc_mma_tf32_ts(d, a_hi + ca, db_hi, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
+            if (!GM_ABL(1)) tc_mma_tf32_ts_e(d, a_hi + ca, db_hi, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
             if (!GM_ABL(1) && !GM_ABL(2)) {
-              tc_mma_tf32_ts(d, a_hi + ca, db_lo, idesc, 1u);
-              tc_mma_tf32_ts(d, a_lo + ca, db_hi, idesc, 1u);
+              tc_mma_tf32_ts_e(d, a_hi + ca, db_lo, idesc, 1u);
+              tc_mma_tf32_ts_e(d, a_lo + ca, db_hi, idesc, 1u);
             }
           }
-          tc_commit(smem_u32(&ta_empty[s]));
+          tc_commit_e(smem_u32(&ta_empty[s]));
         }
-        tc_commit(smem_u32(&acc_full[as]));
+        tc_commit_e(smem_u32(&acc_full[as]));
       }
     }
   } else if (warp < 10) {

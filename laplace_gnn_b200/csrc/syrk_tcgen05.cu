@@ -117,7 +117,7 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
   uint64_t* acc_empty = acc_full + 1;              // [1]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = (int)warp_uniform(threadIdx.x >> 5), lane = threadIdx.x & 31;
   const int64_t step_beg = (int64_t)blockIdx.x * P.steps_per_cta;
   int64_t step_end = step_beg + P.steps_per_cta;
   if (step_end > P.steps_total) step_end = P.steps_total;
@@ -149,7 +149,7 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
       for (int64_t s = 0; s < my_steps; ++s) {
         int st = (int)(s % TC_RAW_STAGES);
@@ -163,12 +163,16 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0 && my_steps > 0) {
+    // the WHOLE warp walks the loop (uniform control flow, uniform operands), one elected lane issues each MMA /
+    // commit (tc_common.cuh: tc_mma_tf32_e)
+    if (my_steps > 0) {
+      const uint32_t tb = warp_uniform(tmem_base);
       // instruction descriptor: D fp32, A/B tf32, both K-major, N>>3 at bit 17, M>>4 at bit 24
       const uint32_t idesc_base = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(128 >> 4) << 24);
       const uint32_t idesc0 = idesc_base | ((uint32_t)(P.np >> 3) << 17);
       const uint32_t idesc1 = idesc_base | ((uint32_t)((P.np - 128) >> 3) << 17);
       const uint32_t lbo = P.lbo, sbo = TC_SBO;
+      const uint32_t op0 = smem_u32(op_base);
       for (int64_t s = 0; s < my_steps; ++s) {
         const bool seg_first = (s % P.seg_steps) == 0;
         if (seg_first && s > 0) {
@@ -180,7 +184,7 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
         uint32_t ph = (uint32_t)((s / TC_OP_STAGES) & 1);
         mbar_wait(smem_u32(&full_op[st]), ph);
         tc_fence_after();
-        const uint32_t hi = smem_u32(op_base + (size_t)st * 2 * P.op_bytes);
+        const uint32_t hi = op0 + (uint32_t)st * 2u * (uint32_t)P.op_bytes;
         const uint32_t lo = hi + P.op_bytes;
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
@@ -189,26 +193,26 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
           {  // M block 0: rows 0..127 x columns 0..np-1
             const uint64_t a_hi = make_smem_desc(hi + koff, lbo, sbo);
             const uint64_t a_lo = make_smem_desc(lo + koff, lbo, sbo);
-            if (!TC_ABL(1)) tc_mma_tf32(tmem_base, a_hi, a_hi, idesc0, acc);
+            if (!TC_ABL(1)) tc_mma_tf32_e(tb, a_hi, a_hi, idesc0, acc);
             if (!TC_ABL(1) && !TC_ABL(2)) {
-              tc_mma_tf32(tmem_base, a_hi, a_lo, idesc0, 1u);
-              tc_mma_tf32(tmem_base, a_lo, a_hi, idesc0, 1u);
+              tc_mma_tf32_e(tb, a_hi, a_lo, idesc0, 1u);
+              tc_mma_tf32_e(tb, a_lo, a_hi, idesc0, 1u);
             }
           }
           if (P.mb == 2) {  // M block 1: rows 128..255 x columns 128..np-1 (128 rows = 16 groups)
             const uint32_t off = koff + 16u * TC_SBO;
             const uint64_t a_hi = make_smem_desc(hi + off, lbo, sbo);
             const uint64_t a_lo = make_smem_desc(lo + off, lbo, sbo);
-            const uint32_t d = tmem_base + (uint32_t)P.np;
-            if (!TC_ABL(1)) tc_mma_tf32(d, a_hi, a_hi, idesc1, acc);
+            const uint32_t d = tb + (uint32_t)P.np;
+            if (!TC_ABL(1)) tc_mma_tf32_e(d, a_hi, a_hi, idesc1, acc);
             if (!TC_ABL(1) && !TC_ABL(2)) {
-              tc_mma_tf32(d, a_hi, a_lo, idesc1, 1u);
-              tc_mma_tf32(d, a_lo, a_hi, idesc1, 1u);
+              tc_mma_tf32_e(d, a_hi, a_lo, idesc1, 1u);
+              tc_mma_tf32_e(d, a_lo, a_hi, idesc1, 1u);
             }
           }
         }
-        tc_commit(smem_u32(&empty_op[st]));  // implies fence::before_thread_sync
-        if ((s % P.seg_steps) == P.seg_steps - 1 || s == my_steps - 1) tc_commit(smem_u32(acc_full));
+        tc_commit_e(smem_u32(&empty_op[st]));  // implies fence::before_thread_sync
+        if ((s % P.seg_steps) == P.seg_steps - 1 || s == my_steps - 1) tc_commit_e(smem_u32(acc_full));
       }
     }
   } else if (warp < 6) {

@@ -83,6 +83,52 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, ui
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- warp-collective issue (the whole MMA warp runs the loop, ONE elected lane issues) ----------------------
+// Issuing from `if (lane == 0) { ... }` makes ptxas treat every tcgen05 operand as possibly divergent: each MMA
+// becomes a waterfall loop (ELECT, R2UR.BROADCAST per operand, UTCHMMA, BRA.U.ANY) of ~60-100 issue cycles —
+// more than the 32-128 cycles the tensor pipe needs for it, so the pipe idled 43-50 % of the time (ncu,
+// profiles/r2b_*).  With elect.sync in the same asm block and warp-uniform operands the operands live in uniform
+// registers and an MMA is one predicated UTCHMMA.
+__device__ __forceinline__ void tc_mma_tf32_e(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] . B[smem]^T
+__device__ __forceinline__ void tc_mma_tf32_ts_e(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_e(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+      ::"r"(bar)
+      : "memory");
+}
+// one lane of a converged warp (elect.sync): ptxas knows the guarded region runs single-lane, so TMA / tcgen05
+// operands are moved to uniform registers with plain R2UR instead of waterfall loops
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// a value every lane of the warp holds, told to the compiler (lane 0's copy broadcast): keeps address arithmetic
+// derived from it in uniform registers
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __shfl_sync(0xffffffffu, v, 0); }
+
 // Shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor, version 1).
 //   K-major, no swizzle (layout 0): 8-row x 16-byte core matrices; LBO = stride between the 16-byte
 //     k-chunks, SBO = stride between 8-row groups.

@@ -170,7 +170,7 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, sparse_halo=False):
+                    unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=True, sparse_halo=False):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -217,7 +217,8 @@ class _B200KFAC:
         self.unit_hub_split = bool(unit_hub_split)
         # output-layer SpMM with its Hessian-sqrt right-hand sides rebuilt per edge from five softmax vectors per
         # node (csrc/spmm_hess.cu): 576 instead of 3072 gathered bytes per edge at g = 16, C = 47, and no
-        # lgnn_hess_rhs_f32 pass.  OFF by default until the kernel has run on a B200 (LGNN_LAB=1 tests)
+        # lgnn_hess_rhs_f32 pass.  Measured on the products shape: 18.9 ms against 43.6 ms per 16-column group, the
+        # fit 1,678 against 1,786 ms (profiles/r2b_hess_spmm_lab.txt); shapes it does not take fall back
         self.fused_hess_spmm = bool(fused_hess_spmm)
         # row-partitioned passes: when fewer than half of the other ranks' rows are referenced (a graph with
         # locality, partitioned), exchange only those halo rows (all-to-all) instead of all-gathering whole slabs
@@ -645,7 +646,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=False, sparse_halo=False):
+                 unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=True, sparse_halo=False):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:

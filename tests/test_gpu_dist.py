@@ -148,3 +148,40 @@ def test_nccl_lab_switches_match_single_gpu():
         out = m.dict()
         mp.spawn(_lab_worker, args=(world, _free_port(), out), nprocs=world, join=True)
         assert len(out) == world
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
+def test_model_on_another_device_than_the_current_one():
+    """The backend, the GCN layers and the graph build run on the device of their tensors whichever device is
+    current in the calling thread; a raw ops.* call with a foreign device's tensor raises instead of launching on the
+    wrong stream (_lib.stream() is the current device's stream)."""
+    sys.path.insert(0, ROOT)
+    import laplace_gnn_b200 as L
+    from laplace_gnn_b200 import ops
+    from laplace_gnn_b200._lib import LgnnError
+    torch.cuda.set_device(0)
+    n, u, f, c, h, layers = 5_000, 30_000, 16, 5, 64, 3
+    gen = torch.Generator().manual_seed(0)
+    ei = torch.randint(0, n, (2, u), generator=gen)
+    X = torch.randn(n, f, generator=gen)
+    idx = torch.randperm(n, generator=gen)[: int(0.6 * n)].sort().values
+    y = torch.randint(0, c, (idx.numel(),), generator=gen)
+    results = []
+    for d in ("cuda:0", "cuda:1"):
+        graph = L.Graph.from_edge_index(ei.to(d), n)                     # current device stays 0
+        torch.manual_seed(0)
+        model = L.SparseGCN(f, h, c, layers, X.to(d), graph).to(d)
+        out = model(idx.to(d))
+        out.sum().backward()
+        la = L.Laplace(model, "classification", backend=L.B200GGN)
+        la.fit(L.TensorBatchLoader(idx.to(d), y.to(d)))
+        results.append((float(la.log_marginal_likelihood()), [[t.cpu() for t in blk] for blk in la.H_facs.kfacs],
+                        model.convs[0].lin.weight.grad.cpu()))
+        assert torch.cuda.current_device() == 0
+    assert results[0][0] == results[1][0]
+    for ba, bb in zip(results[0][1], results[1][1]):
+        for a, b in zip(ba, bb):
+            assert torch.equal(a, b)
+    assert torch.equal(results[0][2], results[1][2])
+    with pytest.raises(LgnnError, match="current CUDA device"):
+        ops.spmm(graph.ahat, torch.randn(n, 8, device="cuda:1"))        # graph lives on cuda:1, current device is 0

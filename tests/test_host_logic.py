@@ -559,7 +559,7 @@ def test_on_the_fly_hessian_sqrt_spmm_gives_the_same_factors(fake_ops, mode):
         be1 = L.B200GGN(model, "classification", hess_sqrt=mode, unit_min_width=0, fused_hess_spmm=True)
         l1, k1 = be1.kron(idx, y, N=len(y))
         assert calls["fly"] == be1.last_stats["n_groups"] and calls["rhs"] == 0
-        be2 = L.B200GGN(model, "classification", hess_sqrt=mode, unit_min_width=0)
+        be2 = L.B200GGN(model, "classification", hess_sqrt=mode, unit_min_width=0, fused_hess_spmm=False)
         l2, k2 = be2.kron(idx, y, N=len(y))
         assert calls["rhs"] == be2.last_stats["n_groups"]
     finally:

@@ -1,6 +1,7 @@
 #!/bin/bash
-# Multi-GPU follow-up of round 2 (gpurun --gpus N): the default command, then the switches of DESIGN.md §6c.
-#   /usr/local/graft/bin/gpurun --gpus 8 --timeout 900 -- 'bash tools/round2_multi_gpu.sh 8'
+# Multi-GPU pass of round 2 (gpurun --gpus N): NCCL parity tests (incl. the lab switches), then the DRIVER's bench
+# command at N ranks (--steps 20 --warmup 5: the run that ran out of memory at N = 2 / 4 in round 1), then switches.
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'bash tools/round2_multi_gpu.sh 2'
 set -u
 N=${1:-8}
 mkdir -p gpurun_out
@@ -8,19 +9,25 @@ P=29540
 S=$(date +%s)
 LGNN_LAB=1 timeout 600 python -m pytest tests/test_gpu_dist.py -x -q > gpurun_out/r2_n${N}_tests.log 2>&1; echo "multi-GPU tests (incl. lab switches over NCCL) rc=$? in $(( $(date +%s) - S )) s"
 tail -3 gpurun_out/r2_n${N}_tests.log | cut -c1-200
-for flags in "" "--shard-eigh" "--unit-even-groups --shard-eigh" "--unit-even-groups --shard-eigh --fused-hess-spmm"; do
-  tag=$(echo "base $flags" | tr -d '-' | tr ' ' '_')
-  S=$(date +%s)
-  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P \
-      bench.py --gpus $N --steps 3 --warmup 3 --no-e2e --no-parity $flags > gpurun_out/r2_n${N}_$tag.log 2>gpurun_out/r2_n${N}_$tag.err
-  echo "N=$N [$flags] rc=$? in $(( $(date +%s) - S )) s"
+bench() {  # tag, steps, warmup, extra flags...
+  local tag=$1 steps=$2 warm=$3; shift 3
+  local S=$(date +%s)
+  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P \
+      bench.py --gpus $N --steps $steps --warmup $warm "$@" > gpurun_out/r2_n${N}_$tag.log 2>gpurun_out/r2_n${N}_$tag.err
+  echo "N=$N $tag [$*] rc=$? in $(( $(date +%s) - S )) s"
   python - "gpurun_out/r2_n${N}_$tag.log" <<'PY'
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
-    print("   ", round(d["value"]), "nodes/s", round(d["ms_per_step"], 1), "ms  marglik", d["marglik"], d["roofline"]["ms_per_step_by_kind"])
+    print("   ", round(d["value"]), "nodes/s", round(d["ms_per_step"], 1), "ms  marglik", d["marglik"], d["roofline"]["ms_per_step_by_kind"],
+          "parity", d.get("parity"), "alloc", d.get("allocator_in_timed_region"), "e2e", (d.get("e2e") or {}).get("value"))
 except Exception as e:
     print("    no bench line:", e)
 PY
+  tail -4 "gpurun_out/r2_n${N}_$tag.err" | cut -c1-300
   P=$((P + 1))
-done
+}
+bench driver 20 5
+bench shard_eigh 5 3 --no-e2e --no-parity --shard-eigh
+bench pad4 5 3 --no-e2e --no-parity --no-unit-even-groups
+bench rows 5 3 --no-e2e --no-parity --backward-parallel rows
