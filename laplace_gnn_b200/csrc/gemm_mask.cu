@@ -37,6 +37,7 @@
 // MMA instead of 32).  An L2 prefetch ahead of the ring and doubling the transform warps changed
 // nothing, which rules out HBM latency and the transform chain.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -78,6 +79,7 @@ struct GmParams {
   int n_kb;          // k-blocks (K_pad / 32)
   int last_ksteps;   // 8-wide k-steps in the last k-block (1..4)
   int cl;            // cluster size = N / 64
+  int unicast;       // 1: every CTA loads the whole A tile itself (L2 serves the cluster's repeats); 0: multicast slices
   int group;
   const float* act;  // may be null (no mask)
   int64_t ld_act;
@@ -140,7 +142,7 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < GM_RAW_STAGES; ++i) {
       mbar_init(smem_u32(&full_raw[i]), 1);
-      mbar_init(smem_u32(&empty_raw[i]), (uint32_t)(4 * cl));
+      mbar_init(smem_u32(&empty_raw[i]), (uint32_t)(P.unicast ? 4 : 4 * cl));
     }
     for (int i = 0; i < GM_TM_STAGES; ++i) {
       mbar_init(smem_u32(&ta_full[i]), 4);
@@ -184,6 +186,10 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         mbar_wait(smem_u32(&empty_raw[s]), ph ^ 1u);
         const uint32_t bar = smem_u32(&full_raw[s]);
         mbar_arrive_expect_tx(bar, (uint32_t)GM_A_TILE);
+        if (P.unicast) {
+          tma_load_2d(smem_u32(a_raw + (size_t)s * GM_A_TILE), &tm_a, kb * GM_BK, (int)(tile * GM_BM), bar);
+          continue;
+        }
         const uint32_t dst = smem_u32(a_raw + (size_t)s * GM_A_TILE + (size_t)rank * rows_per_cta * GM_BK * 4);
         const int row0 = (int)(tile * GM_BM + (int64_t)rank * rows_per_cta);
         if (cl > 1) tma_load_2d_multicast(dst, &tm_a, kb * GM_BK, row0, bar, cta_mask);
@@ -261,7 +267,9 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         lo[j] = __float_as_uint(__uint_as_float(hi[j]) - __uint_as_float(hi[j] & 0xffffe000u));
       // the raw stage is in registers: hand it back to every producer of the cluster
       __syncwarp();
-      if (lane < cl) {
+      if (P.unicast) {
+        if (lane == 0) mbar_arrive(smem_u32(&empty_raw[rs]));
+      } else if (lane < cl) {
         if (cl > 1) mbar_arrive_remote(smem_u32(&empty_raw[rs]), (uint32_t)lane);
         else mbar_arrive(smem_u32(&empty_raw[rs]));
       }
@@ -455,6 +463,8 @@ int lgnn_gemm_mask_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, c
   P.n_kb = k_pad / GM_BK;
   P.last_ksteps = (int)((k - (int64_t)(P.n_kb - 1) * GM_BK + 7) / 8);
   P.cl = (int)(n / GM_BN);
+  P.unicast = 0;
+  if (const char* u = getenv("LGNN_GEMM_UNICAST")) P.unicast = atoi(u) != 0;   // lab switch
   P.group = group;
   P.act = act;
   P.ld_act = ld_act;
@@ -462,7 +472,7 @@ int lgnn_gemm_mask_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, c
   P.ldo = ldo;
   CUtensorMap tm_a, tm_bhi, tm_blo;
   int rc;
-  if ((rc = encode_2d(&tm_a, a, (uint64_t)k, (uint64_t)m_rows, (uint64_t)lda * 4, GM_BK, GM_BM / P.cl))) return rc;
+  if ((rc = encode_2d(&tm_a, a, (uint64_t)k, (uint64_t)m_rows, (uint64_t)lda * 4, GM_BK, P.unicast ? GM_BM : GM_BM / P.cl))) return rc;
   if ((rc = encode_2d(&tm_bhi, wt_hi, (uint64_t)k_pad, (uint64_t)n, (uint64_t)k_pad * 4, GM_BK, GM_BN))) return rc;
   if ((rc = encode_2d(&tm_blo, wt_lo, (uint64_t)k_pad, (uint64_t)n, (uint64_t)k_pad * 4, GM_BK, GM_BN))) return rc;
   const size_t smem = 1024 + (size_t)2 * P.n_kb * GM_B_TILE + (size_t)GM_RAW_STAGES * GM_A_TILE + 4 * GM_STG_WARP + 256;

@@ -31,3 +31,9 @@ bench driver 20 5
 bench shard_eigh 5 3 --no-e2e --no-parity --shard-eigh
 bench pad4 5 3 --no-e2e --no-parity --no-unit-even-groups
 bench rows 5 3 --no-e2e --no-parity --backward-parallel rows
+# single-GPU extras riding on this call: the unicast variant of the fused GEMM against the multicast one
+if [ "${EXTRA_GEMM_LAB:-0}" = "1" ]; then
+  timeout 200 python tools/gemm_lab.py > gpurun_out/r2_gemm_lab_mc.log 2>&1; head -4 gpurun_out/r2_gemm_lab_mc.log | cut -c1-200
+  LGNN_GEMM_UNICAST=1 timeout 200 python tools/gemm_lab.py > gpurun_out/r2_gemm_lab_uc.log 2>&1; head -4 gpurun_out/r2_gemm_lab_uc.log | cut -c1-200
+  LGNN_GEMM_UNICAST=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -x -k "gemm" > gpurun_out/r2_gemm_uc_tests.log 2>&1; tail -2 gpurun_out/r2_gemm_uc_tests.log | cut -c1-200
+fi
