@@ -68,7 +68,8 @@ def parse_args():
 
 
 def workload_name(workload, h, l):
-    return (f"ogbn-{workload}-shaped synthetic graph, {l}-layer GCN h={h}, KFAC-GGN "
+    pre = "ogbn-" if workload in ("arxiv", "products") else ""
+    return (f"{pre}{workload}-shaped synthetic graph, {l}-layer GCN h={h}, KFAC-GGN "
             "Laplace fit + log marglik, single full batch")
 
 
@@ -170,32 +171,74 @@ def cpu_fit_nodes_per_s(args, n, u, f, c, h, l, seed=0, repeats=1):
     return n / best, best, threads, g.nnz
 
 
+def reference_classes_fit_seconds(args, n, u, f, c, h, l, seed=0):
+    """One fit + marglik by the UNMODIFIED reference classes on the host cores (tier O2 of SURVEY 8c): the
+    reference's GCNConv layers over the sparse Â (oracle.make_golden.SparseRefGCN), its Laplace / KronLaplace, its
+    default CurvlinopsGGN backend with the vendored curvlinops.  Feasible at the Cora / Pubmed shapes (the C
+    retained autograd graphs of kfac.py:650-661 need > 61 GB at the arxiv shape)."""
+    import numpy as np
+    import torch
+    from torch.utils.data import DataLoader, TensorDataset
+    from oracle import gcn_kfac_oracle as O, ref_loader
+    from oracle.make_golden import SparseRefGCN
+    R = ref_loader.load()
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    g = O.build_graph(O.synthetic_edges(n, u, seed=seed), n)
+    x = torch.from_numpy(rng.standard_normal((n, f)).astype(np.float32))
+    idx = torch.from_numpy(np.sort(rng.permutation(n)[: int(0.6 * n)]).astype(np.int64))
+    y = torch.from_numpy(rng.integers(0, c, idx.shape[0]).astype(np.int64))
+    ahat = torch.sparse_csr_tensor(torch.from_numpy(g.rowptr), torch.from_numpy(g.col.astype(np.int64)),
+                                   torch.from_numpy(g.val), size=(n, n))
+    torch.manual_seed(seed)
+    model = SparseRefGCN(R, [f] + [h] * (l - 1) + [c], x, ahat).eval()
+    loader = DataLoader(TensorDataset(idx, y), batch_size=len(idx), shuffle=False)
+    t0 = time.perf_counter()
+    la = R.Laplace(model, "classification", subset_of_weights="all", hessian_structure="kron")
+    la.fit(loader)
+    float(la.log_marginal_likelihood())
+    return time.perf_counter() - t0, threads, g.nnz
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  The reference is pure
-    Python and cannot travel to the GPU box, so this times the oracle port (kind "port") on a bounded
-    sample: the same workload shape at 1/cpu_sample_div of the nodes and edges."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores.
+
+    Cora / Pubmed shapes, reference tree available (dev container, or its staged copy under baseline/_ref/ on the
+    GPU box): the reference's OWN classes on the whole workload (kind "reference").  arxiv / products shapes: the
+    reference needs C retained autograd graphs (> 61 GB at arxiv), so the oracle port (kind "port", pinned to the
+    reference by tests/golden) runs on a bounded sample: the same shape at 1/cpu_sample_div of the nodes and edges."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n, u, f, c, h, l = shape(args)
-    div = args.cpu_sample_div
+    from oracle import ref_loader
+    own = args.workload in ("cora", "pubmed") and ref_loader.available()
+    div = 1 if own else args.cpu_sample_div
     ns, us = max(64, n // div), max(64, u // div)
     times = []
     for i in range(args.warmup + args.steps):
-        nps, dt, threads, nnz = cpu_fit_nodes_per_s(args, ns, us, f, c, h, l, seed=i)
+        if own:
+            dt, threads, nnz = reference_classes_fit_seconds(args, ns, us, f, c, h, l, seed=i)
+        else:
+            nps, dt, threads, nnz = cpu_fit_nodes_per_s(args, ns, us, f, c, h, l, seed=i)
         if i >= args.warmup:
             times.append(dt)
         if sum(times) > 240:
             break
     ms = 1e3 * sum(times) / len(times)
     val = ns / (ms / 1e3)
-    sample = f"{args.workload}-shaped at 1/{div} scale: {ns} nodes, nnz {nnz}, F={f} C={c} h={h} L={l}, one full batch"
+    kind = "reference" if own else "port"
+    sample = (f"the whole {args.workload}-shaped workload: {ns} nodes, nnz {nnz}, F={f} C={c} h={h} L={l}, one full batch, "
+              "the reference's own Laplace / KronLaplace / CurvlinopsGGN classes over the sparse normalised adjacency"
+              if own else
+              f"{args.workload}-shaped at 1/{div} scale: {ns} nodes, nnz {nnz}, F={f} C={c} h={h} L={l}, one full batch")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "nodes/s", "n_gpus": args.gpus,
         "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, h, l), "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "nodes/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "nodes/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -421,14 +464,29 @@ def main():
     if not args.no_e2e:
         del model, la, loader
         torch.cuda.empty_cache()
-        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        nbytes = {k: v.numel() * v.element_size() for k, v in host.items()}
+        # all ranks together: the edge list and the features cross PCIe once (1 / world per rank), indices and labels
+        # once per rank
+        h2d = nbytes["edge_index"] + nbytes["X"] + world * (nbytes["idx"] + nbytes["y"])
 
         def e2e_step():
-            ei_d = host["edge_index"].to(dev, non_blocking=True)
-            X_d = host["X"].to(dev, non_blocking=True)
             idx_d = host["idx"].to(dev, non_blocking=True)
             y_d = host["y"].to(dev, non_blocking=True)
-            mdl = build_model(ei_d, X_d)
+            if world == 1:
+                ei_d = host["edge_index"].to(dev, non_blocking=True)
+                X_d = host["X"].to(dev, non_blocking=True)
+                mdl = build_model(ei_d, X_d)
+            else:
+                # sharded ingest (laplace_gnn_b200/dist.py): every rank copies 1 / world of the edge list over its own
+                # PCIe link, the shards are all-gathered over NVLink, the graph is built on every rank; of the
+                # features a rank copies its node block only (the row-partitioned forward reads nothing else)
+                from laplace_gnn_b200 import dist as D
+                ei_d = D.ingest_edge_index(host["edge_index"], dev, pg)
+                graph = L.Graph.from_edge_index(ei_d, n, assume_undirected=True)
+                lo, hi = D.row_block(graph, pg)
+                X_d = D.ingest_rows(host["X"], lo, hi, dev)
+                torch.manual_seed(0)
+                mdl = L.SparseGCN(f, h, c, l, X_d, graph, x_rows=(lo, hi)).to(dev)
             ldr = L.TensorBatchLoader(idx_d, y_d)
             _, ml_ = step(mdl, ldr)
             return float(ml_.cpu())           # D2H read of the result
@@ -446,7 +504,10 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": n / float(tt.item()), "unit": "nodes/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": 4, "ms_per_step": 1e3 * float(tt.item()), "steps": ks,
-               "includes": "H2D of edge list/features/labels/indices, CSR build + normalisation, fit, marglik, D2H"}
+               "includes": "H2D of edge list/features/labels/indices, CSR build + normalisation, fit, marglik, D2H",
+               "ingest": "whole inputs on the one device" if world == 1 else
+               f"sharded: 1/{world} of the edge list and of the feature rows per rank over PCIe, edge shards "
+               "all-gathered over NVLink, graph built on every rank", "marglik": ml_e2e}
 
     # ---------------- parity bit of THIS run (outside every timed region): the same workload shape at 1/div of
     # the nodes and edges, the SAME seeded inputs through (i) this run's backend configuration on the device(s),

@@ -252,7 +252,12 @@ class _B200KFAC:
         h = self.model.X
         if h.dtype != torch.float32 or not h.is_contiguous():
             h = h.float().contiguous()
-        if part is not None:
+        x_rows = getattr(self.model, "x_rows", None)
+        if x_rows is not None:                        # the model holds this rank's node block only (sharded ingest)
+            if part is None or x_rows != (part.lo, part.hi):
+                raise ValueError(f"the model holds rows {x_rows} of X; the fit needs "
+                                 f"{'all rows' if part is None else (part.lo, part.hi)}")
+        elif part is not None:
             h = h[part.lo:part.hi]
         Hs = [h]
         L = len(Ws)
@@ -580,7 +585,7 @@ class _B200KFAC:
             # every rank needs H_l (relu' masks) and the logits of ALL nodes: in-place all-gather of the padded
             # slabs the forward wrote its rows into, then into natural node order — persistent buffers, no
             # allocation per fit
-            full_H, full_logits = [self.model.X.float().contiguous()], None
+            full_H, full_logits = [Hs[0]], None          # slot 0 (the features) is never read by the backward
             for l, t_loc in enumerate(Hs[1:] + [logits]):
                 w, slab = t_loc.shape[1], self._fwd_out[l]
                 ldz = slab.shape[1]

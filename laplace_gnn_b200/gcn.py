@@ -63,7 +63,7 @@ class SparseGCN(nn.Module):
 
     def __init__(self, in_channels: int, hidden_channels: int, out_channels: int, num_layers: int,
                  X: torch.Tensor, graph, dropout_p: float = 0.5, act: Optional[str] = "relu",
-                 symmetric: bool = False, bias: bool = True, **kwargs):
+                 symmetric: bool = False, bias: bool = True, x_rows: Optional[tuple] = None, **kwargs):
         super().__init__()
         if act != "relu":
             raise NotImplementedError("SparseGCN supports act='relu' only (the GCN hot path)")
@@ -73,6 +73,12 @@ class SparseGCN(nn.Module):
             graph = Graph.from_edge_index(graph, X.shape[0], symmetric=symmetric)
         self.graph = graph
         self.X = X
+        # multi-GPU Laplace fits read only this rank's node block of X (dist.row_block): ``x_rows=(lo, hi)`` says
+        # that X holds just those rows (dist.ingest_rows).  Such a model serves B200GGN with a process group; its
+        # own forward() (training step) needs all rows and raises.
+        self.x_rows = None if x_rows is None else (int(x_rows[0]), int(x_rows[1]))
+        if self.x_rows is not None and X.shape[0] != self.x_rows[1] - self.x_rows[0]:
+            raise ValueError(f"x_rows={self.x_rows} but X has {X.shape[0]} rows")
         self.in_channels = in_channels
         self.hidden_channels = hidden_channels
         self.out_channels = out_channels
@@ -88,6 +94,9 @@ class SparseGCN(nn.Module):
             conv.reset_parameters()
 
     def forward(self, x_indices: torch.Tensor) -> torch.Tensor:
+        if self.x_rows is not None:
+            raise RuntimeError("this SparseGCN holds a row block of X (x_rows): only the row-partitioned Laplace fit "
+                               "(B200GGN with a process group) can run on it")
         x = self.X
         for i in range(self.num_layers - 1):
             x = self.convs[i](self.graph, x)

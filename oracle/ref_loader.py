@@ -1,7 +1,7 @@
-"""TEST INFRASTRUCTURE — loads the *unmodified* reference from /root/reference.
+"""TEST INFRASTRUCTURE — loads the *unmodified* reference from /root/reference (dev container) or from
+its staged copy under the git-ignored baseline/_ref/ (GPU box; oracle/stage_reference.py).
 
-Only usable in the dev container (the reference tree does not exist on the GPU
-box).  It is used by ``oracle/make_golden.py`` to generate the committed golden
+It is used by ``oracle/make_golden.py`` to generate the committed golden
 fixtures under ``tests/golden/`` and by CPU tests that pin the numpy oracle to
 the reference's own classes.  Nothing in the product package imports this.
 
@@ -24,7 +24,22 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("LGNN_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root() -> str:
+    """/root/reference in the dev container; on the GPU box the copy oracle/stage_reference.py put under the
+    git-ignored baseline/_ref/ (it travels with the gpurun snapshot)."""
+    env = os.environ.get("LGNN_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if os.path.isdir(os.path.join(cand, "laplace")) and os.path.isdir(os.path.join(cand, "curvlinops")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 _STUB_ROOTS = (
     "torchmetrics",

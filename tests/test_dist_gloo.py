@@ -228,3 +228,62 @@ def test_sparse_halo_exchange_matches_the_single_rank_pass(world):
         out = m.dict()
         mp.spawn(_halo_worker, args=(world, port, out), nprocs=world, join=True)
         assert len(out) == world
+
+
+def _ingest_worker(rank, world, port, out):
+    """dist.ingest_edge_index / ingest_rows / row_block: the sharded copy + all-gather gives the graph of the
+    unsharded list bit for bit, and a model holding only its node block of X (x_rows) fits to the same factors."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import fake_ops as F
+        import laplace_gnn_b200 as L
+        import laplace_gnn_b200.ops as ops
+        from laplace_gnn_b200 import dist as D
+        for n in F.ALL:
+            setattr(ops, n, getattr(F, n))
+        from helpers import build_model
+        g = Golden("tiny_directed_3l")
+        cpu = torch.device("cpu")
+        host_ei = torch.from_numpy(g.edge_index.astype("int64"))              # E = 160: not a multiple of 3
+        ei = D.ingest_edge_index(host_ei, cpu, dist.group.WORLD)
+        assert ei.shape[0] == 2 and ei.shape[1] >= host_ei.shape[1]
+        assert set(map(tuple, ei.t().tolist())) == set(map(tuple, host_ei.t().tolist()))
+        whole, shard = L.Graph.from_edge_index(host_ei, g.n), L.Graph.from_edge_index(ei, g.n)
+        for a, b in ((whole.ahat, shard.ahat), (whole.ahat_t, shard.ahat_t)):
+            assert torch.equal(a.rowptr, b.rowptr) and torch.equal(a.col, b.col) and torch.equal(a.val, b.val)
+        assert D.ingest_edge_index(host_ei[:, :1], cpu, dist.group.WORLD).shape == (2, world)   # fewer edges than ranks
+        # a model that holds this rank's node block of X only
+        ref = build_model(g)
+        lo, hi = D.row_block(shard, dist.group.WORLD)
+        x_loc = D.ingest_rows(torch.from_numpy(g.x), lo, hi, cpu)
+        model = L.SparseGCN(g.F, g.h, g.C, g.L, x_loc, shard, x_rows=(lo, hi))
+        model.load_state_dict(ref.state_dict())
+        idx, y = torch.from_numpy(g.idx), torch.from_numpy(g.y)
+        kw = {"process_group": dist.group.WORLD, "backward_parallel": "columns"}
+        la = L.Laplace(model, "classification", backend=L.B200GGN, backend_kwargs=kw)
+        la.fit(L.TensorBatchLoader(idx, y))
+        la_ref = L.Laplace(ref, "classification", backend=L.B200GGN, backend_kwargs=kw)
+        la_ref.fit(L.TensorBatchLoader(idx, y))
+        for fa, fb in zip(la.H_facs.kfacs, la_ref.H_facs.kfacs):
+            for a, b in zip(fa, fb):
+                assert torch.equal(a, b)
+        assert float(la.log_marginal_likelihood()) == float(la_ref.log_marginal_likelihood())
+        with pytest.raises(RuntimeError):
+            model(idx)                                                        # the training forward needs all rows
+        with pytest.raises(ValueError):
+            L.B200GGN(model, "classification").kron(idx, y, N=len(y))         # ... and so does a single-device fit
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_ingest_gives_the_same_graph_and_fit(world):
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_ingest_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+        assert len(out) == world

@@ -47,7 +47,7 @@ def _worker(rank, world, port, out):
         ref, ref_ml = fit()
         for kw in ({"backward_parallel": "rows", "overlap": False},
                    {"backward_parallel": "rows", "overlap": True, "rhs_tile_bytes": 64 << 20},
-                   {"backward_parallel": "columns"}):
+                   {"backward_parallel": "columns", "unit_min_width": 0}):    # 5 columns per rank travel as 6 x 128
             la, ml = fit(process_group=dist.group.WORLD, **kw)
             for blk, rblk in zip(la.H_facs.kfacs, ref.H_facs.kfacs):
                 for a, b in zip(blk, rblk):
@@ -140,7 +140,6 @@ def _lab_worker(rank, world, port, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs at least 2 GPUs")
-@pytest.mark.skipif(os.environ.get("LGNN_LAB") != "1", reason="lab paths, not on the default path: set LGNN_LAB=1 to run")
 def test_nccl_lab_switches_match_single_gpu():
     import torch.multiprocessing as mp
     world = min(torch.cuda.device_count(), 4)
