@@ -52,7 +52,6 @@ constexpr int GM_TM_STAGES = 4;       // TMEM ring of (hi, lo) A operand k-block
 constexpr int GM_THREADS = 448;            // 1 TMA + 1 MMA + 8 transform + 4 epilogue warps
 constexpr int GM_A_TILE = GM_BM * GM_BK * 4;   // 16 KB
 constexpr int GM_B_TILE = GM_BN * GM_BK * 4;   // 8 KB
-constexpr int GM_TILES_PER_CLUSTER = 32;
 constexpr int GM_MAX_KB = 8;                   // K <= 256
 constexpr int GM_STG_PITCH = 80;               // epilogue staging: 16 floats per row + 16 bytes pad
 constexpr int GM_STG_WARP = 32 * GM_STG_PITCH; // per epilogue warp
@@ -79,7 +78,7 @@ struct GmParams {
   int n_kb;          // k-blocks (K_pad / 32)
   int last_ksteps;   // 8-wide k-steps in the last k-block (1..4)
   int cl;            // cluster size = N / 64
-  int unicast;       // 1: every CTA loads the whole A tile itself (L2 serves the cluster's repeats); 0: multicast slices
+  int tiles_per_cluster;
   int group;
   const float* act;  // may be null (no mask)
   int64_t ld_act;
@@ -131,18 +130,21 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int cl = P.cl;
   const uint32_t rank = cl > 1 ? cluster_ctarank() : 0u;
   const int64_t cluster_id = blockIdx.x / cl;
-  const int64_t tile_beg = cluster_id * GM_TILES_PER_CLUSTER;
-  int64_t tile_end = tile_beg + GM_TILES_PER_CLUSTER;
+  const int64_t tile_beg = cluster_id * P.tiles_per_cluster;
+  int64_t tile_end = tile_beg + P.tiles_per_cluster;
   if (tile_end > P.tiles_total) tile_end = P.tiles_total;
-  const int64_t n_tiles = tile_end - tile_beg;              // >= 1 by construction of the grid
-  const int64_t total_it = n_tiles * P.n_kb;
+  // 32-bit loop state everywhere below, ring stages and phases stepped incrementally: a 64-bit division per
+  // k-block (it / n_kb, it % 5) was ~500 issue cycles of the single producer thread — the whole 625-cycle k-block
+  // budget of the round-1 kernel (profiles/r2c_*)
+  const int n_tiles = (int)(tile_end - tile_beg);           // >= 1 by construction of the grid
+  const int total_it = n_tiles * P.n_kb;
   const uint16_t cta_mask = (uint16_t)((1u << cl) - 1u);
   const int n0 = (int)rank * GM_BN;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < GM_RAW_STAGES; ++i) {
       mbar_init(smem_u32(&full_raw[i]), 1);
-      mbar_init(smem_u32(&empty_raw[i]), (uint32_t)(P.unicast ? 4 : 4 * cl));
+      mbar_init(smem_u32(&empty_raw[i]), (uint32_t)(4 * cl));
     }
     for (int i = 0; i < GM_TM_STAGES; ++i) {
       mbar_init(smem_u32(&ta_full[i]), 4);
@@ -178,22 +180,19 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         tma_load_2d(smem_u32(b_lo + (size_t)kb * GM_B_TILE), &tm_blo, kb * GM_BK, n0, smem_u32(b_full));
       }
       const int rows_per_cta = GM_BM / cl;
-      for (int64_t it = 0; it < total_it; ++it) {
-        const int s = (int)(it % GM_RAW_STAGES);
-        const uint32_t ph = (uint32_t)((it / GM_RAW_STAGES) & 1);
-        const int64_t tile = tile_beg + it / P.n_kb;
-        const int kb = (int)(it % P.n_kb);
+      const uint32_t raw0 = smem_u32(a_raw) + (uint32_t)rank * (uint32_t)(rows_per_cta * GM_BK * 4);
+      int row0 = (int)(tile_beg * GM_BM) + (int)rank * rows_per_cta;
+      int s = 0, kb = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < total_it; ++it) {
         mbar_wait(smem_u32(&empty_raw[s]), ph ^ 1u);
         const uint32_t bar = smem_u32(&full_raw[s]);
         mbar_arrive_expect_tx(bar, (uint32_t)GM_A_TILE);
-        if (P.unicast) {
-          tma_load_2d(smem_u32(a_raw + (size_t)s * GM_A_TILE), &tm_a, kb * GM_BK, (int)(tile * GM_BM), bar);
-          continue;
-        }
-        const uint32_t dst = smem_u32(a_raw + (size_t)s * GM_A_TILE + (size_t)rank * rows_per_cta * GM_BK * 4);
-        const int row0 = (int)(tile * GM_BM + (int64_t)rank * rows_per_cta);
+        const uint32_t dst = raw0 + (uint32_t)s * GM_A_TILE;
         if (cl > 1) tma_load_2d_multicast(dst, &tm_a, kb * GM_BK, row0, bar, cta_mask);
         else tma_load_2d(dst, &tm_a, kb * GM_BK, row0, bar);
+        if (++kb == P.n_kb) { kb = 0; row0 += GM_BM; }
+        if (++s == GM_RAW_STAGES) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -205,16 +204,15 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       const uint32_t idesc = make_idesc_tf32(GM_BM, GM_BN);
       const uint32_t bh0 = smem_u32(b_hi), bl0 = smem_u32(b_lo);
       mbar_wait(smem_u32(b_full), 0);
-      for (int64_t t = 0; t < n_tiles; ++t) {
-        const int as = (int)(t & 1);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = 0; t < n_tiles; ++t) {
+        const int as = t & 1;
         const uint32_t aph = (uint32_t)((t >> 1) & 1);
         mbar_wait(smem_u32(&acc_empty[as]), aph ^ 1u);
         tc_fence_after();
         const uint32_t d = tb + (uint32_t)(as * GM_BN);
         for (int kb = 0; kb < P.n_kb; ++kb) {
-          const int64_t it = t * P.n_kb + kb;
-          const int s = (int)(it % GM_TM_STAGES);
-          const uint32_t ph = (uint32_t)((it / GM_TM_STAGES) & 1);
           mbar_wait(smem_u32(&ta_full[s]), ph);
           tc_fence_after();
           const uint32_t a_hi = tb + GM_TMEM_A0 + (uint32_t)(s * 64);   // 32 columns hi, 32 columns lo
@@ -235,6 +233,7 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
           }
           tc_commit_e(smem_u32(&ta_empty[s]));
+          if (++s == GM_TM_STAGES) { s = 0; ph ^= 1u; }
         }
         tc_commit_e(smem_u32(&acc_full[as]));
       }
@@ -246,11 +245,9 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    for (int64_t it = (warp - 2) >> 2; it < total_it; it += 2) {
-      const int rs = (int)(it % GM_RAW_STAGES);
-      const uint32_t rph = (uint32_t)((it / GM_RAW_STAGES) & 1);
-      const int ts = (int)(it % GM_TM_STAGES);
-      const uint32_t tph = (uint32_t)((it / GM_TM_STAGES) & 1);
+    int rs = (warp - 2) >> 2, ts = rs;          // this set's first k-block: 0 or 1
+    uint32_t rph = 0, tph = 0;
+    for (int it = rs; it < total_it; it += 2) {
       mbar_wait(smem_u32(&full_raw[rs]), rph);
       const uint8_t* row = a_raw + (size_t)rs * GM_A_TILE + (size_t)r * 128;
       uint32_t hi[32], lo[32];
@@ -267,9 +264,7 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         lo[j] = __float_as_uint(__uint_as_float(hi[j]) - __uint_as_float(hi[j] & 0xffffe000u));
       // the raw stage is in registers: hand it back to every producer of the cluster
       __syncwarp();
-      if (P.unicast) {
-        if (lane == 0) mbar_arrive(smem_u32(&empty_raw[rs]));
-      } else if (lane < cl) {
+      if (lane < cl) {
         if (cl > 1) mbar_arrive_remote(smem_u32(&empty_raw[rs]), (uint32_t)lane);
         else mbar_arrive(smem_u32(&empty_raw[rs]));
       }
@@ -284,6 +279,10 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ta_full[ts]));
+      rs += 2;
+      if (rs >= GM_RAW_STAGES) { rs -= GM_RAW_STAGES; rph ^= 1u; }
+      ts += 2;
+      if (ts >= GM_TM_STAGES) { ts -= GM_TM_STAGES; tph ^= 1u; }
     }
   } else {
     // ===================================================================== epilogue warps
@@ -294,7 +293,7 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     // relu' mask words of one tile for this thread: mk[4*p + i] covers pass p (columns 16p + 4*sub_c ..),
     // row i*8 + sub_r.  They do not depend on the MMAs, so tile t+1's are fetched while tile t is stored.
     float4 mk[16];
-    auto fetch_mask = [&](int64_t t) {
+    auto fetch_mask = [&](int t) {
       const int64_t row_base = (tile_beg + t) * GM_BM + quarter * 32;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -307,8 +306,8 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     };
     if (masked) fetch_mask(0);
-    for (int64_t t = 0; t < n_tiles; ++t) {
-      const int as = (int)(t & 1);
+    for (int t = 0; t < n_tiles; ++t) {
+      const int as = t & 1;
       const uint32_t aph = (uint32_t)((t >> 1) & 1);
       const int64_t row_base = (tile_beg + t) * GM_BM + quarter * 32;
       unsigned long long keep = ~0ull;   // bit 4*(4*p + i) + e
@@ -463,8 +462,16 @@ int lgnn_gemm_mask_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, c
   P.n_kb = k_pad / GM_BK;
   P.last_ksteps = (int)((k - (int64_t)(P.n_kb - 1) * GM_BK + 7) / 8);
   P.cl = (int)(n / GM_BN);
-  P.unicast = 0;
-  if (const char* u = getenv("LGNN_GEMM_UNICAST")) P.unicast = atoi(u) != 0;   // lab switch
+  // tiles per cluster: a few waves over the clusters that fit the device at once — long enough to amortise a CTA's
+  // prologue (barriers, TMEM allocation, the 128 KB weight slice, two cluster syncs), short enough to balance the tail
+  {
+    const int64_t resident = sm_count() / P.cl > 0 ? sm_count() / P.cl : 1;
+    int64_t tpc = (P.tiles_total + resident * 4 - 1) / (resident * 4);
+    if (tpc < 32) tpc = 32;
+    if (tpc > 4096) tpc = 4096;
+    if (const char* t = getenv("LGNN_GEMM_TILES_PER_CLUSTER")) { int v = atoi(t); if (v >= 1) tpc = v; }   // lab switch
+    P.tiles_per_cluster = (int)tpc;
+  }
   P.group = group;
   P.act = act;
   P.ld_act = ld_act;
@@ -472,12 +479,12 @@ int lgnn_gemm_mask_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, c
   P.ldo = ldo;
   CUtensorMap tm_a, tm_bhi, tm_blo;
   int rc;
-  if ((rc = encode_2d(&tm_a, a, (uint64_t)k, (uint64_t)m_rows, (uint64_t)lda * 4, GM_BK, P.unicast ? GM_BM : GM_BM / P.cl))) return rc;
+  if ((rc = encode_2d(&tm_a, a, (uint64_t)k, (uint64_t)m_rows, (uint64_t)lda * 4, GM_BK, GM_BM / P.cl))) return rc;
   if ((rc = encode_2d(&tm_bhi, wt_hi, (uint64_t)k_pad, (uint64_t)n, (uint64_t)k_pad * 4, GM_BK, GM_BN))) return rc;
   if ((rc = encode_2d(&tm_blo, wt_lo, (uint64_t)k_pad, (uint64_t)n, (uint64_t)k_pad * 4, GM_BK, GM_BN))) return rc;
   const size_t smem = 1024 + (size_t)2 * P.n_kb * GM_B_TILE + (size_t)GM_RAW_STAGES * GM_A_TILE + 4 * GM_STG_WARP + 256;
   LGNN_CUDA_TRY(cudaFuncSetAttribute(gemm_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t n_clusters = (P.tiles_total + GM_TILES_PER_CLUSTER - 1) / GM_TILES_PER_CLUSTER;
+  const int64_t n_clusters = (P.tiles_total + P.tiles_per_cluster - 1) / P.tiles_per_cluster;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_clusters * P.cl), 1, 1);
   cfg.blockDim = dim3(GM_THREADS, 1, 1);

@@ -151,14 +151,17 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
     // ===================================================================== TMA producer
     if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-      for (int64_t s = 0; s < my_steps; ++s) {
-        int st = (int)(s % TC_RAW_STAGES);
-        uint32_t ph = (uint32_t)((s / TC_RAW_STAGES) & 1);
+      // 32-bit loop state, stages and phases stepped incrementally (no 64-bit division per step)
+      const uint32_t raw0 = smem_u32(raw_base);
+      int row = (int)(step_beg * TC_BK), st = 0;
+      uint32_t ph = 0;
+      for (int s = 0; s < (int)my_steps; ++s) {
         mbar_wait(smem_u32(&empty_raw[st]), ph ^ 1);
         uint32_t bar = smem_u32(&full_raw[st]);
         mbar_arrive_expect_tx(bar, (uint32_t)P.raw_bytes);
-        tma_load_2d(smem_u32(raw_base + (size_t)st * P.raw_bytes), &tmap, 0,
-                    (int)((step_beg + s) * TC_BK), bar);
+        tma_load_2d(raw0 + (uint32_t)st * (uint32_t)P.raw_bytes, &tmap, 0, row, bar);
+        row += TC_BK;
+        if (++st == TC_RAW_STAGES) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -173,15 +176,17 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
       const uint32_t idesc1 = idesc_base | ((uint32_t)((P.np - 128) >> 3) << 17);
       const uint32_t lbo = P.lbo, sbo = TC_SBO;
       const uint32_t op0 = smem_u32(op_base);
-      for (int64_t s = 0; s < my_steps; ++s) {
-        const bool seg_first = (s % P.seg_steps) == 0;
+      int st = 0, in_seg = 0;             // operand stage, step inside the current accumulation segment
+      uint32_t ph = 0, seg_ph = 0;        // operand-ring phase, parity of the segments drained so far
+      const int n_steps = (int)my_steps;
+      for (int s = 0; s < n_steps; ++s) {
+        const bool seg_first = in_seg == 0;
         if (seg_first && s > 0) {
           // the epilogue warps have drained the previous segment out of TMEM
-          mbar_wait(smem_u32(acc_empty), (uint32_t)((s / P.seg_steps - 1) & 1));
+          mbar_wait(smem_u32(acc_empty), seg_ph);
+          seg_ph ^= 1u;
           tc_fence_after();
         }
-        int st = (int)(s % TC_OP_STAGES);
-        uint32_t ph = (uint32_t)((s / TC_OP_STAGES) & 1);
         mbar_wait(smem_u32(&full_op[st]), ph);
         tc_fence_after();
         const uint32_t hi = op0 + (uint32_t)st * 2u * (uint32_t)P.op_bytes;
@@ -212,7 +217,11 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
           }
         }
         tc_commit_e(smem_u32(&empty_op[st]));  // implies fence::before_thread_sync
-        if ((s % P.seg_steps) == P.seg_steps - 1 || s == my_steps - 1) tc_commit_e(smem_u32(acc_full));
+        if (++in_seg == P.seg_steps || s == n_steps - 1) {
+          tc_commit_e(smem_u32(acc_full));
+          in_seg = 0;
+        }
+        if (++st == TC_OP_STAGES) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp < 6) {
@@ -220,11 +229,9 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
     const int t = threadIdx.x - 64;  // 0..127
     const int np4 = P.np >> 2;
     const int items = (TC_BK / 4) * np4;
-    for (int64_t s = 0; s < my_steps; ++s) {
-      const int rs = (int)(s % TC_RAW_STAGES);
-      const uint32_t rph = (uint32_t)((s / TC_RAW_STAGES) & 1);
-      const int os = (int)(s % TC_OP_STAGES);
-      const uint32_t oph = (uint32_t)((s / TC_OP_STAGES) & 1);
+    int rs = 0, os = 0;
+    uint32_t rph = 0, oph = 0;
+    for (int s = 0; s < (int)my_steps; ++s) {
       mbar_wait(smem_u32(&full_raw[rs]), rph);
       mbar_wait(smem_u32(&empty_op[os]), oph ^ 1);
       const float* raw = reinterpret_cast<const float*>(raw_base + (size_t)rs * P.raw_bytes);
@@ -265,6 +272,8 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
         mbar_arrive(smem_u32(&full_op[os]));
         mbar_arrive(smem_u32(&empty_raw[rs]));
       }
+      if (++rs == TC_RAW_STAGES) { rs = 0; rph ^= 1u; }
+      if (++os == TC_OP_STAGES) { os = 0; oph ^= 1u; }
     }
   } else {
     // ===================================================================== epilogue warps
