@@ -55,8 +55,8 @@ def parse_args():
     ap.add_argument("--no-fused-hess-spmm", action="store_true",
                     help="materialise the Hessian-sqrt right-hand sides (round-1 path) instead of rebuilding them per edge "
                          "inside the output-layer SpMM (csrc/spmm_hess.cu)")
-    ap.add_argument("--shard-eigh", action="store_true",
-                    help="lab, multi-GPU: spread the factor eigendecompositions over the ranks (kron.Kron.decompose)")
+    ap.add_argument("--no-shard-eigh", action="store_true",
+                    help="multi-GPU: every rank decomposes every factor (round-1 behaviour) instead of a share of them")
     ap.add_argument("--rhs-tile-gb", type=float, default=None,
                     help="HBM budget of the two multi-RHS slabs (sizes the column groups; default: 45 %% of HBM)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -314,7 +314,7 @@ def main():
         bk["process_group"] = pg
         bk["backward_parallel"] = args.backward_parallel
         bk["overlap"] = not args.no_overlap
-        bk["shard_eigh"] = args.shard_eigh
+        bk["shard_eigh"] = not args.no_shard_eigh
     loader = L.TensorBatchLoader(idx, y)      # one full batch, no per-sample collation
 
     def step(mdl, ldr, kwargs=None):

@@ -12,7 +12,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblgnn.so")
+# LGNN_LIB_PATH: another build of the same ABI (kernel bisects on the GPU box); default: the in-tree library
+LIB_PATH = os.environ.get("LGNN_LIB_PATH") or os.path.join(_HERE, "liblgnn.so")
 
 OK = 0
 HESS_REFERENCE, HESS_GGN = 0, 1

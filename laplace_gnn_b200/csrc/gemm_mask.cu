@@ -22,9 +22,8 @@
 // with A in TMEM the tensor path reads 64 B/clk.
 //
 // Per CTA (14 warps): warp 0 TMA producer; warp 1 MMA issuer (one thread; 12 MMAs M=128 N=64 K=8 per
-// 32-wide k-block; accumulator double-buffered in TMEM); warps 2-9 transform (two sets of four
-// alternate k-blocks: the wait -> ld.shared -> split -> tcgen05.st -> wait::st -> arrive chain of one
-// k-block is longer than the 384 cycles its MMAs take); warps 10-13 epilogue (tcgen05.ld ->
+// 32-wide k-block; accumulator double-buffered in TMEM); warps 2-9 transform (every k-block by all eight, in
+// order: warps 2-5 its columns 0..15, warps 6-9 its columns 16..31); warps 10-13 epilogue (tcgen05.ld ->
 // shared-memory staging -> 128-bit stores of 64 contiguous bytes per row; the relu' mask words of the
 // NEXT tile are prefetched while the current one is stored).  A raw ring
 // stage is recycled when the transform warps of ALL CTAs of the cluster have read it (remote
@@ -86,15 +85,12 @@ struct GmParams {
   int64_t ldo;
 };
 
-__device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t* v) {
+__device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t* v) {
   asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
       ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]),
-        "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]),
-        "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
       : "memory");
 }
 // arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
@@ -144,10 +140,10 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   if (threadIdx.x == 0) {
     for (int i = 0; i < GM_RAW_STAGES; ++i) {
       mbar_init(smem_u32(&full_raw[i]), 1);
-      mbar_init(smem_u32(&empty_raw[i]), (uint32_t)(4 * cl));
+      mbar_init(smem_u32(&empty_raw[i]), (uint32_t)(8 * cl));
     }
     for (int i = 0; i < GM_TM_STAGES; ++i) {
-      mbar_init(smem_u32(&ta_full[i]), 4);
+      mbar_init(smem_u32(&ta_full[i]), 8);
       mbar_init(smem_u32(&ta_empty[i]), 1);
     }
     mbar_init(smem_u32(b_full), 1);
@@ -240,27 +236,34 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
   } else if (warp < 10) {
     // ===================================================================== transform warps
-    // thread = tile row = TMEM lane (a warp may only touch its own quarter of the lanes);
-    // warps 2-5 take the even k-blocks, warps 6-9 the odd ones
+    // thread = tile row = TMEM lane (a warp may only touch its own quarter of the lanes).  EVERY k-block is
+    // handled by all eight warps, in order: warps 2-5 take its columns 0..15, warps 6-9 its columns 16..31
+    // (4 of the row's 8 swizzled 16-byte chunks each).  (Round 1 let two sets of four warps take alternate
+    // k-blocks.  With a ring of 5 stages a set then revisits a stage's barrier every 10 k-blocks — two phases
+    // apart, which a parity wait cannot tell from "already there": once k-blocks landed out of order the set read
+    // a stage early, arrived on its `empty` barrier a second time, the producer re-armed a `full` barrier inside
+    // an open phase and the kernel died with an illegal-instruction exception.  Seen at N = 64 after the MMA
+    // issue got fast, cuda-gdb, profiles/r2f_*.)
     const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;             // 0: columns 0..15 of the k-block, 1: columns 16..31
     const int r = quarter * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    int rs = (warp - 2) >> 2, ts = rs;          // this set's first k-block: 0 or 1
+    int rs = 0, ts = 0;
     uint32_t rph = 0, tph = 0;
-    for (int it = rs; it < total_it; it += 2) {
+    for (int it = 0; it < total_it; ++it) {
       mbar_wait(smem_u32(&full_raw[rs]), rph);
       const uint8_t* row = a_raw + (size_t)rs * GM_A_TILE + (size_t)r * 128;
-      uint32_t hi[32], lo[32];
+      uint32_t hi[16], lo[16];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {   // 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
-        const float4 x = *reinterpret_cast<const float4*>(row + ((c ^ (r & 7)) << 4));
+      for (int c = 0; c < 4; ++c) {   // 16-byte chunk c of row r sits at chunk position c ^ (r & 7)
+        const float4 x = *reinterpret_cast<const float4*>(row + (((4 * half + c) ^ (r & 7)) << 4));
         hi[4 * c + 0] = __float_as_uint(x.x);
         hi[4 * c + 1] = __float_as_uint(x.y);
         hi[4 * c + 2] = __float_as_uint(x.z);
         hi[4 * c + 3] = __float_as_uint(x.w);
       }
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
+      for (int j = 0; j < 16; ++j)
         lo[j] = __float_as_uint(__uint_as_float(hi[j]) - __uint_as_float(hi[j] & 0xffffe000u));
       // the raw stage is in registers: hand it back to every producer of the cluster
       __syncwarp();
@@ -270,19 +273,17 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
       mbar_wait(smem_u32(&ta_empty[ts]), tph ^ 1u);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + lane_addr + GM_TMEM_A0 + (uint32_t)(ts * 64);
+      const uint32_t taddr = tmem_base + lane_addr + GM_TMEM_A0 + (uint32_t)(ts * 64 + 16 * half);
       if (!GM_ABL(4)) {
-        tmem_st_x32(taddr, hi);
-        tmem_st_x32(taddr + 32, lo);
+        tmem_st_x16(taddr, hi);
+        tmem_st_x16(taddr + 32, lo);
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&ta_full[ts]));
-      rs += 2;
-      if (rs >= GM_RAW_STAGES) { rs -= GM_RAW_STAGES; rph ^= 1u; }
-      ts += 2;
-      if (ts >= GM_TM_STAGES) { ts -= GM_TM_STAGES; tph ^= 1u; }
+      if (++rs == GM_RAW_STAGES) { rs = 0; rph ^= 1u; }
+      if (++ts == GM_TM_STAGES) { ts = 0; tph ^= 1u; }
     }
   } else {
     // ===================================================================== epilogue warps
@@ -462,13 +463,16 @@ int lgnn_gemm_mask_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, c
   P.n_kb = k_pad / GM_BK;
   P.last_ksteps = (int)((k - (int64_t)(P.n_kb - 1) * GM_BK + 7) / 8);
   P.cl = (int)(n / GM_BN);
-  // tiles per cluster: a few waves over the clusters that fit the device at once — long enough to amortise a CTA's
-  // prologue (barriers, TMEM allocation, the 128 KB weight slice, two cluster syncs), short enough to balance the tail
+  // tiles per cluster: long enough to amortise a CTA's prologue (barriers, TMEM allocation, the 128 KB weight
+  // slice, two cluster syncs), short enough that many more clusters than fit the device at once exist — not every
+  // SM can join a 4-CTA cluster, and the tail of a few long work items costs more than the prologues of many short
+  // ones.  Measured at K = N = 256, 20 M rows: 32 or 256 tiles 15.0 ms, 1,056 tiles 16.2 ms, 4,096 tiles (one
+  // persistent wave) 23.5 ms (profiles/r2e_gemm_lab.txt)
   {
     const int64_t resident = sm_count() / P.cl > 0 ? sm_count() / P.cl : 1;
-    int64_t tpc = (P.tiles_total + resident * 4 - 1) / (resident * 4);
+    int64_t tpc = (P.tiles_total + resident * 16 - 1) / (resident * 16);
     if (tpc < 32) tpc = 32;
-    if (tpc > 4096) tpc = 4096;
+    if (tpc > 256) tpc = 256;
     if (const char* t = getenv("LGNN_GEMM_TILES_PER_CLUSTER")) { int v = atoi(t); if (v >= 1) tpc = v; }   // lab switch
     P.tiles_per_cluster = (int)tpc;
   }
@@ -503,3 +507,13 @@ int lgnn_gemm_mask_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, c
 }
 
 }  // extern "C"
+
+#if defined(LGNN_MBAR_DEBUG) && !defined(LGNN_GM_ABLATE)
+// debug builds only: {line, block, thread, barrier, parity, count} of the first timed-out mbarrier wait since the last call
+extern "C" int lgnn_debug_mbar_timeout(unsigned int* out8) {
+  unsigned int z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(out8, lgnn::g_mbar_timeout, sizeof(z)) != cudaSuccess) return -1;
+  if (cudaMemcpyToSymbol(lgnn::g_mbar_timeout, z, sizeof(z)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif

@@ -14,8 +14,7 @@ inline int& gm_lab_ablate() {
 #define GmParams GmLabParams
 #define gemm_mask_kernel gemm_mask_lab_kernel
 #define gemm_mask_prepare_kernel gemm_mask_lab_prepare_kernel
-#define tmem_st_x32 tmem_st_x32_lab
-#define tc_mma_tf32_ts tc_mma_tf32_ts_lab
+#define tmem_st_x16 tmem_st_x16_lab
 #define mbar_arrive_remote mbar_arrive_remote_lab
 #define lgnn_gemm_mask_supported lgnn_gemm_mask_lab_supported
 #define lgnn_gemm_mask_kpad lgnn_gemm_mask_lab_kpad

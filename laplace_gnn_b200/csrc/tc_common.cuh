@@ -20,6 +20,35 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // bounded wait: a protocol bug traps instead of hanging the GPU
+#ifdef LGNN_MBAR_DEBUG
+// Debug builds (-DLGNN_MBAR_DEBUG, tools/round2_*): a wait that times out records {source line, block, thread, barrier
+// offset} in a device word the host can read afterwards (lgnn_debug_mbar_timeout) and gives up instead of trapping —
+// a trap poisons the context and says nothing about WHICH barrier starved.
+static __device__ unsigned int g_mbar_timeout[8];
+__device__ __forceinline__ void mbar_wait_dbg(uint32_t bar, uint32_t parity, int line) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 21)) {
+      if (atomicCAS(&g_mbar_timeout[0], 0u, (unsigned)line) == 0u) {
+        g_mbar_timeout[1] = blockIdx.x;
+        g_mbar_timeout[2] = threadIdx.x;
+        g_mbar_timeout[3] = bar;
+        g_mbar_timeout[4] = parity;
+      }
+      atomicAdd(&g_mbar_timeout[5], 1u);
+      return;
+    }
+  }
+}
+#define mbar_wait(bar, parity) mbar_wait_dbg(bar, parity, __LINE__)
+#else
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   for (uint32_t spin = 0; !done; ++spin) {
@@ -33,6 +62,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (spin > (1u << 26)) __trap();
   }
 }
+#endif
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
                                             uint32_t bar) {
   asm volatile(

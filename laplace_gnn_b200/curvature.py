@@ -170,7 +170,7 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=True, sparse_halo=False):
+                    unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=False, fused_hess_spmm=True, sparse_halo=False):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -207,8 +207,9 @@ class _B200KFAC:
         # owns 6 of the products shape's 47 columns and would otherwise carry 8 (g = 6: 93.7 ms against 111 ms per
         # hidden layer, profiles/r2a_units_lab.txt; bit-identical to the dense SpMM, tests/test_gpu_units_even.py)
         self.unit_even_groups = bool(unit_even_groups)
-        # with a process group the stand-in KronLaplace can spread the factor eigendecompositions over the ranks
-        # (kron.Kron.decompose); OFF (replicated) until the all-gather has run over NCCL (gloo-tested only)
+        # with a process group the stand-in KronLaplace spreads the factor eigendecompositions over the ranks
+        # (kron.Kron.decompose: one in-place all-gather hands every rank the same eigenpairs, bit for bit — NCCL test
+        # tests/test_gpu_dist.py); shard_eigh=False keeps them replicated
         self.shard_eigh = bool(shard_eigh)
         # power-law graphs: the unit SpMM gives one warp group a whole row, so graphs with rows beyond
         # unit_row_limit non-zeros keep dense slabs — unless unit_hub_split cuts those rows into pieces
@@ -279,8 +280,9 @@ class _B200KFAC:
                     else:
                         z[:, :d_out] = torch.mm(h, Ws[l].t()) if bs[l] is None else torch.addmm(bs[l], h, Ws[l].t())
                         z[:, d_out:] = 0
-                out = _slab(h.device, 1000 + l, 1, n_rows * ldz).view(n_rows, ldz)
-                h = ops.spmm(g.ahat, z, relu=(l < L - 1), out=out)[:, :d_out]
+                rows_out = n_rows + g.extra_rows()          # hub rows of power-law graphs come back in pieces
+                out = _slab(h.device, 1000 + l, 1, rows_out * ldz).view(rows_out, ldz)
+                h = g.propagate(z, relu=(l < L - 1), out=out)[:, :d_out]
             else:
                 # row block of this rank: Z_l goes straight into this rank's slot of the padded all-gather slab,
                 # P_l / H_l into its slot of a second one (the column-parallel backward all-gathers that one in
@@ -651,7 +653,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=False, unit_hub_split=False, fused_hess_spmm=True, sparse_halo=False):
+                 unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=False, fused_hess_spmm=True, sparse_halo=False):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:

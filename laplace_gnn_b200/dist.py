@@ -193,7 +193,8 @@ def ingest_edge_index(host_edge_index: torch.Tensor, device, pg) -> torch.Tensor
     buf = torch.empty(world, 2, S, dtype=torch.int64, device=device)
     mine = buf[rank]
     if hi > lo:
-        mine[:, : hi - lo].copy_(host_edge_index[:, lo:hi], non_blocking=True)
+        for r in range(2):       # row by row: a [2, cols] slice of the pinned list is strided and would be staged on the host
+            mine[r, : hi - lo].copy_(host_edge_index[r, lo:hi], non_blocking=True)
         if hi - lo < S:
             mine[:, hi - lo:] = mine[:, :1]
     else:                                    # more ranks than edges: a copy of the list's first edge

@@ -27,12 +27,12 @@ class GCNConvFunction(torch.autograd.Function):
     def forward(ctx, z: torch.Tensor, graph: Graph) -> torch.Tensor:
         ctx.graph = graph
         with on_device_of(z):
-            return ops.spmm(graph.ahat, z.contiguous())
+            return graph.propagate(z.contiguous())
 
     @staticmethod
     def backward(ctx, grad_out: torch.Tensor):
         with on_device_of(grad_out):
-            return ops.spmm(ctx.graph.ahat_t, grad_out.contiguous()), None
+            return ctx.graph.propagate(grad_out.contiguous(), transpose=True), None
 
 
 class SparseGCNConv(nn.Module):

@@ -64,6 +64,46 @@ class Graph:
         return cls(int(num_nodes), deg, dis, at, a, symmetric or assume_undirected,
                    {"symmetrised": bool(symmetric)})
 
+    # ---- Â x / Â^T x with hub rows of power-law graphs cut into pieces -------------------------------------
+    HUB_ROW_LIMIT = 4096
+
+    def hub_split(self, transpose: bool = False):
+        """``SplitCSR`` of Â (or Â^T) when a row exceeds HUB_ROW_LIMIT non-zeros, else None; built once per graph."""
+        csr = self.ahat_t if transpose else self.ahat
+        if csr.max_row_nnz is None or csr.max_row_nnz <= self.HUB_ROW_LIMIT:
+            return None
+        cache = self.meta.setdefault("_hub_split", {})
+        key = "t" if (transpose and self.ahat_t is not self.ahat) else "n"
+        if key not in cache:
+            cache[key] = split_hub_rows(csr, self.HUB_ROW_LIMIT)
+        return cache[key]
+
+    def extra_rows(self, transpose: bool = False) -> int:
+        """Rows to add to an output buffer handed to ``propagate`` (the pieces of the hub rows)."""
+        sp = self.hub_split(transpose)
+        return 0 if sp is None else sp.n_extra
+
+    def propagate(self, x: torch.Tensor, transpose: bool = False, relu: bool = False,
+                  out: torch.Tensor | None = None) -> torch.Tensor:
+        """Â x (or Â^T x), optionally relu'd: the narrow SpMM of the forward / training step.  The warp-per-row
+        kernel gives one warp a whole row; on a power-law graph a hub row of 10^5 non-zeros then runs for the whole
+        launch (0.51 of the copy rate at d = 256 on R-MAT 2^22, round 1).  Hub rows are therefore cut into pieces of
+        HUB_ROW_LIMIT non-zeros (``split_hub_rows``: extra output rows behind the matrix, summed onto their owners
+        afterwards).  ``out``: optional buffer with ``n + extra_rows()`` rows; the result is its first n rows."""
+        csr = self.ahat_t if transpose else self.ahat
+        sp = self.hub_split(transpose)
+        if sp is None:
+            return ops.spmm(csr, x, relu=relu, out=out)
+        d = int(x.shape[1])
+        rows = self.n + sp.n_extra
+        if out is None or out.shape[0] < rows:
+            out = torch.empty(rows, d, dtype=torch.float32, device=x.device)
+        ops.spmm(sp.csr, x, out=out)
+        y = sp.finish(out, d)
+        if relu:
+            torch.relu_(y[:, :d])
+        return y
+
     def partition_bounds(self, nparts: int) -> torch.Tensor:
         """nnz-balanced contiguous row blocks of Â (int64 [nparts+1], device)."""
         return ops.row_partition(self.ahat.rowptr, nparts)

@@ -803,3 +803,43 @@ def test_node_factorised_diag_is_exact_without_edges_and_close_to_bruteforce(fak
     assert torch.isfinite(la.log_marginal_likelihood())
     with pytest.raises(ValueError):
         L.B200GGN(model, "classification", diag_mode="fast")
+
+
+def test_hub_rows_are_split_for_the_narrow_forward_spmm(fake_ops):
+    """Graph.propagate: on a graph with rows beyond HUB_ROW_LIMIT the forward / training-step SpMM runs over the
+    split matrix (pieces as extra rows, summed afterwards, relu after the sum) and gives what the plain SpMM gives;
+    the fit built on it reproduces the factors of the unsplit graph."""
+    import laplace_gnn_b200 as L
+    from laplace_gnn_b200 import ops
+    from oracle import gcn_kfac_oracle as O
+    n = 500
+    ei = torch.from_numpy(O.synthetic_edges(n, 4000, seed=11, rmat=True, directed=True))
+    plain, split = L.Graph.from_edge_index(ei, n), L.Graph.from_edge_index(ei, n)
+    split.HUB_ROW_LIMIT = 16
+    assert plain.hub_split() is None and split.hub_split() is not None and split.extra_rows() > 0
+    assert split.hub_split(transpose=True) is not None
+    x = torch.randn(n, 12)
+    for t in (False, True):
+        want = ops.spmm(plain.ahat_t if t else plain.ahat, x)
+        got = split.propagate(x, transpose=t)
+        assert got.shape == want.shape and max_rel_err(got.numpy(), want.numpy()) <= 1e-6
+        assert max_rel_err(split.propagate(x, transpose=t, relu=True).numpy(), want.clamp(min=0).numpy()) <= 1e-6
+        buf = torch.full((n + split.extra_rows(t), 12), -7.0)
+        assert split.propagate(x, transpose=t, out=buf).data_ptr() == buf.data_ptr()
+    gen = torch.Generator().manual_seed(0)
+    X = torch.randn(n, 9, generator=gen)
+    idx = torch.randperm(n, generator=gen)[:300].sort().values
+    y = torch.randint(0, 4, (300,), generator=gen)
+    res = []
+    for g in (plain, split):
+        torch.manual_seed(0)
+        model = L.SparseGCN(9, 32, 4, 3, X, g)
+        model(idx).sum().backward()                                       # training forward / backward through propagate
+        la = L.Laplace(model, "classification", backend=L.B200GGN)
+        la.fit(L.TensorBatchLoader(idx, y))
+        res.append((float(la.log_marginal_likelihood()), la.H_facs.kfacs, model.convs[0].lin.weight.grad.clone()))
+    assert abs(res[0][0] - res[1][0]) <= 1e-5 * abs(res[0][0])
+    assert max_rel_err(res[1][2].numpy(), res[0][2].numpy()) <= 1e-5
+    for fa, fb in zip(res[0][1], res[1][1]):
+        for a, b in zip(fa, fb):
+            assert max_rel_err(b.numpy(), a.numpy()) <= 1e-5
