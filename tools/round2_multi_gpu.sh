@@ -1,14 +1,17 @@
 #!/bin/bash
-# Multi-GPU pass of round 2 (gpurun --gpus N): NCCL parity tests (incl. the lab switches), then the DRIVER's bench
-# command at N ranks (--steps 20 --warmup 5: the run that ran out of memory at N = 2 / 4 in round 1), then switches.
-#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'bash tools/round2_multi_gpu.sh 2'
+# Multi-GPU pass of round 2 (gpurun --gpus N): NCCL parity tests, then the DRIVER's bench command at N ranks
+# (--steps 20 --warmup 5: the run that ran out of memory at N = 2 / 4 in round 1), then single switches.
+#   /usr/local/graft/bin/gpurun --gpus 8 --timeout 900 -- 'bash tools/round2_multi_gpu.sh 8 full'
 set -u
 N=${1:-8}
+MODE=${2:-full}
 mkdir -p gpurun_out
 P=29540
-S=$(date +%s)
-LGNN_LAB=1 timeout 600 python -m pytest tests/test_gpu_dist.py -x -q > gpurun_out/r2_n${N}_tests.log 2>&1; echo "multi-GPU tests (incl. lab switches over NCCL) rc=$? in $(( $(date +%s) - S )) s"
-tail -3 gpurun_out/r2_n${N}_tests.log | cut -c1-200
+if [ "$MODE" = full ]; then
+  S=$(date +%s)
+  timeout 600 python -m pytest tests/test_gpu_dist.py -x -q > gpurun_out/r2_n${N}_tests.log 2>&1; echo "multi-GPU tests rc=$? in $(( $(date +%s) - S )) s"
+  tail -3 gpurun_out/r2_n${N}_tests.log | cut -c1-200
+fi
 bench() {  # tag, steps, warmup, extra flags...
   local tag=$1 steps=$2 warm=$3; shift 3
   local S=$(date +%s)
@@ -19,21 +22,17 @@ bench() {  # tag, steps, warmup, extra flags...
 import json, sys
 try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+    e = d.get("e2e") or {}
     print("   ", round(d["value"]), "nodes/s", round(d["ms_per_step"], 1), "ms  marglik", d["marglik"], d["roofline"]["ms_per_step_by_kind"],
-          "parity", d.get("parity"), "alloc", d.get("allocator_in_timed_region"), "e2e", (d.get("e2e") or {}).get("value"))
+          "parity", (d.get("parity") or {}).get("ok"), "alloc", d.get("allocator_in_timed_region"), "e2e", e.get("value"), e.get("ms_per_step"))
 except Exception as e:
     print("    no bench line:", e)
 PY
-  tail -4 "gpurun_out/r2_n${N}_$tag.err" | cut -c1-300
+  grep -vE "^\s*$|OMP_NUM|\*\*\*\*|Warning|sparse_csr|warn" "gpurun_out/r2_n${N}_$tag.err" | tail -4 | cut -c1-300
   P=$((P + 1))
 }
 bench driver 20 5
-bench shard_eigh 5 3 --no-e2e --no-parity --shard-eigh
-bench pad4 5 3 --no-e2e --no-parity --no-unit-even-groups
-bench rows 5 3 --no-e2e --no-parity --backward-parallel rows
-# single-GPU extras riding on this call: the unicast variant of the fused GEMM against the multicast one
-if [ "${EXTRA_GEMM_LAB:-0}" = "1" ]; then
-  timeout 200 python tools/gemm_lab.py > gpurun_out/r2_gemm_lab_mc.log 2>&1; head -4 gpurun_out/r2_gemm_lab_mc.log | cut -c1-200
-  LGNN_GEMM_UNICAST=1 timeout 200 python tools/gemm_lab.py > gpurun_out/r2_gemm_lab_uc.log 2>&1; head -4 gpurun_out/r2_gemm_lab_uc.log | cut -c1-200
-  LGNN_GEMM_UNICAST=1 timeout 300 python -m pytest tests/test_gpu_parity.py -q -x -k "gemm" > gpurun_out/r2_gemm_uc_tests.log 2>&1; tail -2 gpurun_out/r2_gemm_uc_tests.log | cut -c1-200
+if [ "$MODE" = full ]; then
+  bench pad4 5 3 --no-e2e --no-parity --no-unit-even-groups
+  bench replicated_eigh 5 3 --no-e2e --no-parity --no-shard-eigh
 fi

@@ -9,8 +9,8 @@ timeout 600 python -m pytest tests/test_gpu_dist.py -x -q > gpurun_out/r2d_n${N}
 tail -3 gpurun_out/r2d_n${N}_tests.log | cut -c1-200
 for tag in rows_noov rows_ov; do
   fl="--backward-parallel rows"; [ $tag = rows_noov ] && fl="$fl --no-overlap"
-  CUDA_LAUNCH_BLOCKING=1 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P \
-      bench.py --gpus $N --steps 1 --warmup 1 --no-e2e --no-parity $fl > gpurun_out/r2d_n${N}_$tag.log 2>gpurun_out/r2d_n${N}_$tag.err
+  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P \
+      bench.py --gpus $N --steps 5 --warmup 3 --no-e2e --no-parity $fl > gpurun_out/r2d_n${N}_$tag.log 2>gpurun_out/r2d_n${N}_$tag.err
   echo "$tag rc=$?"; P=$((P + 1))
   grep -E "LgnnError|Error|File \"/.*laplace_gnn_b200|File \"/.*bench.py" gpurun_out/r2d_n${N}_$tag.err | head -12 | cut -c1-260
   python - "gpurun_out/r2d_n${N}_$tag.log" <<'PY'
