@@ -19,14 +19,20 @@
 //
 // Pipeline per CTA (14 warps):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes [BK rows x NP cols] of raw fp32 into a
-//               4-deep shared-memory ring (out-of-bounds rows / columns arrive as zeros, which makes
+//               6-deep shared-memory ring (out-of-bounds rows / columns arrive as zeros, which makes
 //               every edge case — row tail, n not a multiple of 16 — free);
-//   warps 2..5  transform: read a raw box, split hi / lo, write both as K-major no-swizzle UMMA
-//               operands (8-row x 16-byte core matrices, padded 144-byte group stride so the 128-bit
-//               transposed stores are bank-conflict free) into a 3-deep operand ring;
-//   warp 1      one elected lane issues, per 8-wide k-step and per M block, three tcgen05.mma
-//               (hi.hi, hi.lo, lo.hi; A and B descriptors point into the SAME operand buffers because
-//               both operands are X), then tcgen05.commit frees the operand stage;
+//   warps 2..5  transform: thread = feature = TMEM lane.  It reads its COLUMN of the raw box (16 values,
+//               consecutive lanes -> consecutive words), splits hi / lo and writes the operand twice:
+//               (A) into TENSOR MEMORY (tcgen05.st: lane = feature, column = row of the box) for the M side,
+//               (B) as K-major no-swizzle UMMA operand rows in shared memory (8-row x 16-byte core matrices,
+//               padded 144-byte group stride) for the N side; a 2-deep operand ring;
+//   warp 1      the whole warp walks the loop, one elected lane issues, per 8-wide k-step and per M block,
+//               three tcgen05.mma with A FROM TMEM and B from shared memory (hi.hi, hi.lo, lo.hi), then
+//               tcgen05.commit frees the operand stage.  (Round 1 took both operands from shared memory:
+//               120 KB of operand reads per 16-row step on top of the transform's 64 KB is more than the
+//               128 B/clk an SM's shared memory delivers in the 1,152 cycles the step's MMAs take — ncu showed
+//               8.5-way "bank conflicts" on conflict-free loads and the tensor pipe 57 % busy.  With A in TMEM
+//               the MMAs read 72 KB per step.)
 //   warps 6..13 epilogue, once per segment: tcgen05.ld the accumulator (two warps per 32-lane TMEM
 //               quarter, alternating 16-column chunks) and add it into this CTA's zero-initialised
 //               partial n x NP block with fire-and-forget red.global.add.v4.f32 (RN adds in L2; every
@@ -46,8 +52,8 @@
 namespace lgnn {
 
 constexpr int TC_BK = 16;          // rows of X per pipeline stage (two k=8 UMMA steps)
-constexpr int TC_RAW_STAGES = 4;
-constexpr int TC_OP_STAGES = 3;
+constexpr int TC_RAW_STAGES = 6;
+constexpr int TC_OP_STAGES = 2;    // operand stages: B rows in shared memory + A columns in TMEM (32 per M block)
 constexpr int TC_SBO = 144;        // byte stride between 8-row core-matrix groups (128 + 16 pad)
 constexpr int TC_THREADS = 448;
 constexpr int TC_TRANSFORM_THREADS = 128;
@@ -59,7 +65,8 @@ struct TcGeom {
   int lbo;              // byte stride between the 16-byte k-chunks of one row group set
   int op_bytes;         // bytes of one (hi or lo) operand stage
   int raw_bytes;        // bytes of one raw stage
-  int tmem_cols;        // power of two >= mb*np, >= 32
+  int tmem_cols;        // power of two >= accumulator columns + A operand stages, >= 32
+  int a_col0;           // first TMEM column of the A operand stages (behind the accumulators)
   size_t smem_bytes;
 };
 
@@ -73,6 +80,9 @@ static TcGeom tc_geom(int n) {
   g.op_bytes = (TC_BK / 4) * g.lbo;
   g.raw_bytes = TC_BK * g.np * 4;
   int cols = g.mb == 1 ? g.np : g.np + (g.np - 128);   // block 1 only holds columns 128..np-1
+  cols = (cols + 31) / 32 * 32;                        // A operand stages start on a 32-column boundary
+  g.a_col0 = cols;
+  cols += TC_OP_STAGES * g.mb * 32;                    // per stage and M block: 16 columns hi + 16 columns lo
   g.tmem_cols = 32;
   while (g.tmem_cols < cols) g.tmem_cols <<= 1;
   g.smem_bytes = 1024 /*align slack*/ + (size_t)TC_RAW_STAGES * g.raw_bytes +
@@ -90,11 +100,20 @@ static TcGeom tc_geom(int n) {
 #define TC_ABL(bit) false
 #endif
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
 struct TcParams {
 #ifdef LGNN_TC_ABLATE
   int ablate;
 #endif
-  int n, np, mb, lbo, op_bytes, raw_bytes, tmem_cols;
+  int n, np, mb, lbo, op_bytes, raw_bytes, tmem_cols, a_col0;
   int seg_steps;     // steps per TMEM accumulation segment
   int64_t steps_total;
   int64_t steps_per_cta;
@@ -191,28 +210,31 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
         tc_fence_after();
         const uint32_t hi = op0 + (uint32_t)st * 2u * (uint32_t)P.op_bytes;
         const uint32_t lo = hi + P.op_bytes;
+        const uint32_t a_st = tb + (uint32_t)P.a_col0 + (uint32_t)(st * P.mb * 32);   // A stage: [block][hi 16 | lo 16]
 #pragma unroll
         for (int ks = 0; ks < TC_BK / 8; ++ks) {
           const uint32_t koff = (uint32_t)ks * 2u * (uint32_t)P.lbo;  // two 16-byte k-chunks per k=8 step
           const uint32_t acc = (seg_first && ks == 0) ? 0u : 1u;
-          {  // M block 0: rows 0..127 x columns 0..np-1
-            const uint64_t a_hi = make_smem_desc(hi + koff, lbo, sbo);
-            const uint64_t a_lo = make_smem_desc(lo + koff, lbo, sbo);
-            if (!TC_ABL(1)) tc_mma_tf32_e(tb, a_hi, a_hi, idesc0, acc);
+          {  // M block 0: features 0..127 (TMEM) x features 0..np-1 (shared memory)
+            const uint64_t b_hi = make_smem_desc(hi + koff, lbo, sbo);
+            const uint64_t b_lo = make_smem_desc(lo + koff, lbo, sbo);
+            const uint32_t a_hi = a_st + (uint32_t)(ks * 8), a_lo = a_hi + 16u;
+            if (!TC_ABL(1)) tc_mma_tf32_ts_e(tb, a_hi, b_hi, idesc0, acc);
             if (!TC_ABL(1) && !TC_ABL(2)) {
-              tc_mma_tf32_e(tb, a_hi, a_lo, idesc0, 1u);
-              tc_mma_tf32_e(tb, a_lo, a_hi, idesc0, 1u);
+              tc_mma_tf32_ts_e(tb, a_hi, b_lo, idesc0, 1u);
+              tc_mma_tf32_ts_e(tb, a_lo, b_hi, idesc0, 1u);
             }
           }
-          if (P.mb == 2) {  // M block 1: rows 128..255 x columns 128..np-1 (128 rows = 16 groups)
+          if (P.mb == 2) {  // M block 1: features 128..255 x features 128..np-1 (B rows 128.. = 16 groups on)
             const uint32_t off = koff + 16u * TC_SBO;
-            const uint64_t a_hi = make_smem_desc(hi + off, lbo, sbo);
-            const uint64_t a_lo = make_smem_desc(lo + off, lbo, sbo);
+            const uint64_t b_hi = make_smem_desc(hi + off, lbo, sbo);
+            const uint64_t b_lo = make_smem_desc(lo + off, lbo, sbo);
+            const uint32_t a_hi = a_st + 32u + (uint32_t)(ks * 8), a_lo = a_hi + 16u;
             const uint32_t d = tb + (uint32_t)P.np;
-            if (!TC_ABL(1)) tc_mma_tf32_e(d, a_hi, a_hi, idesc1, acc);
+            if (!TC_ABL(1)) tc_mma_tf32_ts_e(d, a_hi, b_hi, idesc1, acc);
             if (!TC_ABL(1) && !TC_ABL(2)) {
-              tc_mma_tf32_e(d, a_hi, a_lo, idesc1, 1u);
-              tc_mma_tf32_e(d, a_lo, a_hi, idesc1, 1u);
+              tc_mma_tf32_ts_e(d, a_hi, b_lo, idesc1, 1u);
+              tc_mma_tf32_ts_e(d, a_lo, b_hi, idesc1, 1u);
             }
           }
         }
@@ -226,46 +248,54 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
     }
   } else if (warp < 6) {
     // ===================================================================== transform warps
-    const int t = threadIdx.x - 64;  // 0..127
-    const int np4 = P.np >> 2;
-    const int items = (TC_BK / 4) * np4;
+    // thread = feature = TMEM lane: warp w owns lanes 32 (w & 3) .. + 31, i.e. feature f = 128 m + 32 (w & 3) + lane
+    // of M block m.  Per step it reads column f of the raw box (TC_BK values), and writes them (A) to its TMEM lane
+    // and (B) as row f of the K-major shared-memory operand, hi and lo each.
+    const int fl = (warp & 3) * 32 + lane;                                  // lane inside an M block
+    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     int rs = 0, os = 0;
     uint32_t rph = 0, oph = 0;
     for (int s = 0; s < (int)my_steps; ++s) {
       mbar_wait(smem_u32(&full_raw[rs]), rph);
       mbar_wait(smem_u32(&empty_op[os]), oph ^ 1);
+      tc_fence_after();
       const float* raw = reinterpret_cast<const float*>(raw_base + (size_t)rs * P.raw_bytes);
       uint8_t* hi = op_base + (size_t)os * 2 * P.op_bytes;
       uint8_t* lo = hi + P.op_bytes;
-      for (int it = t; it < items; it += TC_TRANSFORM_THREADS) {
-        const int kq = it / np4, i4 = it - kq * np4;
-        float4 r[4];
+      for (int m = 0; m < P.mb; ++m) {
+        const int f = m * 128 + fl;
+        uint32_t vh[TC_BK], vl[TC_BK];
+        if (f < P.np) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          r[q] = *reinterpret_cast<const float4*>(raw + (size_t)(4 * kq + q) * P.np + 4 * i4);
-        const float v[4][4] = {{r[0].x, r[1].x, r[2].x, r[3].x},
-                               {r[0].y, r[1].y, r[2].y, r[3].y},
-                               {r[0].z, r[1].z, r[2].z, r[3].z},
-                               {r[0].w, r[1].w, r[2].w, r[3].w}};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = 4 * i4 + j;
-          const uint32_t off = (uint32_t)(i >> 3) * TC_SBO + (uint32_t)kq * (uint32_t)P.lbo + (uint32_t)(i & 7) * 16u;
-          float4 h, l;
-          h.x = __uint_as_float(__float_as_uint(v[j][0]) & 0xffffe000u);
-          h.y = __uint_as_float(__float_as_uint(v[j][1]) & 0xffffe000u);
-          h.z = __uint_as_float(__float_as_uint(v[j][2]) & 0xffffe000u);
-          h.w = __uint_as_float(__float_as_uint(v[j][3]) & 0xffffe000u);
-          l.x = v[j][0] - h.x;
-          l.y = v[j][1] - h.y;
-          l.z = v[j][2] - h.z;
-          l.w = v[j][3] - h.w;
-          if (!TC_ABL(4)) {
-            *reinterpret_cast<float4*>(hi + off) = h;
-            *reinterpret_cast<float4*>(lo + off) = l;
+          for (int r = 0; r < TC_BK; ++r) {
+            const float x = raw[r * P.np + f];
+            const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+            vh[r] = __float_as_uint(h);
+            vl[r] = __float_as_uint(x - h);
           }
+          if (!TC_ABL(4)) {
+            const uint32_t off = (uint32_t)(f >> 3) * TC_SBO + (uint32_t)(f & 7) * 16u;
+#pragma unroll
+            for (int kq = 0; kq < TC_BK / 4; ++kq) {
+              *reinterpret_cast<uint4*>(hi + off + (uint32_t)kq * (uint32_t)P.lbo) =
+                  make_uint4(vh[4 * kq], vh[4 * kq + 1], vh[4 * kq + 2], vh[4 * kq + 3]);
+              *reinterpret_cast<uint4*>(lo + off + (uint32_t)kq * (uint32_t)P.lbo) =
+                  make_uint4(vl[4 * kq], vl[4 * kq + 1], vl[4 * kq + 2], vl[4 * kq + 3]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < TC_BK; ++r) vh[r] = vl[r] = 0u;
+        }
+        // (A) lane = feature, 16 columns hi then 16 columns lo of this stage and block (warp-collective)
+        const uint32_t taddr = tmem_base + lane_addr + (uint32_t)P.a_col0 + (uint32_t)(os * P.mb * 32 + m * 32);
+        if (!TC_ABL(4)) {
+          tmem_st16(taddr, vh);
+          tmem_st16(taddr + 16, vl);
         }
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor-core (async) proxy
       __syncwarp();
       if (lane == 0) {
@@ -383,6 +413,7 @@ int syrk_tcgen05_launch(const float* x, int64_t ldx, int64_t k_rows, int n, floa
 #endif
   P.n = n; P.np = g.np; P.mb = g.mb; P.lbo = g.lbo; P.op_bytes = g.op_bytes; P.raw_bytes = g.raw_bytes;
   P.tmem_cols = g.tmem_cols;
+  P.a_col0 = g.a_col0;
   P.seg_steps = TC_SEG_STEPS_DEFAULT;
   if (const char* sg = getenv("LGNN_SYRK_SEG_STEPS")) {  // accuracy / speed experiments
     int v = atoi(sg);
