@@ -286,85 +286,9 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       if (++ts == GM_TM_STAGES) { ts = 0; tph ^= 1u; }
     }
   } else {
-#ifdef LGNN_GM_EPI_DIRECT
-    // ===================================================================== epilogue warps (direct variant)
-    // thread = tile row = TMEM lane: it masks and stores its own 64 contiguous floats (256 bytes) straight from the
-    // registers tcgen05.ld filled — no shared-memory staging (the kernel's shared-memory bandwidth is what the MMA
-    // operand reads, the TMA writes and the transform reads already oversubscribe), no warp syncs, a quarter of the
-    // instructions.  One store instruction touches 32 rows x 16 bytes; the 16 stores of a row fill its two 128-byte
-    // lines back to back, L2 merges them.
-    const int quarter = warp & 3;
-    const bool masked = P.act != nullptr;
-    float4 mk[16];                   // relu' mask source of one tile for this thread's row (64 floats)
-    auto fetch_mask = [&](int t) {
-      const int64_t row = (tile_beg + t) * GM_BM + quarter * 32 + lane;
-      const bool ok = t < n_tiles && row < P.m_rows;
-      const float* src = P.act + (int64_t)((uint32_t)row / (uint32_t)P.group) * P.ld_act + n0;
-#pragma unroll
-      for (int q = 0; q < 16; ++q)
-        mk[q] = ok ? __ldg(reinterpret_cast<const float4*>(src + 4 * q)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    if (masked) fetch_mask(0);
-    for (int t = 0; t < n_tiles; ++t) {
-      const int as = t & 1;
-      const uint32_t aph = (uint32_t)((t >> 1) & 1);
-      const int64_t row = (tile_beg + t) * GM_BM + quarter * 32 + lane;
-      unsigned long long keep = ~0ull;   // bit c <-> column n0 + c survives
-      if (masked) {
-        keep = 0ull;
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const unsigned long long b4 = (mk[q].x > 0.f ? 1ull : 0ull) | (mk[q].y > 0.f ? 2ull : 0ull) |
-                                        (mk[q].z > 0.f ? 4ull : 0ull) | (mk[q].w > 0.f ? 8ull : 0ull);
-          keep |= b4 << (4 * q);
-        }
-        fetch_mask(t + 1);               // in flight during this tile's TMEM drain and stores
-      }
-      mbar_wait(smem_u32(&acc_full[as]), aph);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * GM_BN);
-      float* dst = P.out + row * P.ldo + n0;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-            : "r"(taddr + (uint32_t)(32 * h)));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-        for (int q = 0; q < 2; ++q)   // pin the uses of v[] behind the wait (volatile asms keep their order)
-          asm volatile("" : "+r"(v[16 * q + 0]), "+r"(v[16 * q + 1]), "+r"(v[16 * q + 2]), "+r"(v[16 * q + 3]),
-                            "+r"(v[16 * q + 4]), "+r"(v[16 * q + 5]), "+r"(v[16 * q + 6]), "+r"(v[16 * q + 7]),
-                            "+r"(v[16 * q + 8]), "+r"(v[16 * q + 9]), "+r"(v[16 * q + 10]), "+r"(v[16 * q + 11]),
-                            "+r"(v[16 * q + 12]), "+r"(v[16 * q + 13]), "+r"(v[16 * q + 14]), "+r"(v[16 * q + 15]));
-        if (h == 1) {   // the whole accumulator has left TMEM: hand the buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(smem_u32(&acc_empty[as]));
-        }
-        if (row < P.m_rows && !GM_ABL(8)) {
-          const unsigned kb32 = (unsigned)(keep >> (32 * h));
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o;
-            o.x = (kb32 >> (4 * j + 0)) & 1u ? __uint_as_float(v[4 * j + 0]) : 0.f;
-            o.y = (kb32 >> (4 * j + 1)) & 1u ? __uint_as_float(v[4 * j + 1]) : 0.f;
-            o.z = (kb32 >> (4 * j + 2)) & 1u ? __uint_as_float(v[4 * j + 2]) : 0.f;
-            o.w = (kb32 >> (4 * j + 3)) & 1u ? __uint_as_float(v[4 * j + 3]) : 0.f;
-            *reinterpret_cast<float4*>(dst + 32 * h + 4 * j) = o;
-          }
-        }
-      }
-    }
-  }
-#else
     // ===================================================================== epilogue warps
+    // (A variant in which every thread stores its own row straight from the tcgen05.ld registers — no staging —
+    // was 7 % slower at K = 256 and 15 % faster at K = 47, profiles/r2h_gemm_epilogue_ab.txt; not kept.)
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
     uint8_t* my_stg = stg + (size_t)(warp - 10) * GM_STG_WARP;
     const int sub_r = lane >> 2, sub_c = lane & 3;
@@ -456,7 +380,6 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     }
   }
-#endif
   tc_fence_before();
   __syncthreads();
   if (cl > 1) cluster_sync_all();   // nobody leaves while a peer may still multicast into it / arrive on it

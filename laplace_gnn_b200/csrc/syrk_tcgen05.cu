@@ -17,11 +17,11 @@
 // Only the upper block-triangle is computed: M block 0 (rows 0..127) against all np columns, M block
 // 1 (rows 128..255) against columns 128..np-1 only — 25 % fewer MMAs and TMEM columns at n = 256.
 //
-// Pipeline per CTA (14 warps):
+// Pipeline per CTA (18 warps):
 //   warp 0      TMA producer: cp.async.bulk.tensor 2-D boxes [BK rows x NP cols] of raw fp32 into a
 //               6-deep shared-memory ring (out-of-bounds rows / columns arrive as zeros, which makes
 //               every edge case — row tail, n not a multiple of 16 — free);
-//   warps 2..5  transform: thread = feature = TMEM lane.  It reads its COLUMN of the raw box (16 values,
+//   warps 2..9  transform (2..5: features 0..127, 6..9: features 128..255): thread = feature = TMEM lane.  It reads its COLUMN of the raw box (16 values,
 //               consecutive lanes -> consecutive words), splits hi / lo and writes the operand twice:
 //               (A) into TENSOR MEMORY (tcgen05.st: lane = feature, column = row of the box) for the M side,
 //               (B) as K-major no-swizzle UMMA operand rows in shared memory (8-row x 16-byte core matrices,
@@ -33,7 +33,7 @@
 //               128 B/clk an SM's shared memory delivers in the 1,152 cycles the step's MMAs take — ncu showed
 //               8.5-way "bank conflicts" on conflict-free loads and the tensor pipe 57 % busy.  With A in TMEM
 //               the MMAs read 72 KB per step.)
-//   warps 6..13 epilogue, once per segment: tcgen05.ld the accumulator (two warps per 32-lane TMEM
+//   warps 10..17 epilogue, once per segment: tcgen05.ld the accumulator (two warps per 32-lane TMEM
 //               quarter, alternating 16-column chunks) and add it into this CTA's zero-initialised
 //               partial n x NP block with fire-and-forget red.global.add.v4.f32 (RN adds in L2; every
 //               address is only ever touched by one thread, so the order of adds — and the result —
@@ -55,8 +55,7 @@ constexpr int TC_BK = 16;          // rows of X per pipeline stage (two k=8 UMMA
 constexpr int TC_RAW_STAGES = 6;
 constexpr int TC_OP_STAGES = 2;    // operand stages: B rows in shared memory + A columns in TMEM (32 per M block)
 constexpr int TC_SBO = 144;        // byte stride between 8-row core-matrix groups (128 + 16 pad)
-constexpr int TC_THREADS = 448;
-constexpr int TC_TRANSFORM_THREADS = 128;
+constexpr int TC_THREADS = 576;            // 1 TMA + 1 MMA + 8 transform + 8 epilogue warps
 constexpr int TC_EPILOGUE_WARPS = 8;
 constexpr int TC_SEG_STEPS_DEFAULT = 32;  // 32 steps x 2 k-steps x 3 products = 192 accumulates per chain
 
@@ -145,10 +144,10 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TC_RAW_STAGES; ++i) {
       mbar_init(smem_u32(&full_raw[i]), 1);
-      mbar_init(smem_u32(&empty_raw[i]), TC_TRANSFORM_THREADS / 32);
+      mbar_init(smem_u32(&empty_raw[i]), (uint32_t)(4 * P.mb));
     }
     for (int i = 0; i < TC_OP_STAGES; ++i) {
-      mbar_init(smem_u32(&full_op[i]), TC_TRANSFORM_THREADS / 32);
+      mbar_init(smem_u32(&full_op[i]), (uint32_t)(4 * P.mb));
       mbar_init(smem_u32(&empty_op[i]), 1);
     }
     mbar_init(smem_u32(acc_full), 1);
@@ -246,24 +245,25 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
         if (++st == TC_OP_STAGES) { st = 0; ph ^= 1u; }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // ===================================================================== transform warps
-    // thread = feature = TMEM lane: warp w owns lanes 32 (w & 3) .. + 31, i.e. feature f = 128 m + 32 (w & 3) + lane
-    // of M block m.  Per step it reads column f of the raw box (TC_BK values), and writes them (A) to its TMEM lane
-    // and (B) as row f of the K-major shared-memory operand, hi and lo each.
-    const int fl = (warp & 3) * 32 + lane;                                  // lane inside an M block
-    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-    int rs = 0, os = 0;
-    uint32_t rph = 0, oph = 0;
-    for (int s = 0; s < (int)my_steps; ++s) {
-      mbar_wait(smem_u32(&full_raw[rs]), rph);
-      mbar_wait(smem_u32(&empty_op[os]), oph ^ 1);
-      tc_fence_after();
-      const float* raw = reinterpret_cast<const float*>(raw_base + (size_t)rs * P.raw_bytes);
-      uint8_t* hi = op_base + (size_t)os * 2 * P.op_bytes;
-      uint8_t* lo = hi + P.op_bytes;
-      for (int m = 0; m < P.mb; ++m) {
-        const int f = m * 128 + fl;
+    // thread = feature = TMEM lane: warps 2-5 own M block 0 (features 0..127), warps 6-9 M block 1 (features
+    // 128..255; idle when n <= 128); warp w holds TMEM lanes 32 (w & 3) .. + 31.  Per step a thread reads column f
+    // of the raw box (TC_BK values: consecutive lanes -> consecutive words) and writes them (A) to its TMEM lane and
+    // (B) as row f of the K-major shared-memory operand, hi and lo each.  Every step is handled by every active warp,
+    // in order.  (One set of four warps doing both blocks was latency-bound on its own chain — wait, 32 loads, split,
+    // 16 stores, tcgen05.st, wait::st, fence, arrive: 1,390 cycles per step against 1,152 for the step's MMAs,
+    // profiles/r2h_syrk_lab_a_in_tmem.txt.)
+    const int m = (warp - 2) >> 2;
+    if (m < P.mb) {
+      const int f = m * 128 + (warp & 3) * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+      const uint32_t boff = (uint32_t)(f >> 3) * TC_SBO + (uint32_t)(f & 7) * 16u;
+      int rs = 0, os = 0;
+      uint32_t rph = 0, oph = 0;
+      for (int s = 0; s < (int)my_steps; ++s) {
+        mbar_wait(smem_u32(&full_raw[rs]), rph);
+        const float* raw = reinterpret_cast<const float*>(raw_base + (size_t)rs * P.raw_bytes);
         uint32_t vh[TC_BK], vl[TC_BK];
         if (f < P.np) {
 #pragma unroll
@@ -273,19 +273,25 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
             vh[r] = __float_as_uint(h);
             vl[r] = __float_as_uint(x - h);
           }
-          if (!TC_ABL(4)) {
-            const uint32_t off = (uint32_t)(f >> 3) * TC_SBO + (uint32_t)(f & 7) * 16u;
-#pragma unroll
-            for (int kq = 0; kq < TC_BK / 4; ++kq) {
-              *reinterpret_cast<uint4*>(hi + off + (uint32_t)kq * (uint32_t)P.lbo) =
-                  make_uint4(vh[4 * kq], vh[4 * kq + 1], vh[4 * kq + 2], vh[4 * kq + 3]);
-              *reinterpret_cast<uint4*>(lo + off + (uint32_t)kq * (uint32_t)P.lbo) =
-                  make_uint4(vl[4 * kq], vl[4 * kq + 1], vl[4 * kq + 2], vl[4 * kq + 3]);
-            }
-          }
         } else {
 #pragma unroll
           for (int r = 0; r < TC_BK; ++r) vh[r] = vl[r] = 0u;
+        }
+        // the raw box is in registers
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&empty_raw[rs]));
+        mbar_wait(smem_u32(&empty_op[os]), oph ^ 1);
+        tc_fence_after();
+        if (f < P.np && !TC_ABL(4)) {
+          uint8_t* hi = op_base + (size_t)os * 2 * P.op_bytes;
+          uint8_t* lo = hi + P.op_bytes;
+#pragma unroll
+          for (int kq = 0; kq < TC_BK / 4; ++kq) {
+            *reinterpret_cast<uint4*>(hi + boff + (uint32_t)kq * (uint32_t)P.lbo) =
+                make_uint4(vh[4 * kq], vh[4 * kq + 1], vh[4 * kq + 2], vh[4 * kq + 3]);
+            *reinterpret_cast<uint4*>(lo + boff + (uint32_t)kq * (uint32_t)P.lbo) =
+                make_uint4(vl[4 * kq], vl[4 * kq + 1], vl[4 * kq + 2], vl[4 * kq + 3]);
+          }
         }
         // (A) lane = feature, 16 columns hi then 16 columns lo of this stage and block (warp-collective)
         const uint32_t taddr = tmem_base + lane_addr + (uint32_t)P.a_col0 + (uint32_t)(os * P.mb * 32 + m * 32);
@@ -293,22 +299,19 @@ syrk_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap, const TcParams P) 
           tmem_st16(taddr, vh);
           tmem_st16(taddr + 16, vl);
         }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&full_op[os]));
+        if (++rs == TC_RAW_STAGES) { rs = 0; rph ^= 1u; }
+        if (++os == TC_OP_STAGES) { os = 0; oph ^= 1u; }
       }
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor-core (async) proxy
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(smem_u32(&full_op[os]));
-        mbar_arrive(smem_u32(&empty_raw[rs]));
-      }
-      if (++rs == TC_RAW_STAGES) { rs = 0; rph ^= 1u; }
-      if (++os == TC_OP_STAGES) { os = 0; oph ^= 1u; }
     }
   } else {
     // ===================================================================== epilogue warps
     const int quarter = warp & 3;          // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
-    const int half = (warp - 6) >> 2;      // the two warps of a quarter take alternate 16-column chunks
+    const int half = (warp - 10) >> 2;     // the two warps of a quarter take alternate 16-column chunks
     float* out = P.part + (size_t)blockIdx.x * P.n * P.np;
     const int64_t n_seg = (my_steps + P.seg_steps - 1) / P.seg_steps;
     for (int64_t seg = 0; seg < n_seg; ++seg) {

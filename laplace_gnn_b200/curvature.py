@@ -170,7 +170,7 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=False, fused_hess_spmm=True, sparse_halo=False):
+                    unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=True, fused_hess_spmm=True, sparse_halo=False):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -213,8 +213,8 @@ class _B200KFAC:
         self.shard_eigh = bool(shard_eigh)
         # power-law graphs: the unit SpMM gives one warp group a whole row, so graphs with rows beyond
         # unit_row_limit non-zeros keep dense slabs — unless unit_hub_split cuts those rows into pieces
-        # (graph.split_hub_rows; the pieces are summed by a small SpMM afterwards).  OFF by default until the
-        # R-MAT sweep has run with it on a B200 (tools/rmat_sweep.py --hub-split)
+        # (graph.split_hub_rows; the pieces are summed by a small SpMM afterwards).  R-MAT 2^20 - 2^22, degree
+        # 16 - 64: 13 - 19 % faster fits than dense slabs, same marglik to the last digit (profiles/r2h_rmat_sweep.txt)
         self.unit_hub_split = bool(unit_hub_split)
         # output-layer SpMM with its Hessian-sqrt right-hand sides rebuilt per edge from five softmax vectors per
         # node (csrc/spmm_hess.cu): 576 instead of 3072 gathered bytes per edge at g = 16, C = 47, and no
@@ -653,7 +653,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=False, fused_hess_spmm=True, sparse_halo=False):
+                 unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=True, fused_hess_spmm=True, sparse_halo=False):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:

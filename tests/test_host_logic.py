@@ -469,7 +469,7 @@ def test_even_column_groups_take_what_the_rank_owns(fake_ops, C, want_group):
 def test_hub_rows_are_split_for_the_unit_spmm(fake_ops, limit):
     """unit_hub_split: a power-law graph whose longest row exceeds the unit kernel's row limit takes the
     unit-compacted slabs through graph.split_hub_rows (pieces as extra rows, summed afterwards) and gives the
-    factors of the dense slabs; without the switch it keeps dense slabs."""
+    factors of the dense slabs (the default); with unit_hub_split=False it keeps dense slabs."""
     import laplace_gnn_b200 as L
     from laplace_gnn_b200.graph import split_hub_rows
     from oracle import gcn_kfac_oracle as O
@@ -484,7 +484,7 @@ def test_hub_rows_are_split_for_the_unit_spmm(fake_ops, limit):
     y = torch.randint(0, C, (300,), generator=gen)
     ref = L.B200GGN(model, "classification", unit_slabs=False)
     l0, k0 = ref.kron(idx, y, N=300)
-    plain = L.B200GGN(model, "classification", unit_min_width=0)
+    plain = L.B200GGN(model, "classification", unit_min_width=0, unit_hub_split=False)
     plain.unit_row_limit = limit
     plain.kron(idx, y, N=300)
     assert plain.last_stats["unit_slabs"] == 0                      # hub rows and no split: dense slabs
