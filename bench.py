@@ -362,7 +362,7 @@ def main():
     allocator["max_allocated_gb"] = round(torch.cuda.max_memory_allocated(dev) / 1e9, 2)
     # records -> plain numbers (timings, counts): nothing of the timed steps stays alive past this point
     prof = [{"kind": r["kind"], "d": r["d"], "ms": r["start"].elapsed_time(r["end"]), "bytes": r["bytes"],
-             "dense_bytes": r.get("dense_bytes", 0.0)} for r in ops.profile_end()]
+             "dense_bytes": r.get("dense_bytes", 0.0), "issued": r.get("issued", 0.0)} for r in ops.profile_end()]
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
@@ -378,7 +378,8 @@ def main():
         for rec in prof:
             ms = rec["ms"]
             gk = (rec["kind"], rec["d"])
-            a = groups.setdefault(gk, {"ms": 0.0, "launches": 0, "bytes": 0.0, "dense_bytes": 0.0})
+            a = groups.setdefault(gk, {"ms": 0.0, "launches": 0, "bytes": 0.0, "dense_bytes": 0.0, "issued": 0.0})
+            a["issued"] += rec.get("issued", 0.0)
             a["ms"] += ms
             a["launches"] += 1
             a["bytes"] += rec["bytes"]                     # algorithmic bytes (SpMM) or useful flops (SYRK / GEMM), summed
@@ -441,11 +442,14 @@ def main():
              "avg_launch_ms": v["ms"] / v["launches"], "gbs": v["bytes"] / (v["ms"] * 1e-3) / 1e9,
              "frac": v["bytes"] / (v["ms"] * 1e-3) / 1e9 / hbm_peak}
             for (k, dd), v in sorted(spmm_groups.items(), key=lambda kv: -kv[1]["ms"]) if v["ms"] > 0]
-        # secondary, tensor-bound kernels: useful TFLOP/s (3xTF32 issues 3x that) against the TF32 dense
-        # peak taken as half the measured bf16 GEMM figure (MEASURED_PEAKS.json has no tf32 entry)
-        tf32_peak = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0
-        try:        # a measured TF32 GEMM rate, once tools/tf32_peak.py has been run on the pool's B200
+        # secondary, tensor-bound kernels against the TF32 GEMM rate MEASURED on this pool's B200 (tools/tf32_peak.py
+        # -> profiles/tf32_peak.json: cuBLAS through torch.matmul, 8192^3; sustained figure, these kernels run inside
+        # a long step); half the measured bf16 figure if that file is missing.  `achieved` = useful flops (what the
+        # algorithm needs), `issued` = what the 3xTF32 split and the block-triangle make the tensor pipe execute
+        tf32_peak, tf32_src = float(peaks.get("bf16_tflops_sustained", 1400.0)) / 2.0, "bf16_sustained / 2"
+        try:
             tf32_peak = float(json.load(open(os.path.join(ROOT, "profiles", "tf32_peak.json")))["tf32_tflops_sustained"])
+            tf32_src = "measured (profiles/tf32_peak.json, sustained)"
         except Exception:
             pass
         tens = []
@@ -453,10 +457,12 @@ def main():
             if k in ("syrk", "gemm_mask") and v["ms"] > 0 and v["bytes"] > 0:
                 avg = v["ms"] / v["launches"]
                 ach = v["bytes"] / (v["ms"] * 1e-3) / 1e12
+                iss = v["issued"] / (v["ms"] * 1e-3) / 1e12
                 tens.append({"kernel": f"{k} n={dd}", "bound": "tensor", "achieved": ach, "peak": tf32_peak,
-                             "unit": "TFLOP/s", "frac": ach / tf32_peak, "avg_launch_ms": avg,
-                             "launches_per_step": v["launches"] / args.steps,
-                             "note": "useful flops; the 3xTF32 split issues 3x (SYRK: x2.25 with the block-triangle)"})
+                             "unit": "TFLOP/s", "frac": ach / tf32_peak, "issued": iss, "issued_frac": iss / tf32_peak,
+                             "peak_source": tf32_src, "avg_launch_ms": avg, "launches_per_step": v["launches"] / args.steps,
+                             "note": "achieved = useful flops; issued = executed by the tensor pipe (3 products of the "
+                                     "3xTF32 split; SYRK: on 128-row blocks of the upper block-triangle)"})
         roof["tensor_kernels"] = tens
 
     # ---------------- end to end from pinned host buffers through the public API

@@ -258,6 +258,15 @@ int lgnn_gemm_mask_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, c
                        const float* wt_lo, int64_t n, const float* act, int64_t ld_act, int32_t group,
                        float* out, int64_t ldo, lgnn_stream_t stream);
 
+/* out[r, 0:n] = A[r, 0:k] . W[0:k, 0:n] + bias[0:n],  r in [0, m_rows): the linear layer of GCNConv,
+ * Z_l = H_{l-1} W_l^T + 1 b_l^T (gnn/models/layers.py:45, torch.nn.Linear), on the same 3xTF32 tcgen05 kernel with
+ * the bias added in its epilogue.  W here is conv.lin.weight TRANSPOSED ([k = d_{l-1}, n = d_l], prepared with
+ * lgnn_gemm_mask_prepare_f32; a d_l outside {64, 128, 256} is zero-padded to the next of them by the caller, ldo
+ * then >= the padded n); bias [n] 16-byte aligned, or NULL.  Same shape and alignment rules as lgnn_gemm_mask_f32. */
+int lgnn_gemm_bias_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, const float* wt_hi,
+                       const float* wt_lo, int64_t n, const float* bias, float* out, int64_t ldo,
+                       lgnn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

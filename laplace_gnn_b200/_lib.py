@@ -54,6 +54,7 @@ PROTOTYPES = {
     "lgnn_gemm_mask_kpad": (_i64, [_i64]),
     "lgnn_gemm_mask_prepare_f32": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "lgnn_gemm_mask_f32": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _i64, _i32, _vp, _i64, _vp]),
+    "lgnn_gemm_bias_f32": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp]),
     "lgnn_syrk_workspace_bytes": (_sz, [_i64, _i64, C.c_int]),
     "lgnn_syrk_f32": (C.c_int, [_vp, _i64, _i64, _i64, _f32, _f32, _vp, _i64, _vp, _sz, C.c_int, _vp]),
 }

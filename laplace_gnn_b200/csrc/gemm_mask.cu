@@ -81,6 +81,7 @@ struct GmParams {
   int group;
   const float* act;  // may be null (no mask)
   int64_t ld_act;
+  const float* bias; // may be null; added after the mask (the forward linear layer passes a bias and no mask)
   float* out;
   int64_t ldo;
 };
@@ -309,6 +310,10 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     };
     if (masked) fetch_mask(0);
+    float4 bs[4];                    // this thread's 4 x 4 output columns of the bias (pass p: columns 16p + 4 sub_c ..)
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+      bs[p] = P.bias ? __ldg(reinterpret_cast<const float4*>(P.bias + n0 + 16 * p + 4 * sub_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t = 0; t < n_tiles; ++t) {
       const int as = t & 1;
       const uint32_t aph = (uint32_t)((t >> 1) & 1);
@@ -369,10 +374,10 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int64_t row = row_base + rl;
             float4 o = *reinterpret_cast<const float4*>(my_stg + (size_t)rl * GM_STG_PITCH + sub_c * 16);
             const unsigned kb4 = (unsigned)(keep >> (4 * (4 * p + i))) & 15u;
-            o.x = (kb4 & 1u) ? o.x : 0.f;
-            o.y = (kb4 & 2u) ? o.y : 0.f;
-            o.z = (kb4 & 4u) ? o.z : 0.f;
-            o.w = (kb4 & 8u) ? o.w : 0.f;
+            o.x = ((kb4 & 1u) ? o.x : 0.f) + bs[p].x;
+            o.y = ((kb4 & 2u) ? o.y : 0.f) + bs[p].y;
+            o.z = ((kb4 & 4u) ? o.z : 0.f) + bs[p].z;
+            o.w = ((kb4 & 8u) ? o.w : 0.f) + bs[p].w;
             if (row < P.m_rows && !GM_ABL(8)) *reinterpret_cast<float4*>(P.out + row * P.ldo + n0 + 16 * p + 4 * sub_c) = o;
           }
           __syncwarp();
@@ -441,9 +446,9 @@ int lgnn_gemm_mask_prepare_f32(const float* w, int64_t ldw, int64_t k, int64_t n
   return LGNN_OK;
 }
 
-int lgnn_gemm_mask_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, const float* wt_hi,
+static int gemm_launch(const float* a, int64_t lda, int64_t m_rows, int64_t k, const float* wt_hi,
                        const float* wt_lo, int64_t n, const float* act, int64_t ld_act, int32_t group,
-                       float* out, int64_t ldo, lgnn_stream_t stream) {
+                       const float* bias, float* out, int64_t ldo, lgnn_stream_t stream) {
   if (m_rows < 0 || !wt_hi || !wt_lo || !out || group < 1 || lda < k || ldo < n || (act && ld_act < n))
     return fail(LGNN_E_BADARG, "gemm_mask: bad argument");
   if (!lgnn_gemm_mask_supported(k, n)) return fail(LGNN_E_UNSUPPORTED, "gemm_mask: needs K <= 256 and N in {64, 128, 256}");
@@ -481,6 +486,7 @@ int lgnn_gemm_mask_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, c
   P.group = group;
   P.act = act;
   P.ld_act = ld_act;
+  P.bias = bias;
   P.out = out;
   P.ldo = ldo;
   CUtensorMap tm_a, tm_bhi, tm_blo;
@@ -506,6 +512,19 @@ int lgnn_gemm_mask_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, c
   LGNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_mask_kernel, tm_a, tm_bhi, tm_blo, P));
   LGNN_LAUNCH_CHECK("gemm_mask_kernel");
   return LGNN_OK;
+}
+
+int lgnn_gemm_mask_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, const float* wt_hi,
+                       const float* wt_lo, int64_t n, const float* act, int64_t ld_act, int32_t group,
+                       float* out, int64_t ldo, lgnn_stream_t stream) {
+  return gemm_launch(a, lda, m_rows, k, wt_hi, wt_lo, n, act, ld_act, group, nullptr, out, ldo, stream);
+}
+
+int lgnn_gemm_bias_f32(const float* a, int64_t lda, int64_t m_rows, int64_t k, const float* wt_hi,
+                       const float* wt_lo, int64_t n, const float* bias, float* out, int64_t ldo,
+                       lgnn_stream_t stream) {
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return fail(LGNN_E_ALIGN, "gemm_bias: bias must be 16-byte aligned");
+  return gemm_launch(a, lda, m_rows, k, wt_hi, wt_lo, n, nullptr, 0, 1, bias, out, ldo, stream);
 }
 
 }  // extern "C"

@@ -20,6 +20,7 @@ inline int& gm_lab_ablate() {
 #define lgnn_gemm_mask_kpad lgnn_gemm_mask_lab_kpad
 #define lgnn_gemm_mask_prepare_f32 lgnn_gemm_mask_lab_prepare_f32
 #define lgnn_gemm_mask_f32 lgnn_gemm_mask_lab_f32
+#define lgnn_gemm_bias_f32 lgnn_gemm_bias_lab_f32
 #include "gemm_mask.cu"
 
 extern "C" int lgnn_gemm_mask_lab_set_ablate(int bits) {

@@ -112,6 +112,65 @@ __global__ void __launch_bounds__(SPMM_THREADS, 2) spmm_vec_kernel(
   }
 }
 
+// Narrow rows (d <= 64 floats, e.g. the 48-float logits of the products shape): with one float4 per lane only d/4 of
+// the 32 lanes would work (12 at d = 48: the forward logits SpMM ran at 0.25 of the copy rate).  The warp is cut into
+// SPLIT groups of W = 32 / SPLIT lanes; group s takes the neighbours j = s (mod SPLIT) of every batch of 32, so
+// SPLIT source rows are in flight per step and every lane that has a column works; the groups' partial sums are
+// added with xor-shuffles at the end (the summation order therefore differs from the other kernels' — rounding
+// level, far inside the 1e-5 SpMM tolerance).  Hub rows are left to spmm_hub_kernel like in spmm_vec_kernel.
+template <int SPLIT, int UNROLL>
+__global__ void __launch_bounds__(SPMM_THREADS, 3) spmm_narrow_kernel(
+    int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
+    const float* __restrict__ val, const float* __restrict__ x, int64_t ldx, float* __restrict__ y,
+    int64_t ldy, int d4, int64_t hub_len, int flags) {
+  constexpr int W = 32 / SPLIT;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = ((int64_t)blockIdx.x * SPMM_THREADS + threadIdx.x) >> 5;
+  if (row >= n_rows) return;
+  const int sub = lane / W, l = lane - sub * W;
+  const bool act = l < d4;
+  const float* xb = x + 4 * l;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t beg = rowptr[row], end = rowptr[row + 1];
+  if (end - beg > hub_len) return;   // hub row: spmm_hub_kernel adds it up in segments
+  for (int64_t k0 = beg; k0 < end; k0 += 32) {
+    const int cnt = (int)((end - k0) < 32 ? (end - k0) : 32);
+    int32_t my_c = 0;
+    float my_v = 0.f;                 // lanes beyond the batch carry a zero weight: their group step loads nothing
+    if (lane < cnt) {
+      my_c = __ldg(col + k0 + lane);
+      my_v = __ldg(val + k0 + lane);
+    }
+    for (int j = 0; j < cnt; j += SPLIT * UNROLL) {
+      float4 buf[UNROLL];
+      float vv[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        const int src_lane = (j + u * SPLIT + sub) & 31;
+        const int32_t c = __shfl_sync(0xffffffffu, my_c, src_lane);
+        vv[u] = __shfl_sync(0xffffffffu, my_v, src_lane);
+        if (j + u * SPLIT + sub >= 32) vv[u] = 0.f;
+        buf[u] = (act && vv[u] != 0.f) ? ldg_f4(xb + (int64_t)c * ldx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) fma4(acc, vv[u], buf[u]);
+    }
+  }
+#pragma unroll
+  for (int off = W; off < 32; off <<= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, off);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, off);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, off);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, off);
+  }
+  if (sub == 0 && act) {
+    if (flags & LGNN_SPMM_RELU) {
+      acc.x = fmaxf(acc.x, 0.f); acc.y = fmaxf(acc.y, 0.f); acc.z = fmaxf(acc.z, 0.f); acc.w = fmaxf(acc.w, 0.f);
+    }
+    *reinterpret_cast<float4*>(y + row * ldy + 4 * l) = acc;
+  }
+}
+
 // Hub rows of the warp-per-row path.  Block b owns the non-zeros [b*SEG, (b+1)*SEG); for every hub row
 // intersecting that range its 8 warps split the intersection evenly and add their partial sums onto
 // the row (cleared beforehand by spmm_zero_hub_rows_kernel) with red.global.add.v4.f32.  Blocks
@@ -464,7 +523,14 @@ extern "C" int lgnn_spmm_f32(int64_t n_rows, int64_t nnz, const int64_t* rowptr,
       spmm_zero_hub_rows_kernel<<<(unsigned)zb, 256, 0, st>>>(n_rows, rowptr, LDG_HUB_LEN, y, ldy, d4);
       LGNN_LAUNCH_CHECK("spmm_zero_hub_rows_kernel");
     }
-    if (d4 <= 32) {
+    if (d4 <= 16 && !(flags & LGNN_SPMM_FORCE_LDG)) {
+      const unsigned nb = (unsigned)((n_rows + warps_per_block - 1) / warps_per_block);
+      if (d4 <= 4) spmm_narrow_kernel<8, 2><<<nb, SPMM_THREADS, 0, st>>>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, hub_len, epi);
+      else if (d4 <= 8) spmm_narrow_kernel<4, 4><<<nb, SPMM_THREADS, 0, st>>>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, hub_len, epi);
+      else spmm_narrow_kernel<2, 4><<<nb, SPMM_THREADS, 0, st>>>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4, hub_len, epi);
+      if (hub_blocks > 0)
+        spmm_hub_kernel<1, 8><<<dim3((unsigned)hub_blocks, 1), SPMM_THREADS, 0, st>>>(n_rows, rowptr, col, val, x, ldx, y, ldy, d4);
+    } else if (d4 <= 32) {
       int64_t warps = n_rows;
       spmm_vec_kernel<1, 8><<<(unsigned)((warps + warps_per_block - 1) / warps_per_block), SPMM_THREADS, 0, st>>>(
           n_rows, rowptr, col, val, x, ldx, y, ldy, d4, 1, hub_len, epi);

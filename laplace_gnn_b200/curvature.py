@@ -263,6 +263,9 @@ class _B200KFAC:
         Hs = [h]
         L = len(Ws)
         self._fwd_out = []          # row-partitioned forward: the padded slabs holding this rank's P_l / H_l rows
+        # Z_l = H_{l-1} W_l^T + b_l on the fused 3xTF32 tcgen05 GEMM (bias in its epilogue) wherever it takes the shape
+        # (d_in, d_out <= 256); cuBLAS fp32 otherwise (e.g. the 1,433 input features of the Cora shape)
+        lin = [self._linear_operands(Ws[l], bs[l]) if (self.fused_gemm and h.is_cuda) else None for l in range(L)]
         for l in range(L):
             d_out = Ws[l].shape[0]
             if part is None:
@@ -270,16 +273,22 @@ class _B200KFAC:
                 # rewritten by every pass and a fresh 2.5 GB allocation per layer per fit is a cudaMalloc each
                 n_rows = h.shape[0]
                 ldz = (d_out + 3) // 4 * 4     # odd class count: pad the pitch so the SpMM takes its 128-bit path
-                z = _slab(h.device, 1000 + l, 0, n_rows * ldz).view(n_rows, ldz)
-                with ops.timed("gemm_fwd", d_out, 2.0 * n_rows * Ws[l].numel()):
-                    if ldz == d_out:
-                        if bs[l] is None:
-                            torch.mm(h, Ws[l].t(), out=z)
+                if lin[l] is not None:         # the kernel writes its whole (zero-padded) output width
+                    wp, bias_p = lin[l]
+                    zbuf = _slab(h.device, 1000 + l, 0, n_rows * wp.n).view(n_rows, wp.n)
+                    ops.gemm_bias(h, wp, bias_p, zbuf, m_rows=n_rows)
+                    z = zbuf[:, :ldz]
+                else:
+                    z = _slab(h.device, 1000 + l, 0, n_rows * ldz).view(n_rows, ldz)
+                    with ops.timed("gemm_fwd", d_out, 2.0 * n_rows * Ws[l].numel()):
+                        if ldz == d_out:
+                            if bs[l] is None:
+                                torch.mm(h, Ws[l].t(), out=z)
+                            else:
+                                torch.addmm(bs[l], h, Ws[l].t(), out=z)
                         else:
-                            torch.addmm(bs[l], h, Ws[l].t(), out=z)
-                    else:
-                        z[:, :d_out] = torch.mm(h, Ws[l].t()) if bs[l] is None else torch.addmm(bs[l], h, Ws[l].t())
-                        z[:, d_out:] = 0
+                            z[:, :d_out] = torch.mm(h, Ws[l].t()) if bs[l] is None else torch.addmm(bs[l], h, Ws[l].t())
+                            z[:, d_out:] = 0
                 rows_out = n_rows + g.extra_rows()          # hub rows of power-law graphs come back in pieces
                 out = _slab(h.device, 1000 + l, 1, rows_out * ldz).view(rows_out, ldz)
                 h = g.propagate(z, relu=(l < L - 1), out=out)[:, :d_out]
@@ -290,15 +299,18 @@ class _B200KFAC:
                 ldz = (d_out + 3) // 4 * 4
                 slab = _slab(h.device, 1100 + l, 0, part.total_rows * ldz).view(part.total_rows, ldz)
                 z = slab[part.slot0:part.slot0 + part.n_local]
-                with ops.timed("gemm_fwd", d_out, 2.0 * h.shape[0] * Ws[l].numel()):
-                    if ldz == d_out:
-                        if bs[l] is None:
-                            torch.mm(h, Ws[l].t(), out=z)
+                if lin[l] is not None and lin[l][0].n == ldz:    # (a padded output width would overrun the slab's pitch)
+                    ops.gemm_bias(h, lin[l][0], lin[l][1], z, m_rows=h.shape[0])
+                else:
+                    with ops.timed("gemm_fwd", d_out, 2.0 * h.shape[0] * Ws[l].numel()):
+                        if ldz == d_out:
+                            if bs[l] is None:
+                                torch.mm(h, Ws[l].t(), out=z)
+                            else:
+                                torch.addmm(bs[l], h, Ws[l].t(), out=z)
                         else:
-                            torch.addmm(bs[l], h, Ws[l].t(), out=z)
-                    else:
-                        z[:, :d_out] = torch.mm(h, Ws[l].t()) if bs[l] is None else torch.addmm(bs[l], h, Ws[l].t())
-                        z[:, d_out:] = 0
+                            z[:, :d_out] = torch.mm(h, Ws[l].t()) if bs[l] is None else torch.addmm(bs[l], h, Ws[l].t())
+                            z[:, d_out:] = 0
                 with ops.timed("allgather", d_out, 4.0 * part.total_rows * ldz):
                     part.exchange_for_spmm(slab)          # whole slab, or the halo rows only when the halo is sparse
                 out_slab = _slab(h.device, 1100 + l, 1, part.total_rows * ldz).view(part.total_rows, ldz)
@@ -308,6 +320,17 @@ class _B200KFAC:
             if l < L - 1:
                 Hs.append(h)
         return Hs, h
+
+    def _linear_operands(self, W: torch.Tensor, b):
+        """(prepared W^T, zero-padded bias) for ops.gemm_bias, or None when the fused GEMM does not take the layer."""
+        wp = ops.linear_prepare(W)
+        if wp is None:
+            return None
+        bias_p = None
+        if b is not None:
+            bias_p = torch.zeros(wp.n, dtype=torch.float32, device=W.device)
+            bias_p[: b.numel()] = b
+        return wp, bias_p
 
     def _group_size(self, rows_in: int, rows_out: int, dmax: int, C: int, device) -> int:
         budget = self.rhs_tile_bytes

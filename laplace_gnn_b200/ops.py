@@ -530,10 +530,47 @@ def gemm_mask(a: torch.Tensor, w: PreparedWeight, act: torch.Tensor | None, grou
         _f32c(act, "act")
         if act.shape[0] * group < m_rows or act.shape[1] < w.n:
             raise ValueError("gemm_mask: act too small")
-    with _Timed("gemm_mask", w.n, 2.0 * m_rows * w.k * w.n):
+    with _Timed("gemm_mask", w.n, 2.0 * m_rows * w.k * w.n) as rec:
         check(lib.lgnn_gemm_mask_f32(ptr(a), a.stride(0), m_rows, w.k, ptr(w.wt_hi), ptr(w.wt_lo), w.n,
                                      ptr(act), 0 if act is None else act.stride(0), int(group),
                                      ptr(out), out.stride(0), stream()), "lgnn_gemm_mask_f32")
+    if rec.rec is not None:       # 3xTF32 issues hi.hi + hi.lo + lo.hi over the K padded to the 8-wide MMA steps
+        rec.rec["issued"] = 3.0 * 2.0 * m_rows * ((w.k + 7) // 8 * 8) * w.n
+    _lib.count_launches(1)
+    return out
+
+
+GEMM_WIDTHS = (64, 128, 256)
+
+
+def linear_prepare(weight: torch.Tensor) -> PreparedWeight | None:
+    """``nn.Linear`` weight [d_out, d_in] as the resident operands of ``gemm_bias`` (W^T, output width zero-padded
+    to 64 / 128 / 256), or None when the fused kernel does not take the shape (d_in > 256 or d_out > 256)."""
+    d_out, d_in = int(weight.shape[0]), int(weight.shape[1])
+    n_pad = next((w for w in GEMM_WIDTHS if w >= d_out), None)
+    if n_pad is None or not gemm_mask_supported(d_in, n_pad):
+        return None
+    wt = torch.zeros(d_in, n_pad, dtype=torch.float32, device=weight.device)
+    wt[:, :d_out] = weight.detach().t()
+    return gemm_mask_prepare(wt)
+
+
+def gemm_bias(a: torch.Tensor, w: PreparedWeight, bias: torch.Tensor | None, out: torch.Tensor,
+              m_rows: int | None = None) -> torch.Tensor:
+    """out[r, :w.n] = a[r, :w.k] @ W + bias  (the GCNConv linear layer on the 3xTF32 tcgen05 kernel; ``bias`` [w.n]
+    or None; ``out`` needs a pitch >= w.n)."""
+    lib = _lib.load()
+    _f32c(a, "a"); _f32c(out, "out")
+    m_rows = int(a.shape[0]) if m_rows is None else int(m_rows)
+    if a.shape[1] < w.k or out.shape[0] < m_rows or out.stride(0) < w.n:
+        raise ValueError("gemm_bias: a has fewer columns than W has rows, or out is too small")
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() < w.n or not bias.is_contiguous()):
+        raise ValueError("gemm_bias: bias must be a contiguous float32 vector with one entry per (padded) output column")
+    with _Timed("gemm_fwd", w.n, 2.0 * m_rows * w.k * w.n) as rec:
+        check(lib.lgnn_gemm_bias_f32(ptr(a), a.stride(0), m_rows, w.k, ptr(w.wt_hi), ptr(w.wt_lo), w.n, ptr(bias),
+                                     ptr(out), out.stride(0), stream()), "lgnn_gemm_bias_f32")
+    if rec.rec is not None:
+        rec.rec["issued"] = 3.0 * 2.0 * m_rows * ((w.k + 7) // 8 * 8) * w.n
     _lib.count_launches(1)
     return out
 
@@ -569,8 +606,13 @@ def syrk(x: torch.Tensor, n: int | None = None, alpha: float = 1.0, beta: float 
     code = _SYRK_IMPL[impl]
     nbytes = lib.lgnn_syrk_workspace_bytes(k_rows, n, code)
     ws = _workspace(nbytes, x.device)
-    with _Timed("syrk", n, float(k_rows) * n * (n + 1)):
+    with _Timed("syrk", n, float(k_rows) * n * (n + 1)) as rec:
         check(lib.lgnn_syrk_f32(ptr(x), x.stride(0), k_rows, n, float(alpha), float(beta), ptr(out),
                                 out.stride(0), ptr(ws), ws.numel(), code, stream()), "lgnn_syrk_f32")
+    if rec.rec is not None and n <= 256 and impl != "simt" and x.stride(0) % 4 == 0:
+        # tensor-core path: three products on M = 128-row blocks of the upper block-triangle (rows 0..127 against all
+        # np columns, rows 128..255 against columns 128..np-1), K rounded up to the 16-row steps
+        np_ = (n + 15) // 16 * 16
+        rec.rec["issued"] = 3.0 * 2.0 * ((k_rows + 15) // 16 * 16) * 128.0 * (np_ + (np_ - 128 if np_ > 128 else 0))
     _lib.count_launches(2)
     return out

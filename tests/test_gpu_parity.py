@@ -621,3 +621,29 @@ def test_unit_compacted_backward_products_like_shapes(h, C, layers):
     for fa, fb in zip(res[0][1], res[1][1]):
         for a, b in zip(fa, fb):            # same slabs bit for bit; the column grouping changes the SYRK's summation order
             assert max_rel_err(a.cpu().numpy(), b.cpu().numpy()) <= 1e-5
+
+
+# ---------------------------------------------------------------------------------- linear layer on the fused GEMM
+@pytest.mark.parametrize("d_in,d_out,bias", [(100, 256, True), (256, 256, True), (256, 47, True), (128, 40, False),
+                                              (16, 7, True), (3, 64, True), (255, 129, True)])
+def test_linear_layer_on_the_tensor_core_gemm(d_in, d_out, bias):
+    """ops.gemm_bias (lgnn_gemm_bias_f32: Z = H W^T + b of gnn/models/layers.py:45 on the 3xTF32 tcgen05 kernel, bias
+    in the epilogue, output width zero-padded to 64 / 128 / 256) against float64; pitched input, row tail."""
+    ops = _ops()
+    m = 70_001
+    gen = torch.Generator(device=DEV).manual_seed(d_in + d_out)
+    h = torch.randn(m, d_in + 4, device=DEV, generator=gen)[:, :d_in] if d_in % 4 == 0 else \
+        torch.randn(m, (d_in + 3) // 4 * 4, device=DEV, generator=gen)[:, :d_in]
+    lin = torch.nn.Linear(d_in, d_out, bias=bias).to(DEV)
+    wp = ops.linear_prepare(lin.weight)
+    assert wp is not None and wp.n in (64, 128, 256) and wp.n >= d_out and wp.k == d_in
+    bp = None
+    if bias:
+        bp = torch.zeros(wp.n, device=DEV)
+        bp[:d_out] = lin.bias.detach()
+    out = torch.full((m, wp.n + 8), -3.0, device=DEV)
+    ops.gemm_bias(h, wp, bp, out[:, : wp.n])
+    want = h.double() @ lin.weight.detach().double().t() + (lin.bias.detach().double() if bias else 0.0)
+    assert max_rel_err(out[:, :d_out].cpu().numpy(), want.cpu().numpy()) <= 2e-6
+    assert bool((out[:, d_out:wp.n] == 0).all()) and bool((out[:, wp.n:] == -3.0).all())
+    assert ops.linear_prepare(torch.randn(7, 1433, device=DEV)) is None          # d_in beyond the kernel: cuBLAS path
