@@ -49,6 +49,7 @@ def parse_args():
                     help="multi-GPU layout of the KFAC backward (laplace_gnn_b200/dist.py)")
     ap.add_argument("--no-overlap", action="store_true", help="rows layout: one column group in flight instead of two")
     ap.add_argument("--no-fused-gemm", action="store_true", help="cuBLAS fp32 GEMM + mask kernel instead of the fused tcgen05 kernel")
+    ap.add_argument("--no-fused-linear", action="store_true", help="forward linear layers on cuBLAS fp32 instead of the tcgen05 kernel")
     ap.add_argument("--dense-slabs", action="store_true", help="keep the slabs below the output layer dense (no unit compaction)")
     ap.add_argument("--no-unit-even-groups", action="store_true",
                     help="column groups padded to multiples of 4 (round-1 behaviour) instead of any even width")
@@ -62,8 +63,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity sample (GPU path vs oracle port) of this run")
-    ap.add_argument("--cpu-sample-div", type=int, default=16,
-                    help="the CPU arm / cpu_baseline run the same workload shape at 1/div of the nodes and edges")
+    ap.add_argument("--cpu-sample-div", type=int, default=None,
+                    help="the CPU arm / cpu_baseline / parity sample run the same workload shape at 1/div of the nodes and "
+                         "edges (default: products 16, arxiv 4, pubmed and cora 1 — the whole workload)")
     return ap.parse_args()
 
 
@@ -73,7 +75,16 @@ def workload_name(workload, h, l):
             "Laplace fit + log marglik, single full batch")
 
 
+# bounded CPU sample per workload: 10-30 s of oracle time on the box's host cores.  Not smaller than needed: a single
+# relu unit of one node whose pre-activation rounds to the other side of zero (3xTF32 and FMA accumulation differ in the
+# last bits) moves an entry of a hidden-layer G factor by ~2/N of the diagonal — 2e-4 at 10 k nodes, 1e-5 at 150 k —
+# so a very small sample would test the tie-breaking of relu, not the kernels
+SAMPLE_DIV = {"products": 16, "arxiv": 4, "pubmed": 1, "cora": 1}
+
+
 def shape(args):
+    if args.cpu_sample_div is None:
+        args.cpu_sample_div = SAMPLE_DIV[args.workload]
     n, u, f, c, h, l = WORKLOADS[args.workload]
     if args.scale != 1.0:
         n, u = max(8, int(n * args.scale)), max(8, int(u * args.scale))
@@ -307,7 +318,7 @@ def main():
         del edge_index
     bk = {"hess_sqrt": args.hess_sqrt, "syrk_impl": args.syrk, "fused_gemm": not args.no_fused_gemm,
           "unit_slabs": not args.dense_slabs, "unit_even_groups": not args.no_unit_even_groups,
-          "fused_hess_spmm": not args.no_fused_hess_spmm}
+          "fused_hess_spmm": not args.no_fused_hess_spmm, "fused_linear": not args.no_fused_linear}
     if args.rhs_tile_gb is not None:
         bk["rhs_tile_bytes"] = int(args.rhs_tile_gb * 1e9)
     if pg is not None:
@@ -529,6 +540,7 @@ def main():
         la_s, ml_s = step(mdl_s, L.TensorBatchLoader(idx_s, y_s))
         facs = [[t.clone() for t in blk] for blk in la_s.H_facs.kfacs]
         rel = lambda a_, b_: float((a_ - b_).abs().max() / b_.abs().max().clamp_min(1e-30))
+        fro = lambda a_, b_: float((a_ - b_).double().norm() / b_.double().norm().clamp_min(1e-30))
         parity = {"sample": f"{args.workload}-shaped at 1/{div} scale: {ns} nodes, nnz {mdl_s.graph.nnz}, same F/C/h/L, "
                             "seeded inputs mirrored from the device", "marglik_gpu": float(ml_s),
                   "tolerance": {"factors": 1e-4, "marglik": 1e-3}}
@@ -559,10 +571,14 @@ def main():
             dt = time.perf_counter() - t0
             same_csr = bool(np.array_equal(mdl_s.graph.ahat.rowptr.cpu().numpy(), g_ref.rowptr) and
                             np.array_equal(mdl_s.graph.ahat.col.cpu().numpy(), g_ref.col))
-            worst = max(rel(a_.cpu(), b_) for fa, fb in zip(facs, kf_ref) for a_, b_ in zip(fa, fb))
+            per_factor = [[rel(a_.cpu(), b_) for a_, b_ in zip(fa, fb)] for fa, fb in zip(facs, kf_ref)]
+            worst = max(v for blk in per_factor for v in blk)
             d_ml = abs(float(ml_s) - float(ml_ref)) / abs(float(ml_ref))
             parity["vs_oracle"] = {"csr_bit_exact": same_csr, "factors_max_rel": worst, "marglik_rel": d_ml,
-                                   "marglik_oracle": float(ml_ref)}
+                                   "marglik_oracle": float(ml_ref),
+                                   "factors_max_frobenius_rel": max(fro(a_.cpu(), b_) for fa, fb in zip(facs, kf_ref)
+                                                                    for a_, b_ in zip(fa, fb)),
+                                   "per_block_rel": [[float(f"{v:.2e}") for v in blk] for blk in per_factor]}
             ok = ok and same_csr and worst <= 1e-4 and d_ml <= 1e-3
             if world == 1 and not args.no_cpu_baseline:
                 cpu = {"value": ns / dt, "unit": "nodes/s", "cores": threads, "kind": "port", "seconds": dt,

@@ -104,6 +104,10 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t local_bar, uint32_t 
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 
+// MASKED: the relu' mask is applied in the epilogue (dense slabs); false: plain product (+ bias) — the unit-compacted
+// hot path and the forward linear layer, whose instantiation carries neither the 64 mask-prefetch registers nor the
+// spills they caused
+template <bool MASKED>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_bhi,
                  const __grid_constant__ CUtensorMap tm_blo, const GmParams P) {
@@ -293,7 +297,7 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
     uint8_t* my_stg = stg + (size_t)(warp - 10) * GM_STG_WARP;
     const int sub_r = lane >> 2, sub_c = lane & 3;
-    const bool masked = P.act != nullptr;
+    constexpr bool masked = MASKED;
     // relu' mask words of one tile for this thread: mk[4*p + i] covers pass p (columns 16p + 4*sub_c ..),
     // row i*8 + sub_r.  They do not depend on the MMAs, so tile t+1's are fetched while tile t is stored.
     float4 mk[16];
@@ -310,10 +314,9 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
       }
     };
     if (masked) fetch_mask(0);
-    float4 bs[4];                    // this thread's 4 x 4 output columns of the bias (pass p: columns 16p + 4 sub_c ..)
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-      bs[p] = P.bias ? __ldg(reinterpret_cast<const float4*>(P.bias + n0 + 16 * p + 4 * sub_c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // bias of this thread's output columns (pass p: columns 16p + 4 sub_c ..): re-read per pass from L1 rather than
+    // held in 16 registers — the epilogue is at the register limit and spills are paid once per tile
+    const float* bias_src = P.bias ? P.bias + n0 + 4 * sub_c : nullptr;
     for (int t = 0; t < n_tiles; ++t) {
       const int as = t & 1;
       const uint32_t aph = (uint32_t)((t >> 1) & 1);
@@ -362,6 +365,7 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
         for (int pp = 0; pp < 2; ++pp) {
           const int p = 2 * h + pp;
+          const float4 bs = bias_src ? __ldg(reinterpret_cast<const float4*>(bias_src + 16 * p)) : make_float4(0.f, 0.f, 0.f, 0.f);
           float4* mine = reinterpret_cast<float4*>(my_stg + (size_t)lane * GM_STG_PITCH);
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -374,10 +378,10 @@ gemm_mask_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const int64_t row = row_base + rl;
             float4 o = *reinterpret_cast<const float4*>(my_stg + (size_t)rl * GM_STG_PITCH + sub_c * 16);
             const unsigned kb4 = (unsigned)(keep >> (4 * (4 * p + i))) & 15u;
-            o.x = ((kb4 & 1u) ? o.x : 0.f) + bs[p].x;
-            o.y = ((kb4 & 2u) ? o.y : 0.f) + bs[p].y;
-            o.z = ((kb4 & 4u) ? o.z : 0.f) + bs[p].z;
-            o.w = ((kb4 & 8u) ? o.w : 0.f) + bs[p].w;
+            o.x = ((kb4 & 1u) ? o.x : 0.f) + bs.x;
+            o.y = ((kb4 & 2u) ? o.y : 0.f) + bs.y;
+            o.z = ((kb4 & 4u) ? o.z : 0.f) + bs.z;
+            o.w = ((kb4 & 8u) ? o.w : 0.f) + bs.w;
             if (row < P.m_rows && !GM_ABL(8)) *reinterpret_cast<float4*>(P.out + row * P.ldo + n0 + 16 * p + 4 * sub_c) = o;
           }
           __syncwarp();
@@ -495,7 +499,8 @@ static int gemm_launch(const float* a, int64_t lda, int64_t m_rows, int64_t k, c
   if ((rc = encode_2d(&tm_bhi, wt_hi, (uint64_t)k_pad, (uint64_t)n, (uint64_t)k_pad * 4, GM_BK, GM_BN))) return rc;
   if ((rc = encode_2d(&tm_blo, wt_lo, (uint64_t)k_pad, (uint64_t)n, (uint64_t)k_pad * 4, GM_BK, GM_BN))) return rc;
   const size_t smem = 1024 + (size_t)2 * P.n_kb * GM_B_TILE + (size_t)GM_RAW_STAGES * GM_A_TILE + 4 * GM_STG_WARP + 256;
-  LGNN_CUDA_TRY(cudaFuncSetAttribute(gemm_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LGNN_CUDA_TRY(cudaFuncSetAttribute(gemm_mask_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  LGNN_CUDA_TRY(cudaFuncSetAttribute(gemm_mask_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int64_t n_clusters = (P.tiles_total + P.tiles_per_cluster - 1) / P.tiles_per_cluster;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(n_clusters * P.cl), 1, 1);
@@ -509,7 +514,8 @@ static int gemm_launch(const float* a, int64_t lda, int64_t m_rows, int64_t k, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LGNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_mask_kernel, tm_a, tm_bhi, tm_blo, P));
+  if (act) LGNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_mask_kernel<true>, tm_a, tm_bhi, tm_blo, P));
+  else LGNN_CUDA_TRY(cudaLaunchKernelEx(&cfg, gemm_mask_kernel<false>, tm_a, tm_bhi, tm_blo, P));
   LGNN_LAUNCH_CHECK("gemm_mask_kernel");
   return LGNN_OK;
 }

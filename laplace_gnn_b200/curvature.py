@@ -170,7 +170,7 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=True, fused_hess_spmm=True, sparse_halo=False):
+                    unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=True, fused_hess_spmm=True, sparse_halo=False, fused_linear=True):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -197,6 +197,9 @@ class _B200KFAC:
         self.backward_parallel = backward_parallel
         self.overlap = bool(overlap)
         self.fused_gemm = bool(fused_gemm)
+        # the forward linear layers Z_l = H_{l-1} W_l^T + b_l on the same tcgen05 kernel (lgnn_gemm_bias_f32);
+        # False: cuBLAS fp32 (torch.addmm)
+        self.fused_linear = bool(fused_linear)
         self.skip_zero_rows = True
         # unit-compacted slabs below the output layer (csrc/spmm_units.cu): the relu' mask is shared by all
         # columns of a node, so the slab rows keep only their live hidden units and the SpMM gathers about
@@ -265,7 +268,7 @@ class _B200KFAC:
         self._fwd_out = []          # row-partitioned forward: the padded slabs holding this rank's P_l / H_l rows
         # Z_l = H_{l-1} W_l^T + b_l on the fused 3xTF32 tcgen05 GEMM (bias in its epilogue) wherever it takes the shape
         # (d_in, d_out <= 256); cuBLAS fp32 otherwise (e.g. the 1,433 input features of the Cora shape)
-        lin = [self._linear_operands(Ws[l], bs[l]) if (self.fused_gemm and h.is_cuda) else None for l in range(L)]
+        lin = [self._linear_operands(Ws[l], bs[l]) if (self.fused_gemm and self.fused_linear and h.is_cuda) else None for l in range(L)]
         for l in range(L):
             d_out = Ws[l].shape[0]
             if part is None:
@@ -273,7 +276,7 @@ class _B200KFAC:
                 # rewritten by every pass and a fresh 2.5 GB allocation per layer per fit is a cudaMalloc each
                 n_rows = h.shape[0]
                 ldz = (d_out + 3) // 4 * 4     # odd class count: pad the pitch so the SpMM takes its 128-bit path
-                if lin[l] is not None:         # the kernel writes its whole (zero-padded) output width
+                if lin[l] is not None and self._tma_ok(h):   # the kernel writes its whole (zero-padded) output width
                     wp, bias_p = lin[l]
                     zbuf = _slab(h.device, 1000 + l, 0, n_rows * wp.n).view(n_rows, wp.n)
                     ops.gemm_bias(h, wp, bias_p, zbuf, m_rows=n_rows)
@@ -299,7 +302,7 @@ class _B200KFAC:
                 ldz = (d_out + 3) // 4 * 4
                 slab = _slab(h.device, 1100 + l, 0, part.total_rows * ldz).view(part.total_rows, ldz)
                 z = slab[part.slot0:part.slot0 + part.n_local]
-                if lin[l] is not None and lin[l][0].n == ldz:    # (a padded output width would overrun the slab's pitch)
+                if lin[l] is not None and lin[l][0].n == ldz and self._tma_ok(h):   # (a padded width would overrun the pitch)
                     ops.gemm_bias(h, lin[l][0], lin[l][1], z, m_rows=h.shape[0])
                 else:
                     with ops.timed("gemm_fwd", d_out, 2.0 * h.shape[0] * Ws[l].numel()):
@@ -320,6 +323,11 @@ class _B200KFAC:
             if l < L - 1:
                 Hs.append(h)
         return Hs, h
+
+    @staticmethod
+    def _tma_ok(t: torch.Tensor) -> bool:
+        """The fused GEMM reads its left operand through TMA: 16-byte aligned rows (e.g. not a 7-feature matrix)."""
+        return t.data_ptr() % 16 == 0 and t.stride(0) % 4 == 0 and t.stride(1) == 1
 
     def _linear_operands(self, W: torch.Tensor, b):
         """(prepared W^T, zero-padded bias) for ops.gemm_bias, or None when the fused GEMM does not take the layer."""
@@ -676,7 +684,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=True, fused_hess_spmm=True, sparse_halo=False):
+                 unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=True, fused_hess_spmm=True, sparse_halo=False, fused_linear=True):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -687,7 +695,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
                          backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs,
-                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split, fused_hess_spmm, sparse_halo)
+                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split, fused_hess_spmm, sparse_halo, fused_linear)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

@@ -644,6 +644,6 @@ def test_linear_layer_on_the_tensor_core_gemm(d_in, d_out, bias):
     out = torch.full((m, wp.n + 8), -3.0, device=DEV)
     ops.gemm_bias(h, wp, bp, out[:, : wp.n])
     want = h.double() @ lin.weight.detach().double().t() + (lin.bias.detach().double() if bias else 0.0)
-    assert max_rel_err(out[:, :d_out].cpu().numpy(), want.cpu().numpy()) <= 2e-6
+    assert max_rel_err(out[:, :d_out].cpu().numpy(), want.cpu().numpy()) <= 5e-6          # 3xTF32: fp32-level
     assert bool((out[:, d_out:wp.n] == 0).all()) and bool((out[:, wp.n:] == -3.0).all())
     assert ops.linear_prepare(torch.randn(7, 1433, device=DEV)) is None          # d_in beyond the kernel: cuBLAS path

@@ -15,6 +15,14 @@ wp = ops.gemm_mask_prepare(w)
 for _ in range(reps):
     ops.gemm_mask(x, wp, act, 12, out=out)
 torch.cuda.synchronize()
-ref = (x[:4096].double() @ w.double()) * (act[: (4096 + 11) // 12].repeat_interleave(12, 0)[:4096] > 0)
-err = float((out[:4096].double() - ref).abs().max() / ref.abs().max())
-print(f"k={k} n={n} m={m} reps={reps} tpc={os.environ.get('LGNN_GEMM_TILES_PER_CLUSTER', 'auto')}: ok, rel err {err:.1e}", flush=True)
+def check(lo, hi):
+    ref = (x[lo:hi].double() @ w.double()) * (act.repeat_interleave(12, 0)[lo:hi] > 0)
+    got = out[lo:hi].double()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    scale = float((got * ref).sum() / (ref * ref).sum()) - 1.0      # systematic shrink / growth of the product
+    bad_rows = int(((got - ref).abs().max(1).values > 1e-4 * ref.abs().max()).sum())
+    return err, scale, bad_rows
+parts = [(0, min(m, 4096)), (max(0, m // 2 - 2048), min(m, m // 2 + 2048)), (max(0, m - 4096), m)]
+res = [check(lo, hi) for lo, hi in parts]
+print(f"k={k} n={n} m={m} reps={reps}: ok, rel err first/middle/last 4096 rows " + " / ".join(f"{e:.1e}" for e, _, _ in res) +
+      "  scale bias " + " / ".join(f"{b:+.1e}" for _, b, _ in res) + "  rows off by > 1e-4: " + " / ".join(str(r) for _, _, r in res), flush=True)
