@@ -377,7 +377,10 @@ extern "C" int lgnn_spmm_units_f32(int64_t n_rows, int64_t n_cols, int64_t nnz, 
   cudaStream_t st = as_stream(stream);
   const uint2* hd = reinterpret_cast<const uint2*>(hdr);
   const int nblk = (int)(h / 32);
-  const int variant = (flags >> 8) & 0xff;   // lab / test override of the unroll and occupancy choice
+  int variant = (flags >> 8) & 0xff;         // lab / test override of the unroll and occupancy choice
+  // defaults measured on the products shape (profiles/r2a_units_lab.txt): 8 rows per warp group everywhere; g = 16:
+  // ring of 4, 3 CTAs per SM (182.7 against 187.8 ms); g = 12: ring of 4, 4 CTAs per SM (139.1 against 141.7 ms)
+  if (variant == 0 && g % 4 == 0) variant = g == 16 ? 14 : (g == 12 ? 13 : 12);
   // the pipelined kernel addresses the slab with 32-bit float4 offsets: slabs up to 64 GB
   const bool narrow = n_cols * lds <= ((int64_t)1 << 34);
   if (g % 4 != 0) {

@@ -123,6 +123,30 @@ def _kron_class():
     return Kron
 
 
+class _DeferredActivations(list):
+    """[X, H_1, ..., H_{L-1}] of ALL nodes in the column-parallel multi-GPU backward; entry l is produced by its
+    thunk (wait for the asynchronous all-gather, copy into natural node order) when it is first indexed."""
+
+    def __init__(self, first, n: int):
+        super().__init__([first] + [None] * (n - 1))
+        self._thunks: dict = {}
+
+    def defer(self, l: int, thunk) -> None:
+        self._thunks[l] = thunk
+
+    def __getitem__(self, i):
+        if isinstance(i, int):
+            j = i if i >= 0 else len(self) + i
+            thunk = self._thunks.pop(j, None)
+            if thunk is not None:
+                list.__setitem__(self, j, thunk())
+        return list.__getitem__(self, i)
+
+    def __iter__(self):
+        for j in range(len(self)):
+            yield self[j]
+
+
 class _Whole:
     """Backward layout: every graph row is local (single device, or the column-parallel backward)."""
 
@@ -618,17 +642,30 @@ class _B200KFAC:
             # every rank needs H_l (relu' masks) and the logits of ALL nodes: in-place all-gather of the padded
             # slabs the forward wrote its rows into, then into natural node order — persistent buffers, no
             # allocation per fit
-            full_H, full_logits = [Hs[0]], None          # slot 0 (the features) is never read by the backward
-            for l, t_loc in enumerate(Hs[1:] + [logits]):
-                w, slab = t_loc.shape[1], self._fwd_out[l]
+            # The logits are needed at once; the hidden activations only when the backward reaches their layer, so
+            # their all-gathers (2.5 GB into every rank each on the products shape) are issued asynchronously, last
+            # layer first, and waited for on first use (_DeferredActivations): they travel under the output-layer
+            # SpMM / SYRK / GEMM instead of in front of them.
+            def finish(l, w):
+                slab = self._fwd_out[l]
                 ldz = slab.shape[1]
-                with ops.timed("allgather", w, 4.0 * part.total_rows * ldz):
-                    part.all_gather_slab(slab)
-                full = part.compact(slab, ldz, out=_slab(dev, 1100 + l, 2, g.n * ldz).view(g.n, ldz))[:, :w]
-                if t_loc is logits:
-                    full_logits = full
-                else:
-                    full_H.append(full)
+                return part.compact(slab, ldz, out=_slab(dev, 1100 + l, 2, g.n * ldz).view(g.n, ldz))[:, :w]
+
+            l_top = len(Hs) - 1                                # index of the logits' slab in _fwd_out
+            with ops.timed("allgather", C, 4.0 * part.total_rows * self._fwd_out[l_top].shape[1]):
+                part.all_gather_slab(self._fwd_out[l_top])
+            full_logits = finish(l_top, C)
+            full_H = _DeferredActivations(Hs[0], len(Hs))      # slot 0 (the features) is never read by the backward
+            for l in range(len(Hs) - 1, 0, -1):                # H_l lives in _fwd_out[l - 1]
+                w = Hs[l].shape[1]
+                work = part.all_gather_slab(self._fwd_out[l - 1], async_op=dev.type == "cuda")
+
+                def ready(l=l, w=w, work=work):
+                    with ops.timed("allgather", w, 4.0 * part.total_rows * self._fwd_out[l - 1].shape[1]):
+                        if work is not None:
+                            work.wait()
+                    return finish(l - 1, w)
+                full_H.defer(l, ready)
             if self._want_hess_stats:
                 cp = (C + 3) // 4 * 4
                 whole.hess_stats = ops.hess_stats(full_logits, idx, self.hess_sqrt, C,
