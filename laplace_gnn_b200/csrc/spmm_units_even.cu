@@ -131,11 +131,17 @@ __global__ void __launch_bounds__(EVEN_THREADS, MINB) spmm_units_even_kernel(
     p = 0u;
     if (c >= 0) {
       uint32_t first;
-      if (NB == 2) {
-        const uint4 hd = __ldg(reinterpret_cast<const uint4*>(hdr + (int64_t)c * nblk));   // blocks 2w and 2w+1
+      if (NB >= 2) {
+        const uint4* h4 = reinterpret_cast<const uint4*>(hdr + (int64_t)c * nblk);   // blocks NB w .. NB w + NB - 1
+        const uint4 hd = __ldg(h4);
         m[0] = hd.x;
         first = hd.y;
-        m[NB - 1] = hd.z;
+        m[1 % NB] = hd.z;
+        if (NB == 4) {
+          const uint4 hd2 = __ldg(h4 + 1);
+          m[2 % NB] = hd2.x;
+          m[3 % NB] = hd2.z;
+        }
       } else {
         const uint2 hd = __ldg(hdr + (int64_t)c * nblk);
         m[0] = hd.x;
@@ -180,7 +186,8 @@ __global__ void __launch_bounds__(EVEN_THREADS, MINB) spmm_units_even_kernel(
       if (jj < cnt) {
         const uint32_t p = __shfl_sync(0xffffffffu, my_p, jj);
         int slots = __popc(__shfl_sync(0xffffffffu, my_m[0], jj));
-        if (NB == 2) slots = ((slots + 1) & ~1) + __popc(__shfl_sync(0xffffffffu, my_m[NB - 1], jj));
+#pragma unroll
+        for (int b = 1; b < NB; ++b) slots = ((slots + 1) & ~1) + __popc(__shfl_sync(0xffffffffu, my_m[b], jj));
         const int n16 = (slots * G2 + 1) >> 1;         // 16-byte pieces covering the run (the last may be half stale)
 #pragma unroll
         for (int t = 0; t < PIECES; ++t) {
@@ -203,19 +210,16 @@ __global__ void __launch_bounds__(EVEN_THREADS, MINB) spmm_units_even_kernel(
         row_end = __shfl_sync(0xffffffffu, my_rp, row + 1);
       }
       const float v = __shfl_sync(0xffffffffu, my_v, j);
-      const uint32_t m0 = __shfl_sync(0xffffffffu, my_m[0], j);
-      if ((m0 >> lane) & 1u) {
-        const uint32_t at = slot_c + 8u * (uint32_t)(__popc(m0 & lt) * G2);
+      int base = 0;                          // first slot of block b inside the run (every block starts on an even slot)
 #pragma unroll
-        for (int t = 0; t < G2; ++t) fma2(acc[0][t], v, lds_f2(at + 8u * t));
-      }
-      if (NB == 2) {
-        const uint32_t m1 = __shfl_sync(0xffffffffu, my_m[NB - 1], j);
-        if ((m1 >> lane) & 1u) {
-          const uint32_t at = slot_c + 8u * (uint32_t)((((__popc(m0) + 1) & ~1) + __popc(m1 & lt)) * G2);
+      for (int b = 0; b < NB; ++b) {
+        const uint32_t mb = __shfl_sync(0xffffffffu, my_m[b], j);
+        if ((mb >> lane) & 1u) {
+          const uint32_t at = slot_c + 8u * (uint32_t)((base + __popc(mb & lt)) * G2);
 #pragma unroll
-          for (int t = 0; t < G2; ++t) fma2(acc[NB - 1][t], v, lds_f2(at + 8u * t));
+          for (int t = 0; t < G2; ++t) fma2(acc[b][t], v, lds_f2(at + 8u * t));
         }
+        base += (__popc(mb) + 1) & ~1;
       }
       __syncwarp();                         // the slot is rewritten by the copy issued next iteration
       slot_c = (slot_c + SLOT == ring + U * SLOT) ? ring : slot_c + SLOT;
@@ -266,10 +270,16 @@ int spmm_units_even(int64_t n_rows, const int64_t* rowptr, const int32_t* col, c
   const int rpg = 4 << ((variant >> 2) & 1);
   const int cfg = variant & 3;
   const bool pair = (nblk % 2 == 0) && !(variant & 16) && (reinterpret_cast<uintptr_t>(hdr) & 15) == 0;
+  const bool quad = pair && (nblk % 4 == 0) && (variant & 32);       // lab: four unit blocks per warp
 #define LGNN_EVEN(G2_, NB_, U_, MINB_) launch_even<G2_, NB_, U_, MINB_>(n_rows, rowptr, col, val, slab, lds, hdr, nblk, y, ldy, rpg, st)
   switch (g) {
     case 2: return pair ? LGNN_EVEN(1, 2, 8, 3) : LGNN_EVEN(1, 1, 8, 3);
     case 6:
+      if (quad) switch (cfg) {
+        case 1: return LGNN_EVEN(3, 4, 3, 3);
+        case 2: return LGNN_EVEN(3, 4, 6, 2);
+        default: return LGNN_EVEN(3, 4, 4, 2);
+      }
       if (pair) switch (cfg) {
         case 1: return LGNN_EVEN(3, 2, 4, 3);
         case 2: return LGNN_EVEN(3, 2, 8, 2);
