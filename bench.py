@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--no-fused-hess-spmm", action="store_true",
                     help="materialise the Hessian-sqrt right-hand sides (round-1 path) instead of rebuilding them per edge "
                          "inside the output-layer SpMM (csrc/spmm_hess.cu)")
+    ap.add_argument("--no-defer-gathers", action="store_true",
+                    help="multi-GPU: all-gather the hidden activations in front of the backward instead of asynchronously under it")
     ap.add_argument("--no-shard-eigh", action="store_true",
                     help="multi-GPU: every rank decomposes every factor (round-1 behaviour) instead of a share of them")
     ap.add_argument("--rhs-tile-gb", type=float, default=None,
@@ -326,6 +328,7 @@ def main():
         bk["backward_parallel"] = args.backward_parallel
         bk["overlap"] = not args.no_overlap
         bk["shard_eigh"] = not args.no_shard_eigh
+        bk["defer_gathers"] = not args.no_defer_gathers
     loader = L.TensorBatchLoader(idx, y)      # one full batch, no per-sample collation
 
     def step(mdl, ldr, kwargs=None):

@@ -78,7 +78,8 @@ __device__ __forceinline__ void fma2(float2& a, float v, const float2& x) {
 // at g = 12 (profiles/r2a_units_lab.txt).  With NB = 2 a lane owns the units 32(2w) + L and 32(2w+1) + L: the
 // runs of two consecutive blocks are adjacent in the row (block 2w+1 starts where block 2w's slots, rounded up
 // to even, end), so the warp copies ONE run of twice the length per neighbour and reads both header words
-// with one 16-byte load — g = 6 then moves what g = 12 moves per iteration.
+// with one 16-byte load — g = 6 then moves what g = 12 moves per iteration.  (Four blocks per warp were no better: 84.7
+// against 82.4 ms at g = 6, profiles/r2n_units_lab.txt — occupancy drops to 16 warps per SM.)
 template <int G2, int NB, int U, int MINB>
 __global__ void __launch_bounds__(EVEN_THREADS, MINB) spmm_units_even_kernel(
     int64_t n_rows, const int64_t* __restrict__ rowptr, const int32_t* __restrict__ col,
@@ -270,16 +271,10 @@ int spmm_units_even(int64_t n_rows, const int64_t* rowptr, const int32_t* col, c
   const int rpg = 4 << ((variant >> 2) & 1);
   const int cfg = variant & 3;
   const bool pair = (nblk % 2 == 0) && !(variant & 16) && (reinterpret_cast<uintptr_t>(hdr) & 15) == 0;
-  const bool quad = pair && (nblk % 4 == 0) && (variant & 32);       // lab: four unit blocks per warp
 #define LGNN_EVEN(G2_, NB_, U_, MINB_) launch_even<G2_, NB_, U_, MINB_>(n_rows, rowptr, col, val, slab, lds, hdr, nblk, y, ldy, rpg, st)
   switch (g) {
     case 2: return pair ? LGNN_EVEN(1, 2, 8, 3) : LGNN_EVEN(1, 1, 8, 3);
     case 6:
-      if (quad) switch (cfg) {
-        case 1: return LGNN_EVEN(3, 4, 3, 3);
-        case 2: return LGNN_EVEN(3, 4, 6, 2);
-        default: return LGNN_EVEN(3, 4, 4, 2);
-      }
       if (pair) switch (cfg) {
         case 1: return LGNN_EVEN(3, 2, 4, 3);
         case 2: return LGNN_EVEN(3, 2, 8, 2);

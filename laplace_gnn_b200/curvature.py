@@ -194,7 +194,7 @@ class _B200KFAC:
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
                     rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                     fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=True, fused_hess_spmm=True, sparse_halo=False, fused_linear=True):
+                    unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=True, fused_hess_spmm=True, sparse_halo=False, fused_linear=True, defer_gathers=True):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -224,6 +224,9 @@ class _B200KFAC:
         # the forward linear layers Z_l = H_{l-1} W_l^T + b_l on the same tcgen05 kernel (lgnn_gemm_bias_f32);
         # False: cuBLAS fp32 (torch.addmm)
         self.fused_linear = bool(fused_linear)
+        # column-parallel multi-GPU backward: all-gathers of the hidden activations issued asynchronously and waited
+        # for on first use; False: gathered in front of the backward (round-1 order)
+        self.defer_gathers = bool(defer_gathers)
         self.skip_zero_rows = True
         # unit-compacted slabs below the output layer (csrc/spmm_units.cu): the relu' mask is shared by all
         # columns of a node, so the slab rows keep only their live hidden units and the SpMM gathers about
@@ -658,7 +661,7 @@ class _B200KFAC:
             full_H = _DeferredActivations(Hs[0], len(Hs))      # slot 0 (the features) is never read by the backward
             for l in range(len(Hs) - 1, 0, -1):                # H_l lives in _fwd_out[l - 1]
                 w = Hs[l].shape[1]
-                work = part.all_gather_slab(self._fwd_out[l - 1], async_op=dev.type == "cuda")
+                work = part.all_gather_slab(self._fwd_out[l - 1], async_op=dev.type == "cuda" and self.defer_gathers)
 
                 def ready(l=l, w=w, work=work):
                     with ops.timed("allgather", w, 4.0 * part.total_rows * self._fwd_out[l - 1].shape[1]):
@@ -721,7 +724,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
                  hess_sqrt="reference", differentiable=False, process_group=None,
                  rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
                  fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=True, fused_hess_spmm=True, sparse_halo=False, fused_linear=True):
+                 unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=True, fused_hess_spmm=True, sparse_halo=False, fused_linear=True, defer_gathers=True):
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -732,7 +735,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
         self.stochastic = False
         self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
                          backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs,
-                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split, fused_hess_spmm, sparse_halo, fused_linear)
+                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split, fused_hess_spmm, sparse_halo, fused_linear, defer_gathers)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 

@@ -24,7 +24,7 @@ def timed(fn, reps=3):
     return e0.elapsed_time(e1) / reps
 h = 256
 variants = {12: (1, 8, 9, 10, 11, 12, 13, 14, 15), 16: (1, 8, 9, 10, 12, 13, 14), 8: (1, 8, 12), 4: (1, 8, 12),
-            6: (8, 12, 40, 41, 42, 44), 10: (8, 9, 12), 14: (8, 9, 12), 2: (8, 12)}   # g % 4 == 2: spmm_units_even.cu   # 1: simple kernel, 8+: staged
+            6: (8, 9, 12, 24), 10: (8, 9, 12), 14: (8, 9, 12), 2: (8, 12)}   # g % 4 == 2: spmm_units_even.cu   # 1: simple kernel, 8+: staged
 print(f"n={n} nnz={g.nnz} peak={peak} GB/s", flush=True)
 for gg in [int(a) for a in sys.argv[1:]] or [12, 16]:
     d = gg * h
