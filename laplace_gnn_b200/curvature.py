@@ -191,10 +191,14 @@ class _Rows:
 class _B200KFAC:
     """kron()/diag() on the B200 kernels; mixed into a CurvatureInterface subclass."""
 
-    def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None,
-                    rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
-                    fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                    unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=True, fused_hess_spmm=True, sparse_halo=False, fused_linear=True, defer_gathers=True):
+    def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None, rhs_tile_bytes=None,
+                    syrk_impl="auto", backward_parallel="rows", overlap=True, fused_gemm=True, fused_linear=True,
+                    cache_input_factor=False, _shared_cache=None, diag_mode="exact",
+                    # data layout of the multi-RHS slabs (defaults = what the benchmark runs; off-switches for A/B)
+                    unit_slabs=True, unit_min_width=1024, unit_even_groups=True, unit_hub_split=True,
+                    fused_hess_spmm=True,
+                    # multi-GPU
+                    shard_eigh=True, defer_gathers=True, sparse_halo=False):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -720,11 +724,9 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
     ``laplace.curvature.GGNInterface`` when integrating into that package)."""
 
     def __init__(self, model, likelihood, last_layer=False, subnetwork_indices=None,
-                 dict_key_x="input_ids", dict_key_y="labels", stochastic=False,
-                 hess_sqrt="reference", differentiable=False, process_group=None,
-                 rhs_tile_bytes=None, syrk_impl="auto", backward_parallel="rows", overlap=True,
-                 fused_gemm=True, cache_input_factor=False, _shared_cache=None, unit_slabs=True,
-                 unit_min_width=1024, diag_mode="exact", unit_even_groups=True, shard_eigh=True, unit_hub_split=True, fused_hess_spmm=True, sparse_halo=False, fused_linear=True, defer_gathers=True):
+                 dict_key_x="input_ids", dict_key_y="labels", stochastic=False, **b200_options):
+        """``b200_options``: the keyword switches of ``_B200KFAC._b200_setup`` (hess_sqrt, process_group,
+        backward_parallel, rhs_tile_bytes, ...); an unknown one raises TypeError there."""
         if stochastic:
             raise NotImplementedError("the MC Fisher is outside the hot path (TYPE2 GGN only)")
         try:
@@ -733,9 +735,7 @@ def make_backend(base: type, name: str = "B200GGN") -> type:
             base.__init__(self, model, likelihood, last_layer, subnetwork_indices, dict_key_x,
                           dict_key_y, stochastic)
         self.stochastic = False
-        self._b200_setup(hess_sqrt, differentiable, process_group, rhs_tile_bytes, syrk_impl,
-                         backward_parallel, overlap, fused_gemm, cache_input_factor, _shared_cache, unit_slabs,
-                         unit_min_width, diag_mode, unit_even_groups, shard_eigh, unit_hub_split, fused_hess_spmm, sparse_halo, fused_linear, defer_gathers)
+        self._b200_setup(**b200_options)
 
     return type(name, (_B200KFAC, base), {"__init__": __init__, "__doc__": __doc__})
 
