@@ -58,6 +58,8 @@ def parse_args():
                          "inside the output-layer SpMM (csrc/spmm_hess.cu)")
     ap.add_argument("--no-defer-gathers", action="store_true",
                     help="multi-GPU: all-gather the hidden activations in front of the backward instead of asynchronously under it")
+    ap.add_argument("--no-unit-rows", action="store_true",
+                    help="multi-GPU rows layout: exchange dense slabs (round-1 behaviour) instead of ragged unit-compacted rows")
     ap.add_argument("--no-shard-eigh", action="store_true",
                     help="multi-GPU: every rank decomposes every factor (round-1 behaviour) instead of a share of them")
     ap.add_argument("--rhs-tile-gb", type=float, default=None,
@@ -329,6 +331,7 @@ def main():
         bk["overlap"] = not args.no_overlap
         bk["shard_eigh"] = not args.no_shard_eigh
         bk["defer_gathers"] = not args.no_defer_gathers
+        bk["unit_rows"] = not args.no_unit_rows
     loader = L.TensorBatchLoader(idx, y)      # one full batch, no per-sample collation
 
     def step(mdl, ldr, kwargs=None):

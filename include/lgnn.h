@@ -160,6 +160,24 @@ int lgnn_spmm_units_f32(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64
                         const float* val, const float* slab, int64_t lds, const void* hdr, int64_t g,
                         int64_t h, float* y, int64_t ldy, int flags, lgnn_stream_t stream);
 
+/* Ragged unit-compacted rows, for the row-partitioned backward (a rank packs its row block, the packed rows are
+ * what the ranks exchange before the SpMM — the reference's per-layer Â^T product of curvlinops/kfac.py:653-661
+ * on a graph split by rows).  Node n's live slots start at the ABSOLUTE slot row_first[n] of dst (rows back to
+ * back: row_first = exclusive scan of the rows' slot counts, + the rank's base in the gathered buffer; for
+ * g % 4 == 2 a 32-unit block takes its live count rounded up to even, as in lgnn_unit_pack_f32), and the header
+ * words carry absolute slots, so the SpMM needs no pitch.
+ *   lgnn_unit_pack_ragged_f32   src [n_rows, lds] dense [g][h] rows -> dst (must not overlap src);
+ *                               src == NULL: headers only;  hdr == NULL: values only
+ *   lgnn_spmm_units_ragged_f32  as lgnn_spmm_units_f32 on a slab of slab_floats floats packed that way
+ *                               (at most 2^32 slots) */
+int lgnn_unit_pack_ragged_f32(const float* src, int64_t lds, const float* act, int64_t lda, int64_t n_rows,
+                              int64_t g, int64_t h, const int64_t* row_first, float* dst, void* hdr,
+                              lgnn_stream_t stream);
+int lgnn_spmm_units_ragged_f32(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* rowptr,
+                               const int32_t* col, const float* val, const float* slab, int64_t slab_floats,
+                               const void* hdr, int64_t g, int64_t h, float* y, int64_t ldy, int flags,
+                               lgnn_stream_t stream);
+
 /* Sampled dense-dense products: out[e] (+)= U[rows[e], 0:d] . V[cols[e], 0:d] for n_pairs (row, column)
  * pairs (int32).  The adjoint of Â[i, j] wherever the path computes Y = Â X is Ybar[i, :] . X[j, :]; summed
  * over the forward and the KFAC backward this is d marglik / dÂ on the requested entries — what the

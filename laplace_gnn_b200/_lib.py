@@ -41,6 +41,8 @@ PROTOTYPES = {
     "lgnn_unit_slabs_supported": (C.c_int, [_i64, _i64]),
     "lgnn_unit_pack_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "lgnn_spmm_units_f32": (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, C.c_int, _vp]),
+    "lgnn_unit_pack_ragged_f32": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "lgnn_spmm_units_ragged_f32": (C.c_int, [_i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, _i64, C.c_int, _vp]),
     "lgnn_sddmm_f32": (C.c_int, [_i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _vp, C.c_int, _vp]),
     "lgnn_softmax_ce_sum": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp, _vp]),
     "lgnn_hess_rhs_f32": (C.c_int, [_vp, _i64, _i32, _vp, _i64, _i32, _i32, _i32, C.c_int, _vp, _vp]),

@@ -67,8 +67,20 @@ __device__ __forceinline__ int64_t row_lower_bound(const int64_t* __restrict__ r
 
 // unit-compacted slabs for column groups with g % 4 == 2 (spmm_units_even.cu); the C ABI entry points of
 // spmm_units.cu validate the arguments and dispatch here
-int unit_pack_even(float* slab, int64_t lds, const float* act, int64_t lda, int64_t n_rows, int g, int h, uint2* hdr,
-                   cudaStream_t st);
+// src [n_rows, lds] dense [g][h] rows (nullptr: headers only) -> dst: row n at dst + n*ldd (in place when
+// dst == src, ldd == lds), or, with row_first, at the absolute slot row_first[n] (ragged rows, back to back)
+struct UnitPackArgs {
+  const float* src;
+  int64_t lds;
+  float* dst;
+  int64_t ldd;
+  const int64_t* row_first;
+  const float* act;
+  int64_t lda;
+  int h;
+  uint2* hdr;     // nullptr: values only
+};
+int unit_pack_even(const UnitPackArgs& A, int64_t n_rows, int g, cudaStream_t st);
 int spmm_units_even(int64_t n_rows, const int64_t* rowptr, const int32_t* col, const float* val, const float* slab,
                     int64_t lds, const uint2* hdr, int g, int nblk, float* y, int64_t ldy, int variant,
                     cudaStream_t st);

@@ -30,26 +30,33 @@ namespace lgnn {
 
 constexpr int UNITS_THREADS = 256;
 
+// One CTA per node, one thread per hidden unit.  In place (src == dst, same pitch) the barrier between the loads
+// and the stores is what makes the rewrite safe.  Ragged (row_first given): node n's slots start at the ABSOLUTE
+// slot row_first[n] of dst — rows lie back to back, which is what travels between ranks in the row-partitioned
+// backward — and the header words carry absolute slots (the SpMM is then launched with pitch 0).  src == nullptr
+// writes the headers only, hdr == nullptr the values only.
 template <int G4>
-__global__ void __launch_bounds__(1024) unit_pack_kernel(float* __restrict__ slab, int64_t lds,
-                                                         const float* __restrict__ act, int64_t lda, int h,
-                                                         uint2* __restrict__ hdr) {
+__global__ void __launch_bounds__(1024) unit_pack_kernel(const UnitPackArgs A) {
   __shared__ uint32_t cnt[32];
   const int u = threadIdx.x, lane = u & 31, w = u >> 5;
   const int64_t row = blockIdx.x;
-  float* base = slab + row * lds;
-  const bool on = __ldg(act + row * lda + u) > 0.f;
+  const int64_t r0 = A.row_first ? __ldg(A.row_first + row) : 0;
+  const bool on = __ldg(A.act + row * A.lda + u) > 0.f;
   const uint32_t m = __ballot_sync(0xffffffffu, on);
   if (lane == 0) cnt[w] = __popc(m);
   float v[4 * G4];
+  if (A.src) {
+    const float* base = A.src + row * A.lds;
 #pragma unroll
-  for (int c = 0; c < 4 * G4; ++c) v[c] = base[(int64_t)c * h + u];
+    for (int c = 0; c < 4 * G4; ++c) v[c] = base[(int64_t)c * A.h + u];
+  }
   __syncthreads();                      // every dense value is in registers before the row is overwritten
   uint32_t first = 0;
   for (int b = 0; b < w; ++b) first += cnt[b];
-  if (lane == 0) hdr[row * (h >> 5) + w] = make_uint2(m, first);
-  if (on) {
-    float4* dst = reinterpret_cast<float4*>(base + (int64_t)(first + __popc(m & ((1u << lane) - 1u))) * (4 * G4));
+  if (lane == 0 && A.hdr) A.hdr[row * (A.h >> 5) + w] = make_uint2(m, (uint32_t)r0 + first);
+  if (on && A.src) {
+    float* out = A.row_first ? A.dst + r0 * (4 * G4) : A.dst + row * A.ldd;
+    float4* dst = reinterpret_cast<float4*>(out + (int64_t)(first + __popc(m & ((1u << lane) - 1u))) * (4 * G4));
 #pragma unroll
     for (int t = 0; t < G4; ++t) dst[t] = make_float4(v[4 * t], v[4 * t + 1], v[4 * t + 2], v[4 * t + 3]);
   }
@@ -338,6 +345,19 @@ using namespace lgnn;
 
 extern "C" int lgnn_unit_slabs_supported(int64_t g, int64_t h) { return units_shape_ok(g, h) ? 1 : 0; }
 
+static int unit_pack_launch(const UnitPackArgs& A, int64_t n_rows, int64_t g, cudaStream_t st) {
+  if (g % 4 != 0) return unit_pack_even(A, n_rows, (int)g, st);
+  const unsigned grid = (unsigned)n_rows, block = (unsigned)A.h;
+  switch (g / 4) {
+    case 1: unit_pack_kernel<1><<<grid, block, 0, st>>>(A); break;
+    case 2: unit_pack_kernel<2><<<grid, block, 0, st>>>(A); break;
+    case 3: unit_pack_kernel<3><<<grid, block, 0, st>>>(A); break;
+    default: unit_pack_kernel<4><<<grid, block, 0, st>>>(A); break;
+  }
+  LGNN_LAUNCH_CHECK("unit_pack_kernel");
+  return LGNN_OK;
+}
+
 extern "C" int lgnn_unit_pack_f32(float* slab, int64_t lds, const float* act, int64_t lda, int64_t n_rows,
                                   int64_t g, int64_t h, void* hdr, lgnn_stream_t stream) {
   if (n_rows < 0) return fail(LGNN_E_BADARG, "unit_pack: negative row count");
@@ -348,19 +368,31 @@ extern "C" int lgnn_unit_pack_f32(float* slab, int64_t lds, const float* act, in
   if ((reinterpret_cast<uintptr_t>(slab) & 15) || (lds % 4) || (reinterpret_cast<uintptr_t>(hdr) & 7))
     return fail(LGNN_E_ALIGN, "unit_pack: slab must be 16-byte aligned with a pitch that is a multiple of 4 floats, hdr 8-byte aligned");
   if (n_rows > 0x7fffffffLL) return fail(LGNN_E_UNSUPPORTED, "unit_pack: too many rows");
-  cudaStream_t st = as_stream(stream);
-  uint2* hd = reinterpret_cast<uint2*>(hdr);
-  if (g % 4 != 0) return unit_pack_even(slab, lds, act, lda, n_rows, (int)g, (int)h, hd, st);
-  const unsigned grid = (unsigned)n_rows, block = (unsigned)h;
-  switch (g / 4) {
-    case 1: unit_pack_kernel<1><<<grid, block, 0, st>>>(slab, lds, act, lda, (int)h, hd); break;
-    case 2: unit_pack_kernel<2><<<grid, block, 0, st>>>(slab, lds, act, lda, (int)h, hd); break;
-    case 3: unit_pack_kernel<3><<<grid, block, 0, st>>>(slab, lds, act, lda, (int)h, hd); break;
-    default: unit_pack_kernel<4><<<grid, block, 0, st>>>(slab, lds, act, lda, (int)h, hd); break;
-  }
-  LGNN_LAUNCH_CHECK("unit_pack_kernel");
-  return LGNN_OK;
+  UnitPackArgs A{slab, lds, slab, lds, nullptr, act, lda, (int)h, reinterpret_cast<uint2*>(hdr)};
+  return unit_pack_launch(A, n_rows, g, as_stream(stream));
 }
+
+extern "C" int lgnn_unit_pack_ragged_f32(const float* src, int64_t lds, const float* act, int64_t lda,
+                                         int64_t n_rows, int64_t g, int64_t h, const int64_t* row_first,
+                                         float* dst, void* hdr, lgnn_stream_t stream) {
+  if (n_rows < 0) return fail(LGNN_E_BADARG, "unit_pack_ragged: negative row count");
+  if (!units_shape_ok(g, h)) return fail(LGNN_E_UNSUPPORTED, "unit_pack_ragged: g must be even, 2 .. 16, and h a multiple of 32 up to 1024 (g=%lld h=%lld)", (long long)g, (long long)h);
+  if (n_rows == 0) return LGNN_OK;
+  if (!act || !row_first) return fail(LGNN_E_BADARG, "unit_pack_ragged: null act / row_first");
+  if (!src && !hdr) return fail(LGNN_E_BADARG, "unit_pack_ragged: neither values (src) nor headers (hdr) asked for");
+  if (src && !dst) return fail(LGNN_E_BADARG, "unit_pack_ragged: src without dst");
+  if (lda < h || (src && lds < g * h)) return fail(LGNN_E_BADARG, "unit_pack_ragged: pitch smaller than the row");
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) || (reinterpret_cast<uintptr_t>(hdr) & 7) || (reinterpret_cast<uintptr_t>(row_first) & 7))
+    return fail(LGNN_E_ALIGN, "unit_pack_ragged: dst must be 16-byte aligned, hdr and row_first 8-byte aligned");
+  if (n_rows > 0x7fffffffLL) return fail(LGNN_E_UNSUPPORTED, "unit_pack_ragged: too many rows");
+  UnitPackArgs A{src, lds, dst, 0, row_first, act, lda, (int)h, reinterpret_cast<uint2*>(hdr)};
+  return unit_pack_launch(A, n_rows, g, as_stream(stream));
+}
+
+// slab_floats: extent of the slab (decides whether the 32-bit float4 offsets of the pipelined kernels reach it)
+static int spmm_units_dispatch(int64_t n_rows, const int64_t* rowptr, const int32_t* col, const float* val,
+                               const float* slab, int64_t lds, int64_t slab_floats, const void* hdr, int64_t g,
+                               int64_t h, float* y, int64_t ldy, int flags, lgnn_stream_t stream);
 
 extern "C" int lgnn_spmm_units_f32(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* rowptr, const int32_t* col,
                                    const float* val, const float* slab, int64_t lds, const void* hdr,
@@ -374,6 +406,30 @@ extern "C" int lgnn_spmm_units_f32(int64_t n_rows, int64_t n_cols, int64_t nnz, 
   if (lds < g * h || ldy < g * h) return fail(LGNN_E_BADARG, "spmm_units: pitch smaller than the row");
   if ((reinterpret_cast<uintptr_t>(slab) & 15) || (lds % 4) || (reinterpret_cast<uintptr_t>(hdr) & 7))
     return fail(LGNN_E_ALIGN, "spmm_units: slab must be 16-byte aligned with a pitch that is a multiple of 4 floats, hdr 8-byte aligned");
+  return spmm_units_dispatch(n_rows, rowptr, col, val, slab, lds, n_cols * lds, hdr, g, h, y, ldy, flags, stream);
+}
+
+// Ragged rows (lgnn_unit_pack_ragged_f32): the headers hold absolute slots, so a row is found through its header
+// alone — the kernels are the same, run with pitch 0.
+extern "C" int lgnn_spmm_units_ragged_f32(int64_t n_rows, int64_t n_cols, int64_t nnz, const int64_t* rowptr,
+                                          const int32_t* col, const float* val, const float* slab,
+                                          int64_t slab_floats, const void* hdr, int64_t g, int64_t h, float* y,
+                                          int64_t ldy, int flags, lgnn_stream_t stream) {
+  if (n_rows < 0 || n_cols < 0 || nnz < 0 || slab_floats < 0) return fail(LGNN_E_BADARG, "spmm_units_ragged: negative size");
+  if (!units_shape_ok(g, h)) return fail(LGNN_E_UNSUPPORTED, "spmm_units_ragged: g must be even, 2 .. 16, and h a multiple of 32 up to 1024 (g=%lld h=%lld)", (long long)g, (long long)h);
+  if (n_rows == 0) return LGNN_OK;
+  if (!rowptr || !slab || !hdr || !y) return fail(LGNN_E_BADARG, "spmm_units_ragged: null pointer");
+  if (nnz > 0 && (!col || !val)) return fail(LGNN_E_BADARG, "spmm_units_ragged: null col / val");
+  if (ldy < g * h) return fail(LGNN_E_BADARG, "spmm_units_ragged: pitch smaller than the row");
+  if ((reinterpret_cast<uintptr_t>(slab) & 15) || (reinterpret_cast<uintptr_t>(hdr) & 7))
+    return fail(LGNN_E_ALIGN, "spmm_units_ragged: slab must be 16-byte aligned, hdr 8-byte aligned");
+  if (slab_floats / g > 0xffffffffLL) return fail(LGNN_E_UNSUPPORTED, "spmm_units_ragged: more than 2^32 slots");
+  return spmm_units_dispatch(n_rows, rowptr, col, val, slab, 0, slab_floats, hdr, g, h, y, ldy, flags, stream);
+}
+
+static int spmm_units_dispatch(int64_t n_rows, const int64_t* rowptr, const int32_t* col, const float* val,
+                               const float* slab, int64_t lds, int64_t slab_floats, const void* hdr, int64_t g,
+                               int64_t h, float* y, int64_t ldy, int flags, lgnn_stream_t stream) {
   cudaStream_t st = as_stream(stream);
   const uint2* hd = reinterpret_cast<const uint2*>(hdr);
   const int nblk = (int)(h / 32);
@@ -382,7 +438,7 @@ extern "C" int lgnn_spmm_units_f32(int64_t n_rows, int64_t n_cols, int64_t nnz, 
   // ring of 4, 3 CTAs per SM (182.7 against 187.8 ms); g = 12: ring of 4, 4 CTAs per SM (139.1 against 141.7 ms)
   if (variant == 0 && g % 4 == 0) variant = g == 16 ? 14 : (g == 12 ? 13 : 12);
   // the pipelined kernel addresses the slab with 32-bit float4 offsets: slabs up to 64 GB
-  const bool narrow = n_cols * lds <= ((int64_t)1 << 34);
+  const bool narrow = slab_floats <= ((int64_t)1 << 34);
   if (g % 4 != 0) {
     if (!narrow) return fail(LGNN_E_UNSUPPORTED, "spmm_units: g = %lld needs a slab of at most 64 GB", (long long)g);
     return spmm_units_even(n_rows, rowptr, col, val, slab, lds, hd, (int)g, nblk, y, ldy, variant, st);

@@ -26,25 +26,27 @@ namespace {
 constexpr int EVEN_THREADS = 256;
 
 template <int G2>
-__global__ void __launch_bounds__(1024) unit_pack_even_kernel(float* __restrict__ slab, int64_t lds,
-                                                              const float* __restrict__ act, int64_t lda, int h,
-                                                              uint2* __restrict__ hdr) {
+__global__ void __launch_bounds__(1024) unit_pack_even_kernel(const UnitPackArgs A) {
   __shared__ uint32_t cnt[32];
   const int u = threadIdx.x, lane = u & 31, w = u >> 5;
   const int64_t row = blockIdx.x;
-  float* base = slab + row * lds;
-  const bool on = __ldg(act + row * lda + u) > 0.f;
+  const int64_t r0 = A.row_first ? __ldg(A.row_first + row) : 0;       // ragged: absolute (even) slot of the row
+  const bool on = __ldg(A.act + row * A.lda + u) > 0.f;
   const uint32_t m = __ballot_sync(0xffffffffu, on);
   if (lane == 0) cnt[w] = ((uint32_t)__popc(m) + 1u) & ~1u;      // slots this block takes: live count rounded up to even
   float v[2 * G2];
+  if (A.src) {
+    const float* base = A.src + row * A.lds;
 #pragma unroll
-  for (int c = 0; c < 2 * G2; ++c) v[c] = base[(int64_t)c * h + u];
+    for (int c = 0; c < 2 * G2; ++c) v[c] = base[(int64_t)c * A.h + u];
+  }
   __syncthreads();                      // every dense value is in registers before the row is overwritten
   uint32_t first = 0;
   for (int b = 0; b < w; ++b) first += cnt[b];
-  if (lane == 0) hdr[row * (h >> 5) + w] = make_uint2(m, first);
-  if (on) {
-    float2* dst = reinterpret_cast<float2*>(base + (int64_t)(first + __popc(m & ((1u << lane) - 1u))) * (2 * G2));
+  if (lane == 0 && A.hdr) A.hdr[row * (A.h >> 5) + w] = make_uint2(m, (uint32_t)r0 + first);
+  if (on && A.src) {
+    float* out = A.row_first ? A.dst + r0 * (2 * G2) : A.dst + row * A.ldd;
+    float2* dst = reinterpret_cast<float2*>(out + (int64_t)(first + __popc(m & ((1u << lane) - 1u))) * (2 * G2));
 #pragma unroll
     for (int t = 0; t < G2; ++t) dst[t] = make_float2(v[2 * t], v[2 * t + 1]);
   }
@@ -249,14 +251,13 @@ int launch_even(int64_t n_rows, const int64_t* rowptr, const int32_t* col, const
 
 }  // namespace
 
-int unit_pack_even(float* slab, int64_t lds, const float* act, int64_t lda, int64_t n_rows, int g, int h, uint2* hdr,
-                   cudaStream_t st) {
-  const unsigned grid = (unsigned)n_rows, block = (unsigned)h;
+int unit_pack_even(const UnitPackArgs& A, int64_t n_rows, int g, cudaStream_t st) {
+  const unsigned grid = (unsigned)n_rows, block = (unsigned)A.h;
   switch (g) {
-    case 2: unit_pack_even_kernel<1><<<grid, block, 0, st>>>(slab, lds, act, lda, h, hdr); break;
-    case 6: unit_pack_even_kernel<3><<<grid, block, 0, st>>>(slab, lds, act, lda, h, hdr); break;
-    case 10: unit_pack_even_kernel<5><<<grid, block, 0, st>>>(slab, lds, act, lda, h, hdr); break;
-    case 14: unit_pack_even_kernel<7><<<grid, block, 0, st>>>(slab, lds, act, lda, h, hdr); break;
+    case 2: unit_pack_even_kernel<1><<<grid, block, 0, st>>>(A); break;
+    case 6: unit_pack_even_kernel<3><<<grid, block, 0, st>>>(A); break;
+    case 10: unit_pack_even_kernel<5><<<grid, block, 0, st>>>(A); break;
+    case 14: unit_pack_even_kernel<7><<<grid, block, 0, st>>>(A); break;
     default: return fail(LGNN_E_UNSUPPORTED, "unit_pack: g = %d is not 2, 6, 10 or 14", g);
   }
   LGNN_LAUNCH_CHECK("unit_pack_even_kernel");

@@ -177,6 +177,7 @@ class _Rows:
         self.csr_t_top = None
         self.split_t = None
         self.hess_stats = None
+        self.plans = {}              # (layer, even-slot layout) -> _RaggedPlan, built per kron call
 
     def gather(self, slab):
         self.part.exchange_for_spmm(slab)
@@ -186,6 +187,43 @@ class _Rows:
         t = torch.tensor([value], dtype=torch.int64, device=self.part.ahat.rowptr.device)
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MIN, group=self.part.pg)
         return int(t.item())
+
+
+class _RaggedPlan:
+    """Where the unit-compacted rows of one hidden layer live in the buffer the ranks all-gather (rows layout).
+
+    The live units of a node are the same for every Hessian-sqrt column and every column group (relu' of H_l), so
+    the plan is made once per fit and layer: rank r packs its rows back to back from slot r*cap on (``row_first``:
+    r*cap + exclusive scan of the rows' slot counts; ``cap`` = the largest per-rank total, agreed by one MAX
+    all-reduce), and the header words (mask, ABSOLUTE first slot per 32 units) of all nodes are all-gathered once —
+    8 bytes per 32 units against the g*4*32 bytes of a group's values."""
+
+    def __init__(self, part, act, g: int, hdr: torch.Tensor):
+        dev = act.device
+        n_loc, h = int(act.shape[0]), int(act.shape[1])
+        slots = ops.unit_row_slots(act, g)
+        scan = torch.cumsum(slots, 0)
+        top = scan[-1:].clone() if n_loc > 0 else torch.zeros(1, dtype=torch.int64, device=dev)
+        torch.distributed.all_reduce(top, op=torch.distributed.ReduceOp.MAX, group=part.pg)
+        self.cap = max((int(top.item()) + 3) // 4 * 4, 4)          # slots per rank, 16-byte aligned for every g
+        self.world = part.world
+        self.ok = self.world * self.cap < (1 << 32)                 # header slots are 32-bit
+        self.hdr = hdr
+        self.live = None
+        if not self.ok:
+            return
+        self.row_first = (scan - slots + part.rank * self.cap).contiguous()
+        hdr.zero_()                                                 # pad rows: empty masks
+        ops.unit_pack_ragged(None, act, g, self.row_first, None, hdr[part.slot0:part.slot0 + n_loc])
+        part.all_gather_slab(hdr)
+        if ops.PROFILE is not None:                                 # live units of every node, for the byte accounting
+            live = torch.zeros(part.total_rows, dtype=torch.int64, device=dev)
+            live[part.slot0:part.slot0 + n_loc] = (act > 0).sum(1)
+            part.all_gather_slab(live)
+            self.live = live
+
+    def floats(self, g: int) -> int:
+        return self.world * self.cap * g
 
 
 class _B200KFAC:
@@ -198,7 +236,7 @@ class _B200KFAC:
                     unit_slabs=True, unit_min_width=1024, unit_even_groups=True, unit_hub_split=True,
                     fused_hess_spmm=True,
                     # multi-GPU
-                    shard_eigh=True, defer_gathers=True, sparse_halo=False):
+                    shard_eigh=True, defer_gathers=True, sparse_halo=False, unit_rows=True):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -259,6 +297,10 @@ class _B200KFAC:
         # locality, partitioned), exchange only those halo rows (all-to-all) instead of all-gathering whole slabs
         # (dist.RowPartition.exchange_for_spmm).  OFF until the all-to-all has run over NCCL (gloo-tested)
         self.sparse_halo = bool(sparse_halo)
+        # unit-compacted slabs in the "rows" layout too: a rank packs the live units of its row block back to back
+        # (ops.unit_pack_ragged), the packed rows are what the all-gather moves (about half the dense slab) and what
+        # the SpMM then gathers from (_RaggedPlan).  False: dense slabs travel (the round-1 rows layout)
+        self.unit_rows = bool(unit_rows)
         self.unit_row_limit = 4096
         # A_0 = X^T X does not depend on the weights: with cache_input_factor the raw Gram matrix of
         # this rank's feature rows is kept (per backend, or in a dict shared across backends by the
@@ -400,7 +442,7 @@ class _B200KFAC:
         part.sparse_halo_below = 0.5 if self.sparse_halo else 0.0
         return part
 
-    def _chain(self, lay, logits, idx, Hs, Ws, Wp, c0, gc, gq, buf_a, buf_b, G, hdr=None):
+    def _chain(self, lay, logits, idx, Hs, Ws, Wp, c0, gc, gq, buf_a, buf_b, G, hdr=None, scratch=None):
         """One group of ``gc`` Hessian-sqrt columns pushed down all layers; a generator that yields
         after each layer so that two groups can be interleaved on two streams (their all-gathers
         then overlap the other group's SpMM).  ``gq >= gc`` is the group's width in the slabs: the
@@ -411,7 +453,9 @@ class _B200KFAC:
         row is local (single GPU, or the column-parallel backward) it is compacted in place to the live
         units of each node (``ops.unit_pack``, which applies the mask itself) and the SpMM gathers only
         those (``ops.spmm_units``).  (A per-element compression of the same slabs was 2x slower than the dense
-        gather — profiles/r1g_pack_lab.txt — and has left the tree.)"""
+        gather — profiles/r1g_pack_lab.txt — and has left the tree.)  In the rows layout (``scratch`` given) the GEMM
+        writes this rank's dense rows into ``scratch``, they are packed back to back into ``buf_a`` at the slots of
+        the layer's ``_RaggedPlan``, and the all-gather moves the packed rows only."""
         L = len(Ws)
         C = logits.shape[1]
         dims = [w.shape[0] for w in Ws]                 # d_1 .. d_L (d_L = C)
@@ -455,7 +499,13 @@ class _B200KFAC:
                 d_prev = dims[l - 1]
                 slab = P[: n_in * gq * d_prev].view(n_in, gq * d_prev)
                 nxt = slab[slot0:slot0 + n_loc].view(n_loc * gq, d_prev)
-                to_units = hdr is not None and self._can_unit(lay, gq, d_prev)
+                plan = lay.plans.get((l, gq % 4 != 0)) if (scratch is not None and lay.communicates) else None
+                if plan is not None and not (plan.ok and self._can_unit(lay, gq, d_prev)):
+                    plan = None
+                if plan is not None:
+                    nxt = scratch[: n_loc * gq * d_prev].view(n_loc * gq, d_prev)
+                to_units = plan is not None or (hdr is not None and not lay.communicates and
+                                                self._can_unit(lay, gq, d_prev))
                 act = None if to_units else Hs[l]           # unit_pack drops the dead units: no mask needed
                 if Wp[l] is not None:      # fused 3xTF32 tensor-core GEMM (+ relu' mask)
                     ops.gemm_mask(gz_rows, Wp[l], act, gq, out=nxt, m_rows=n_loc * gq)
@@ -466,14 +516,22 @@ class _B200KFAC:
                         with ops.timed("relu_mask", d_prev, 2.0 * n_loc * gq * d_prev * 4):
                             ops.relu_mask_mul(nxt, act, gq)
                 width, ld = d_prev, d_prev
-                units = ops.unit_pack(slab, Hs[l], gq, hdr=hdr) if to_units else None
+                if plan is not None:
+                    flat = P[: plan.floats(gq)]
+                    ops.unit_pack_ragged(nxt.view(n_loc, gq * d_prev), Hs[l][:, :d_prev], gq, plan.row_first, flat, None)
+                    with ops.timed("allgather", gq * d_prev, 4.0 * plan.floats(gq)):
+                        lay.part.all_gather_slab(flat)
+                    units = ops.UnitSlab(n_in, gq, d_prev, flat, plan.hdr, None, plan.live, ragged=True)
+                else:
+                    units = ops.unit_pack(slab, Hs[l], gq, hdr=hdr) if to_units else None
             yield
 
     def _units_possible(self, lay) -> bool:
         """Unit-compacted slabs need every row local and a graph without hub rows (the kernel gives one
         warp a whole row)."""
         mx = lay.csr_t.max_row_nnz
-        return (self.unit_slabs and not lay.communicates and mx is not None and
+        local = not lay.communicates or (self.unit_rows and not lay.part.sparse_halo)   # rows layout: ragged rows travel
+        return (self.unit_slabs and local and mx is not None and
                 (mx <= self.unit_row_limit or lay.split_t is not None))
 
     def _can_unit(self, lay, g: int, h: int) -> bool:
@@ -495,7 +553,9 @@ class _B200KFAC:
         # group at a time, 1,972 against 1,786 ms per products fit: the persistent tensor-core CTAs and the SpMM's
         # CTAs time-slice the SMs instead of sharing them; profiles/r2a_lab_switches.txt.)
         lanes = 2 if (self.overlap and lay.communicates and dev.type == "cuda") else 1
-        room = self._group_size(lanes * n_in, lanes * n_loc, dmax, 1 << 30, dev)   # columns the HBM budget allows
+        ragged = lay.communicates and self._units_possible(lay)     # rows layout with unit-compacted rows travelling
+        # columns the HBM budget allows (ragged: a third, local slab per lane for the GEMM's dense rows)
+        room = self._group_size(lanes * n_in, lanes * n_loc * (2 if ragged else 1), dmax, 1 << 30, dev)
         grp = min(room, C)
         grp = lay.agree_min(max(1, min(grp, (c_count + lanes - 1) // lanes)))
         # unit-compacted slabs want groups of 4, 8, 12 or 16 columns (any even count with unit_even_groups):
@@ -515,8 +575,22 @@ class _B200KFAC:
             return grp, 0
         groups = [(c0, min(grp, c_first + c_count - c0)) for c0 in range(c_first, c_first + c_count, grp)]
         width_of = (lambda gc: (gc + q - 1) // q * q) if pad4 else (lambda gc: gc)
-        hdr = torch.empty(n_in, max(max(dims[:-1]) // 32, 1), 2, dtype=torch.int32, device=dev) if pad4 else None
+        ragged = ragged and pad4
+        hdr = (torch.empty(n_in, max(max(dims[:-1]) // 32, 1), 2, dtype=torch.int32, device=dev)
+               if pad4 and not ragged else None)
         hdrs = [hdr, torch.empty_like(hdr) if (hdr is not None and lanes > 1) else None]
+        if ragged:
+            # one plan per hidden layer and slot layout (every rank takes the same branches: widths, limits and the
+            # agreed capacity are the same everywhere), made on the main stream before the lanes start
+            for gq in sorted({width_of(gc) for _, gc in groups}):
+                for l in range(1, len(Ws)):
+                    h = dims[l - 1]
+                    key = (l, gq % 4 != 0)
+                    if key in lay.plans or not self._can_unit(lay, gq, h):
+                        continue
+                    words = _slab(dev, 1200 + l, int(key[1]), n_in * (h // 32) * 2).view(torch.int32)
+                    lay.plans[key] = _RaggedPlan(lay.part, Hs[l][:, :h], gq, words.view(n_in, h // 32, 2))
+            ragged = any(p.ok for p in lay.plans.values())
         # W_l [d_l, d_{l-1}] as resident tensor-core operands, once per pass
         Wp = [None] + [ops.gemm_mask_prepare(Ws[l]) if self.fused_gemm and dev.type == "cuda" and
                        ops.gemm_mask_supported(Ws[l].shape[0], Ws[l].shape[1]) else None
@@ -526,11 +600,13 @@ class _B200KFAC:
         # two slabs per lane, alternating as SpMM input / output
         row_floats = grp * dmax
         bufs = [(_slab(dev, i, 0, n_in * row_floats),
-                 _slab(dev, i, 1, max(n_loc + n_split, 1) * row_floats))
+                 _slab(dev, i, 1, max(n_loc + n_split, 1) * row_floats),
+                 _slab(dev, i, 2, max(n_loc, 1) * row_floats) if ragged else None)
                 for i in range(lanes)]
         if lanes == 1:
             for c0, gc in groups:
-                for _ in self._chain(lay, logits, idx, Hs, Ws, Wp, c0, gc, width_of(gc), bufs[0][0], bufs[0][1], G, hdr):
+                for _ in self._chain(lay, logits, idx, Hs, Ws, Wp, c0, gc, width_of(gc), bufs[0][0], bufs[0][1], G, hdr,
+                                     bufs[0][2]):
                     pass
             return grp, len(groups)
         # two column groups in flight, each on its own stream with its own buffers and factor
@@ -550,7 +626,7 @@ class _B200KFAC:
                     if active[i] is None and pending:
                         c0, gc = pending.pop(0)
                         active[i] = self._chain(lay, logits, idx, Hs, Ws, Wp, c0, gc, width_of(gc), bufs[i][0],
-                                                bufs[i][1], G_lane[i], hdrs[i])
+                                                bufs[i][1], G_lane[i], hdrs[i], bufs[i][2])
                     if active[i] is not None:
                         try:
                             next(active[i])

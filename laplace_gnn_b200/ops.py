@@ -82,7 +82,7 @@ def live_gather_sum(act: torch.Tensor, h: int, col: torch.Tensor) -> torch.Tenso
     key = (act.data_ptr(), tuple(act.shape), h, col.data_ptr(), col.numel())
     t = _LIVE_GATHER.get(key)
     if t is None:
-        k = (act[:, :h] > 0).sum(1)
+        k = act if act.dim() == 1 else (act[:, :h] > 0).sum(1)      # 1-D: the live counts themselves
         t = _LIVE_GATHER[key] = k[col.to(torch.int64)].sum()
     return t
 
@@ -277,6 +277,7 @@ class UnitSlab:
     hdr: torch.Tensor
     act: torch.Tensor | None = None
     _live: torch.Tensor | None = None
+    ragged: bool = False        # rows back to back in a flat ``slab``, absolute slots in ``hdr`` (unit_pack_ragged)
 
     def live_units(self) -> torch.Tensor:
         """int64 [n_rows]: live units per node (profiling only; evaluated outside timed regions)."""
@@ -308,6 +309,46 @@ def unit_pack(slab: torch.Tensor, act: torch.Tensor, g: int, hdr: torch.Tensor |
     return UnitSlab(n, int(g), h, slab, hdr, act)
 
 
+def unit_row_slots(act: torch.Tensor, g: int) -> torch.Tensor:
+    """int64 [n_rows]: slots the compacted row of each node takes (its live units; for g % 4 == 2 every 32-unit
+    block rounded up to an even count, the layout of csrc/spmm_units_even.cu)."""
+    n, h = int(act.shape[0]), int(act.shape[1])
+    if g % 4 == 0:
+        return (act > 0).sum(1)
+    per_block = (act > 0).view(n, h // 32, 32).sum(2)
+    return ((per_block + 1) // 2 * 2).sum(1)
+
+
+def unit_pack_ragged(src: torch.Tensor | None, act: torch.Tensor, g: int, row_first: torch.Tensor,
+                     dst: torch.Tensor | None, hdr: torch.Tensor | None) -> None:
+    """Rows of ``src`` ([n_rows, >= g*h] dense [g][h]) packed back to back into the flat buffer ``dst``: node n's
+    live slots start at the absolute slot ``row_first[n]`` (int64; see unit_row_slots).  ``hdr`` (int32
+    [n_rows, h/32, 2], optional) receives (mask, absolute first slot) per 32 units; ``src=None`` writes the
+    headers only.  What the ranks of the row-partitioned backward exchange (curvature.py)."""
+    lib = _lib.load()
+    _f32c(act, "act")
+    n, h = int(act.shape[0]), int(act.shape[1])
+    if row_first.dtype != torch.int64 or row_first.numel() < n or not row_first.is_contiguous():
+        raise ValueError("unit_pack_ragged: row_first must be a contiguous int64 vector with one entry per row")
+    if src is not None:
+        _f32c(src, "src")
+        if dst is None:
+            raise ValueError("unit_pack_ragged: src without dst")
+        if dst.dtype != torch.float32 or not dst.is_contiguous():
+            raise ValueError("unit_pack_ragged: dst must be a contiguous float32 buffer")
+        if src.shape[0] < n or src.shape[1] < g * h:
+            raise ValueError("unit_pack_ragged: src smaller than [act rows, g*h]")
+    if hdr is not None and (hdr.dtype != torch.int32 or hdr.numel() < n * (h // 32) * 2 or not hdr.is_contiguous()):
+        raise ValueError("unit_pack_ragged: hdr must be a contiguous int32 buffer of n_rows * h/32 * 2 entries")
+    with _Timed("unit_pack", g * h, float(n) * h * ((g * 6 + 4) if src is not None else 4)):
+        check(lib.lgnn_unit_pack_ragged_f32(ptr(src) if src is not None else None, src.stride(0) if src is not None else 0,
+                                            ptr(act), act.stride(0), n, int(g), h, ptr(row_first),
+                                            ptr(dst) if src is not None else None,
+                                            ptr(hdr) if hdr is not None else None, stream()),
+              "lgnn_unit_pack_ragged_f32")
+    _lib.count_launches(1)
+
+
 def spmm_units(a: CSR, us: UnitSlab, out: torch.Tensor | None = None, variant: int = 0) -> torch.Tensor:
     """Y = A @ dense(us), Y: [n_rows, g*h] dense; bit-identical to ``spmm(a, dense slab)``."""
     lib = _lib.load()
@@ -323,12 +364,18 @@ def spmm_units(a: CSR, us: UnitSlab, out: torch.Tensor | None = None, variant: i
     # gathered row, the dense output
     nblk = us.h // 32
     work = a.nnz * (8 + 8 * nblk) + (a.n_rows + 1) * 8 + a.n_rows * d * 4
-    if PROFILE is not None and us.act is not None:
-        work = work + live_gather_sum(us.act, us.h, a.col) * (us.g * 4)
+    if PROFILE is not None and (us.act is not None or us._live is not None):
+        work = work + live_gather_sum(us.act if us.act is not None else us._live, us.h, a.col) * (us.g * 4)
     with _Timed("spmm_units", d, work) as rec:
-        check(lib.lgnn_spmm_units_f32(a.n_rows, us.n_rows, a.nnz, ptr(a.rowptr), ptr(a.col), ptr(a.val), ptr(us.slab),
-                                      us.slab.stride(0), ptr(us.hdr), us.g, us.h, ptr(out), out.stride(0),
-                                      (int(variant) & 0xff) << 8, stream()), "lgnn_spmm_units_f32")
+        if us.ragged:
+            check(lib.lgnn_spmm_units_ragged_f32(a.n_rows, us.n_rows, a.nnz, ptr(a.rowptr), ptr(a.col), ptr(a.val),
+                                                 ptr(us.slab), us.slab.numel(), ptr(us.hdr), us.g, us.h, ptr(out),
+                                                 out.stride(0), (int(variant) & 0xff) << 8, stream()),
+                  "lgnn_spmm_units_ragged_f32")
+        else:
+            check(lib.lgnn_spmm_units_f32(a.n_rows, us.n_rows, a.nnz, ptr(a.rowptr), ptr(a.col), ptr(a.val),
+                                          ptr(us.slab), us.slab.stride(0), ptr(us.hdr), us.g, us.h, ptr(out),
+                                          out.stride(0), (int(variant) & 0xff) << 8, stream()), "lgnn_spmm_units_f32")
     if rec.rec is not None:
         rec.rec["dense_bytes"] = spmm_algorithmic_bytes(a.n_rows, a.nnz, d)
     _lib.count_launches(1)

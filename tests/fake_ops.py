@@ -54,7 +54,8 @@ def csr_slice_remap(a, lo, hi, bounds, pad):
     owner = np.searchsorted(b, c, side="right") - 1
     new_col = (owner * pad + (c - b[owner])).astype(np.int32)
     val = None if a.val is None else a.val[s:e].clone()
-    return CSR(hi - lo, (len(b) - 1) * pad, torch.from_numpy(rp[lo:hi + 1] - s), torch.from_numpy(new_col), val)
+    return CSR(hi - lo, (len(b) - 1) * pad, torch.from_numpy(rp[lo:hi + 1] - s), torch.from_numpy(new_col), val,
+               a.max_row_nnz)
 
 
 def spmm(a, x, relu=False, out=None, d=None, impl="auto"):
@@ -144,7 +145,49 @@ def unit_pack(slab, act, g, hdr=None):
     return UnitSlab(n, g, h, slab, hdr if hdr is not None else torch.zeros(n, h // 32, 2, dtype=torch.int32), act)
 
 
+def _i32_bits(x):
+    """int64 values in [0, 2^32) -> the int32 holding the same 32 bits (what the device writes as uint32)."""
+    return ((x + (1 << 31)) % (1 << 32) - (1 << 31)).to(torch.int32)
+
+
+def unit_pack_ragged(src, act, g, row_first, dst, hdr):
+    """csrc/spmm_units.cu's ragged layout, header words included: node n's slots start at absolute slot
+    row_first[n] of the flat ``dst``; hdr[n][w] = (mask, absolute slot of block w's first live unit)."""
+    n, h = act.shape
+    nb = h // 32
+    blk = (act > 0).view(n, nb, 32)
+    cnt = blk.sum(2)
+    slots = cnt if g % 4 == 0 else (cnt + 1) // 2 * 2
+    first = row_first[:n, None] + torch.cumsum(slots, 1) - slots
+    if hdr is not None:
+        hv = hdr.view(-1, nb, 2)
+        hv[:n, :, 0] = _i32_bits((blk.to(torch.int64) << torch.arange(32)).sum(2))
+        hv[:n, :, 1] = _i32_bits(first)
+    if src is not None:
+        slot = (first[:, :, None] + torch.cumsum(blk, 2) - 1).view(n, h)
+        rows, units = torch.nonzero(blk.view(n, h), as_tuple=True)
+        dense = src[:n, : g * h].reshape(n, g, h)
+        at = slot[rows, units][:, None] * g + torch.arange(g)
+        dst.view(-1)[at.reshape(-1)] = dense[rows, :, units].reshape(-1)
+
+
+def _ragged_to_dense(us):
+    n, g, h = us.n_rows, us.g, us.h
+    nb = h // 32
+    hv = us.hdr.view(-1, nb, 2)[:n].to(torch.int64) & 0xFFFFFFFF
+    blk = ((hv[:, :, 0, None] >> torch.arange(32)) & 1).bool()
+    slot = (hv[:, :, 1, None] + torch.cumsum(blk, 2) - 1).view(n, h)
+    live = blk.view(n, h)
+    dense = torch.zeros(n, g, h, dtype=us.slab.dtype)
+    rows, units = torch.nonzero(live, as_tuple=True)
+    at = slot[rows, units][:, None] * g + torch.arange(g)
+    dense[rows, :, units] = us.slab.view(-1)[at.reshape(-1)].view(-1, g)
+    return dense.reshape(n, g * h)
+
+
 def spmm_units(a, us, out=None, variant=0):
+    if us.ragged:
+        return spmm(a, _ragged_to_dense(us), out=out)
     n, g, h = us.n_rows, us.g, us.h
     live = us.act[:, :h] > 0
     slot = (torch.cumsum(live, 1) - 1).clamp(min=0)
@@ -166,5 +209,5 @@ def gemm_mask_supported(k, n):
     return False          # the CPU double keeps the two-step path (torch.mm + relu_mask_mul)
 
 
-ALL = ["spmm_hess_supported", "hess_stats", "spmm_hess", "sddmm", "unit_slabs_supported", "unit_pack", "spmm_units", "gemm_mask_supported", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
+ALL = ["spmm_hess_supported", "hess_stats", "spmm_hess", "sddmm", "unit_slabs_supported", "unit_pack", "unit_pack_ragged", "spmm_units", "gemm_mask_supported", "csr_with_masked_sources", "csr_from_edge_index", "csr_transpose", "degree_norm", "edge_values", "row_partition",
        "halo_columns", "csr_slice_remap", "spmm", "softmax_ce_sum", "hess_rhs", "relu_mask_mul", "syrk"]

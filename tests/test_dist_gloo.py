@@ -87,12 +87,24 @@ def _unit_worker(rank, world, port, out):
                            unit_min_width=0)
             loss, kron = be.kron(idx, y, N=len(y))
             # column-parallel backward: every rank holds the whole graph -> its 5 columns travel as one
-            # zero-padded group of 8 through the unit-compacted slabs; the row layout exchanges dense slabs
-            assert (be.last_stats["unit_slabs"] > 0) == (mode == "columns")
+            # zero-padded group through the unit-compacted slabs; the row layout packs each rank's rows back to
+            # back (ragged rows, absolute slots in the all-gathered headers) and exchanges those
+            assert be.last_stats["unit_slabs"] > 0
             assert abs(float(loss) - float(ref[0])) <= 1e-5 * abs(float(ref[0]))
             for fa, fb in zip(kron.kfacs, ref[1].kfacs):
                 for a, b in zip(fa, fb):
                     assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+        # rows layout: groups of 12 (slots of 16 bytes) instead of 10 (even-slot layout), several narrow groups,
+        # and the dense exchange with the switch off
+        for kw, units in (({"unit_even_groups": False}, True), ({"rhs_tile_bytes": 600_000}, True),
+                          ({"unit_rows": False}, False)):
+            be = L.B200GGN(model, "classification", process_group=dist.group.WORLD, backward_parallel="rows",
+                           unit_min_width=0, **kw)
+            loss, kron = be.kron(idx, y, N=len(y))
+            assert (be.last_stats["unit_slabs"] > 0) == units, (kw, be.last_stats)
+            for fa, fb in zip(kron.kfacs, ref[1].kfacs):
+                for a, b in zip(fa, fb):
+                    assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()), kw
         # unit_even_groups: the rank's 5 columns travel as a group of 6 instead of 8
         be = L.B200GGN(model, "classification", process_group=dist.group.WORLD, backward_parallel="columns",
                        unit_min_width=0, unit_even_groups=True)

@@ -45,9 +45,16 @@ def _worker(rank, world, port, out):
             return la, float(la.log_marginal_likelihood())
 
         ref, ref_ml = fit()
-        for kw in ({"backward_parallel": "rows", "overlap": False},
-                   {"backward_parallel": "rows", "overlap": True, "rhs_tile_bytes": 64 << 20},
-                   {"backward_parallel": "columns", "unit_min_width": 0}):    # 5 columns per rank travel as 6 x 128
+        # (switches, unit-compacted slabs expected).  Rows layout: the ranks exchange ragged unit-compacted rows —
+        # one group of 10 x 128 (even-slot layout), two lanes of 6 x 128 and of 8 x 128 (16-byte slots) — or dense
+        # slabs where the group is too narrow for the HBM budget given / the switch is off
+        for kw, units in (({"backward_parallel": "rows", "overlap": False}, True),
+                          ({"backward_parallel": "rows", "overlap": True, "rhs_tile_bytes": 64 << 20}, False),
+                          ({"backward_parallel": "rows", "overlap": True, "unit_min_width": 0}, True),
+                          ({"backward_parallel": "rows", "overlap": True, "unit_min_width": 0,
+                            "unit_even_groups": False}, True),
+                          ({"backward_parallel": "rows", "overlap": True, "unit_rows": False}, False),
+                          ({"backward_parallel": "columns", "unit_min_width": 0}, True)):   # 5 columns per rank as 6 x 128
             la, ml = fit(process_group=dist.group.WORLD, **kw)
             for blk, rblk in zip(la.H_facs.kfacs, ref.H_facs.kfacs):
                 for a, b in zip(blk, rblk):
@@ -55,8 +62,7 @@ def _worker(rank, world, port, out):
                     assert err <= 2e-5, (kw, err)
             assert abs(ml - ref_ml) <= 1e-5 * abs(ref_ml), (kw, ml, ref_ml)
             assert abs(float(la.loss) - float(ref.loss)) <= 1e-6 * abs(float(ref.loss))
-            # unit-compacted slabs wherever every row is local (single GPU, column-parallel backward)
-            assert (la.backend.last_stats["unit_slabs"] > 0) == (kw["backward_parallel"] == "columns"), kw
+            assert (la.backend.last_stats["unit_slabs"] > 0) == units, (kw, la.backend.last_stats)
         assert ref.backend.last_stats["unit_slabs"] > 0
         out[rank] = ref_ml
     finally:
