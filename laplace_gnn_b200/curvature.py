@@ -228,6 +228,7 @@ class _RaggedPlan:
 
 class _B200KFAC:
     """kron()/diag() on the B200 kernels; mixed into a CurvatureInterface subclass."""
+    _lanes_on_cpu = False        # tests: walk the two-lane interleaving of the rows layout with the CPU double too
 
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None, rhs_tile_bytes=None,
                     syrk_impl="auto", backward_parallel="rows", overlap=True, fused_gemm=True, fused_linear=True,
@@ -552,7 +553,7 @@ class _B200KFAC:
         # same interleaving — one group's SYRK / GEMM under the other's SpMM — was measured 10 % SLOWER than one
         # group at a time, 1,972 against 1,786 ms per products fit: the persistent tensor-core CTAs and the SpMM's
         # CTAs time-slice the SMs instead of sharing them; profiles/r2a_lab_switches.txt.)
-        lanes = 2 if (self.overlap and lay.communicates and dev.type == "cuda") else 1
+        lanes = 2 if (self.overlap and lay.communicates and (dev.type == "cuda" or self._lanes_on_cpu)) else 1
         ragged = lay.communicates and self._units_possible(lay)     # rows layout with unit-compacted rows travelling
         # columns the HBM budget allows (ragged: a third, local slab per lane for the GEMM's dense rows)
         room = self._group_size(lanes * n_in, lanes * n_loc * (2 if ragged else 1), dmax, 1 << 30, dev)

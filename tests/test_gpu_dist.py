@@ -1,6 +1,7 @@
 """GPU, needs >= 2 devices (skipped on a 1-GPU box): the NCCL row-partitioned pass against the
 single-GPU pass on the same arxiv-like graph — both backward layouts, with and without the
 two-lane overlap.  One process per GPU; never more ranks than GPUs."""
+import datetime
 import os
 import socket
 import sys
@@ -19,13 +20,22 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _guard(seconds: int = 240):
+    """A rank that fails alone leaves its peers waiting in NCCL: dump every thread's stack and exit instead of
+    sitting out the watchdog's default 10 minutes."""
+    import faulthandler
+    faulthandler.enable()
+    faulthandler.dump_traceback_later(seconds, exit=True)
+
+
 def _worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     sys.path.insert(0, ROOT)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    _guard()
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=90))
     try:
         import laplace_gnn_b200 as L
         n, u, f, c, h, layers = 40_000, 300_000, 64, 10, 128, 3
@@ -88,7 +98,8 @@ def _lab_worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    _guard()
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, timeout=datetime.timedelta(seconds=90))
     try:
         import laplace_gnn_b200 as L
 
