@@ -708,7 +708,8 @@ class _B200KFAC:
             keep[idx] = 1
             whole.csr_t_top = ops.csr_with_masked_sources(g.ahat_t, keep)
         mx_row = g.ahat_t.max_row_nnz
-        if (self.fused_hess_spmm and (part is None or self.backward_parallel == "columns") and
+        rows_ok = part is not None and self.backward_parallel == "rows" and self.unit_rows and not part.sparse_halo
+        if (self.fused_hess_spmm and (part is None or self.backward_parallel == "columns" or rows_ok) and
                 ops.spmm_hess_supported(C, 1) and mx_row is not None and mx_row <= self.unit_row_limit):
             self._want_hess_stats = True
         else:
@@ -720,7 +721,25 @@ class _B200KFAC:
                                                   out=_slab(dev, 2000, 0, g.n * 5 * cp).view(g.n, 5 * cp))
             grp, n_groups = self._backward_columns(whole, logits, idx, Hs, Ws, (0, C), G)
         elif self.backward_parallel == "rows":
-            grp, n_groups = self._backward_columns(_Rows(part), logits, idx_loc, Hs, Ws, (0, C), G)
+            lay = _Rows(part)
+            if self._want_hess_stats:
+                # output layer without a slab exchange: every rank writes the five softmax vectors of its train nodes
+                # into its slot of a padded [N, 5 Cp] slab, ONE all-gather per fit (2.3 GB on the products shape
+                # against 22 GB of dense right-hand sides), and lgnn_spmm_hess_f32 rebuilds the right-hand sides per
+                # edge; edges from non-train sources are zeroed in this rank's slice of Â^T as on one device
+                cp = (C + 3) // 4 * 4
+                stats = _slab(dev, 2000, 0, part.total_rows * 5 * cp).view(part.total_rows, 5 * cp)
+                stats.zero_()
+                ops.hess_stats(logits, idx_loc, self.hess_sqrt, C, out=stats[part.slot0:part.slot0 + part.n_local])
+                with ops.timed("allgather", 5 * cp, 4.0 * part.total_rows * 5 * cp):
+                    part.all_gather_slab(stats)
+                lay.hess_stats = stats
+                if self.skip_zero_rows and M < g.n:
+                    keep = torch.zeros(part.total_rows, dtype=torch.uint8, device=dev)
+                    keep[idx_loc + part.slot0] = 1
+                    part.all_gather_slab(keep)
+                    lay.csr_t_top = ops.csr_with_masked_sources(part.ahat_t, keep)
+            grp, n_groups = self._backward_columns(lay, logits, idx_loc, Hs, Ws, (0, C), G)
         else:                                                  # "columns": full graph, own columns
             from .dist import column_share
             # every rank needs H_l (relu' masks) and the logits of ALL nodes: in-place all-gather of the padded

@@ -91,16 +91,31 @@ def spmm_hess_supported(C, width):
     return 1 <= C <= 64 and 1 <= width <= 16
 
 
+_STATS_MODE = ["reference"]
+
+
 def hess_stats(logits, idx, mode="reference", C=None, out=None):
-    """CPU double: keeps what spmm_hess needs (logits, batch indices, mode) in place of the five vectors."""
+    """CPU double: in place of the five softmax vectors the rows keep what spmm_hess needs to rebuild the right-hand
+    sides — the logits and how often the node occurs in the batch (same [n, 5 Cp] shape, so the rows layout can
+    all-gather it like the real thing)."""
     C = logits.shape[1] if C is None else C
-    return {"logits": logits, "idx": idx, "mode": mode, "C": C}
+    cp = (C + 3) // 4 * 4
+    n = logits.shape[0]
+    if out is None:
+        out = torch.zeros(n, 5 * cp, dtype=torch.float32)
+    out.zero_()
+    out[:n, :C] = logits[:, :C]
+    out[:n, cp].index_add_(0, idx, torch.ones(idx.numel(), dtype=torch.float32))
+    _STATS_MODE[0] = mode
+    return out
 
 
 def spmm_hess(a, stats, C, c0, ncols, width, out=None, staged=None):
     cp = (C + 3) // 4 * 4
-    delta = torch.zeros(a.n_cols, width * cp, dtype=torch.float32)
-    hess_rhs(stats["logits"], stats["idx"], c0, ncols, delta, cp, stats["mode"], C)
+    n = a.n_cols
+    idx = torch.repeat_interleave(torch.arange(n), stats[:n, cp].round().to(torch.int64))
+    delta = torch.zeros(n, width * cp, dtype=torch.float32)
+    hess_rhs(stats[:n, :C].contiguous(), idx, c0, ncols, delta, cp, _STATS_MODE[0], C)
     return spmm(a, delta, out=out)
 
 
