@@ -126,6 +126,60 @@ def test_column_parallel_backward_uses_unit_compacted_slabs():
         assert len(out) == 2
 
 
+def _lanes_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import fake_ops as F
+        import laplace_gnn_b200 as L
+        import laplace_gnn_b200.ops as ops
+        from laplace_gnn_b200 import curvature
+        for n in F.ALL:
+            setattr(ops, n, getattr(F, n))
+        curvature._B200KFAC._lanes_on_cpu = True          # two column groups interleaved, as on the device
+        from test_host_logic import _synthetic_model
+        model, idx, y = _synthetic_model(1200, 5000, 12, 64, 11, 3)
+        ref = L.B200GGN(model, "classification", unit_slabs=False).kron(idx, y, N=len(y))
+        seen = []
+        # (switches, group width expected, unit SpMMs expected)
+        for kw, group, units in (({"unit_min_width": 0}, 6, True),                              # 6 + 6(5): even slots
+                                 ({"unit_min_width": 0, "unit_even_groups": False}, 8, True),   # 8 + 4(3): 16-byte slots
+                                 ({"unit_min_width": 0, "rhs_tile_bytes": 2_500_000}, 2, True),  # six narrow groups
+                                 ({"unit_min_width": 0, "hess_sqrt": "ggn"}, 6, True),
+                                 ({"unit_rows": False}, 6, False),
+                                 ({"unit_min_width": 0, "fused_hess_spmm": False}, 6, True)):    # dense output layer
+            ref_kw = ref if kw.get("hess_sqrt") != "ggn" else \
+                L.B200GGN(model, "classification", unit_slabs=False, hess_sqrt="ggn").kron(idx, y, N=len(y))
+            be = L.B200GGN(model, "classification", process_group=dist.group.WORLD, backward_parallel="rows",
+                           overlap=True, **kw)
+            loss, kron = be.kron(idx, y, N=len(y))
+            st = be.last_stats
+            assert st["group"] == group and (st["unit_slabs"] > 0) == units, (kw, st)
+            assert abs(float(loss) - float(ref_kw[0])) <= 1e-5 * abs(float(ref_kw[0]))
+            for fa, fb in zip(kron.kfacs, ref_kw[1].kfacs):
+                for a, b in zip(fa, fb):
+                    assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max()), kw
+            seen.append(st["n_groups"])
+        out[rank] = seen
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_rows_layout_with_two_lanes_and_ragged_unit_rows(world):
+    """The two-lane interleaving of the rows layout (one group's all-gather under the other's SpMM on the device)
+    walked on the CPU double: plans for both slot layouts, narrow groups, both Hessian square roots, the dense
+    exchange and the materialised output layer as A/B — same factors as the single-process dense pass."""
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_lanes_worker, args=(world, port, out), nprocs=world, join=True)
+        assert len(out) == world and len({tuple(v) for v in out.values()}) == 1
+
+
 def test_column_share_covers_all_columns_once():
     from laplace_gnn_b200.dist import column_share
     for C in (1, 3, 7, 40, 47):
