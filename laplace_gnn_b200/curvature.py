@@ -528,8 +528,9 @@ class _B200KFAC:
             yield
 
     def _units_possible(self, lay) -> bool:
-        """Unit-compacted slabs need every row local and a graph without hub rows (the kernel gives one
-        warp a whole row)."""
+        """Unit-compacted slabs need a graph without hub rows (the kernel gives one warp a whole row; hub rows cut
+        into pieces count) and, in the rows layout, the whole-slab exchange (``unit_rows``: ragged rows travel; with
+        a sparse halo the ranks exchange dense halo rows instead)."""
         mx = lay.csr_t.max_row_nnz
         local = not lay.communicates or (self.unit_rows and not lay.part.sparse_halo)   # rows layout: ragged rows travel
         return (self.unit_slabs and local and mx is not None and

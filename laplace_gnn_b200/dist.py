@@ -16,8 +16,10 @@ the B200 design of BASELINE.json's north star:
 ``backward_parallel`` selects how the C Hessian-sqrt columns of the backward are spread:
 
   "rows"     every rank processes all C columns on its row block; each layer step all-gathers the
-             N x (g*d) right-hand-side slab (communication ~ compute at 8 GPUs; hidden behind
-             the SpMM of the other in-flight column group when ``overlap`` is on);
+             group's right-hand sides — below the output layer as ragged unit-compacted rows (the
+             live relu units of each node, back to back: about half the N x (g*d) slab), at the output
+             layer not at all (softmax statistics gathered once per fit) — hidden behind the SpMM of
+             the other in-flight column group when ``overlap`` is on;
   "columns"  the forward stays row-partitioned (halo all-gather of Z_l, all-gather of H_l), then
              rank r back-propagates its own C/world columns on the full graph: no data-path
              collective in the backward at all.
