@@ -180,6 +180,51 @@ def test_rows_layout_with_two_lanes_and_ragged_unit_rows(world):
         assert len(out) == world and len({tuple(v) for v in out.values()}) == 1
 
 
+def _tiny_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import fake_ops as F
+        import laplace_gnn_b200 as L
+        import laplace_gnn_b200.ops as ops
+        for n in F.ALL:
+            setattr(ops, n, getattr(F, n))
+        from test_host_logic import _synthetic_model
+        empties = 0
+        for nodes, pairs in ((3, 2), (7, 5)):
+            model, idx, y = _synthetic_model(nodes, pairs, 4, 32, 3, 3)
+            ref = L.B200GGN(model, "classification", unit_slabs=False).kron(idx, y, N=len(y))
+            for mode in ("rows", "columns"):
+                be = L.B200GGN(model, "classification", process_group=dist.group.WORLD, backward_parallel=mode,
+                               unit_min_width=0)
+                loss, kron = be.kron(idx, y, N=len(y))
+                b = be.last_stats["partition"].bounds
+                empties += sum(b[r + 1] == b[r] for r in range(world))
+                if mode == "rows":              # (columns: 3 classes over 4 ranks leave one rank without a column)
+                    assert be.last_stats["unit_slabs"] > 0
+                assert abs(float(loss) - float(ref[0])) <= 1e-5 * abs(float(ref[0]))
+                for fa, fb in zip(kron.kfacs, ref[1].kfacs):
+                    for a, c in zip(fa, fb):
+                        assert float((a - c).abs().max()) <= 1e-5 * float(c.abs().max()) + 1e-30, (nodes, mode)
+        assert empties > 0                      # 3 nodes over 4 ranks: at least one rank owns no row
+        out[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_more_ranks_than_rows():
+    """Ranks that own no row at all (3 nodes over 4 ranks) in both layouts, unit-compacted slabs on: empty plans,
+    empty packs and empty slots of the all-gathers."""
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_tiny_worker, args=(4, port, out), nprocs=4, join=True)
+        assert len(out) == 4
+
+
 def test_column_share_covers_all_columns_once():
     from laplace_gnn_b200.dist import column_share
     for C in (1, 3, 7, 40, 47):
