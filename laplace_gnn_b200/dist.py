@@ -35,6 +35,38 @@ from . import ops
 from .ops import CSR
 
 
+# Collectives of one communicator must not run concurrently.  torch launches a blocking collective (async_op=False)
+# on the CALLER's current stream, so the two lanes of the overlapped rows layout — each on its own stream — could put
+# two all-gathers of the same communicator on the device at once (seen once as a 600 s watchdog stall of the NCCL
+# parity test on small shapes, where the lanes' collectives are microseconds apart).  Every collective issued here
+# therefore first makes its stream wait for the previous one (an event recorded behind it, or the Work handle of an
+# asynchronous one): the host order, which is the same on every rank, becomes the device order.
+_LAST_COLLECTIVE: dict = {}
+
+
+def _after_previous(pg, t: torch.Tensor, async_op: bool = False) -> None:
+    if not t.is_cuda:
+        return
+    prev = _LAST_COLLECTIVE.get(id(pg))
+    if prev is None:
+        return
+    if isinstance(prev, torch.cuda.Event):
+        torch.cuda.current_stream(t.device).wait_event(prev)
+    elif not async_op:                  # asynchronous collectives share the group's own stream: ordered already
+        prev.wait()                     # Work of an asynchronous collective: the current stream waits for it
+
+
+def _issued(pg, t: torch.Tensor, work=None) -> None:
+    if not t.is_cuda:
+        return
+    if work is not None:
+        _LAST_COLLECTIVE[id(pg)] = work
+    else:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(t.device))
+        _LAST_COLLECTIVE[id(pg)] = ev
+
+
 @dataclass
 class RowPartition:
     """State of one rank for a given (graph, process group)."""
@@ -102,7 +134,10 @@ class RowPartition:
         mine = flat[self.rank]
         if not slab.is_cuda:           # gloo (CPU tests): no in-place guarantee
             mine = mine.clone()
-        return dist.all_gather_into_tensor(flat.view(-1), mine.reshape(-1), group=self.pg, async_op=async_op)
+        _after_previous(self.pg, slab, async_op)
+        work = dist.all_gather_into_tensor(flat.view(-1), mine.reshape(-1), group=self.pg, async_op=async_op)
+        _issued(self.pg, slab, work if async_op else None)
+        return work
 
     # ---- halo-only exchange ------------------------------------------------------------
     @property
@@ -144,9 +179,11 @@ class RowPartition:
         width = slab.shape[1]
         send = slab.index_select(0, plan["send_rows"])
         recv = torch.empty(int(sum(plan["recv_counts"])), width, dtype=slab.dtype, device=slab.device)
+        _after_previous(self.pg, slab)
         dist.all_to_all_single(recv.view(-1), send.view(-1),
                                output_split_sizes=[c * width for c in plan["recv_counts"]],
                                input_split_sizes=[c * width for c in plan["send_counts"]], group=self.pg)
+        _issued(self.pg, slab)
         slab.index_copy_(0, plan["recv_rows"], recv)
         return None
 
@@ -159,7 +196,9 @@ class RowPartition:
     def all_reduce_sum(self, tensors) -> None:
         """One all-reduce over the concatenation of same-dtype tensors (written back in place)."""
         flat = torch.cat([t.reshape(-1) for t in tensors])
+        _after_previous(self.pg, flat)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.pg)
+        _issued(self.pg, flat)
         off = 0
         for t in tensors:
             n = t.numel()
