@@ -60,6 +60,8 @@ def parse_args():
                     help="multi-GPU: all-gather the hidden activations in front of the backward instead of asynchronously under it")
     ap.add_argument("--no-unit-rows", action="store_true",
                     help="multi-GPU rows layout: exchange dense slabs (round-1 behaviour) instead of ragged unit-compacted rows")
+    ap.add_argument("--rows-hess-stats", action="store_true",
+                    help="multi-GPU rows layout: output layer from all-gathered softmax statistics (opt-in, DESIGN.md §6)")
     ap.add_argument("--no-shard-eigh", action="store_true",
                     help="multi-GPU: every rank decomposes every factor (round-1 behaviour) instead of a share of them")
     ap.add_argument("--rhs-tile-gb", type=float, default=None,
@@ -332,6 +334,7 @@ def main():
         bk["shard_eigh"] = not args.no_shard_eigh
         bk["defer_gathers"] = not args.no_defer_gathers
         bk["unit_rows"] = not args.no_unit_rows
+        bk["rows_hess_stats"] = args.rows_hess_stats
     loader = L.TensorBatchLoader(idx, y)      # one full batch, no per-sample collation
 
     def step(mdl, ldr, kwargs=None):

@@ -231,13 +231,14 @@ class _B200KFAC:
     _lanes_on_cpu = False        # tests: walk the two-lane interleaving of the rows layout with the CPU double too
 
     def _b200_setup(self, hess_sqrt="reference", differentiable=False, process_group=None, rhs_tile_bytes=None,
-                    syrk_impl="auto", backward_parallel="rows", overlap=True, fused_gemm=True, fused_linear=True,
+                    syrk_impl="auto", backward_parallel="columns", overlap=True, fused_gemm=True, fused_linear=True,
                     cache_input_factor=False, _shared_cache=None, diag_mode="exact",
                     # data layout of the multi-RHS slabs (defaults = what the benchmark runs; off-switches for A/B)
                     unit_slabs=True, unit_min_width=1024, unit_even_groups=True, unit_hub_split=True,
                     fused_hess_spmm=True,
                     # multi-GPU
-                    shard_eigh=True, defer_gathers=True, sparse_halo=False, unit_rows=True):
+                    shard_eigh=True, defer_gathers=True, sparse_halo=False, unit_rows=True,
+                    rows_hess_stats=False):
         if hess_sqrt not in ("reference", "ggn"):
             raise ValueError(f"hess_sqrt must be 'reference' or 'ggn', got {hess_sqrt!r}")
         if diag_mode not in ("exact", "node_factorised"):
@@ -302,6 +303,11 @@ class _B200KFAC:
         # (ops.unit_pack_ragged), the packed rows are what the all-gather moves (about half the dense slab) and what
         # the SpMM then gathers from (_RaggedPlan).  False: dense slabs travel (the round-1 rows layout)
         self.unit_rows = bool(unit_rows)
+        # rows layout, output layer: softmax statistics all-gathered once per fit and the right-hand sides rebuilt per
+        # edge (as on one device) instead of dense right-hand-side slabs exchanged per column group.  565 against
+        # 622 ms per products fit at 4 GPUs — but OPT-IN: the NCCL parity test passed with it at 4 ranks and failed
+        # once at 2 ranks (factors off by 1.9e-4) in the round's last GPU seconds, unresolved
+        self.rows_hess_stats = bool(rows_hess_stats)
         self.unit_row_limit = 4096
         # A_0 = X^T X does not depend on the weights: with cache_input_factor the raw Gram matrix of
         # this rank's feature rows is kept (per backend, or in a dict shared across backends by the
@@ -709,7 +715,8 @@ class _B200KFAC:
             keep[idx] = 1
             whole.csr_t_top = ops.csr_with_masked_sources(g.ahat_t, keep)
         mx_row = g.ahat_t.max_row_nnz
-        rows_ok = part is not None and self.backward_parallel == "rows" and self.unit_rows and not part.sparse_halo
+        rows_ok = (part is not None and self.backward_parallel == "rows" and self.rows_hess_stats and
+                   self.unit_rows and not part.sparse_halo)
         if (self.fused_hess_spmm and (part is None or self.backward_parallel == "columns" or rows_ok) and
                 ops.spmm_hess_supported(C, 1) and mx_row is not None and mx_row <= self.unit_row_limit):
             self._want_hess_stats = True
@@ -736,9 +743,12 @@ class _B200KFAC:
                     part.all_gather_slab(stats)
                 lay.hess_stats = stats
                 if self.skip_zero_rows and M < g.n:
-                    keep = torch.zeros(part.total_rows, dtype=torch.uint8, device=dev)
-                    keep[idx_loc + part.slot0] = 1
-                    part.all_gather_slab(keep)
+                    # train flags of all nodes in the padded layout; slots padded to 16 bytes for the all-gather
+                    pad16 = (part.pad + 15) // 16 * 16
+                    flags = torch.zeros(part.world, pad16, dtype=torch.uint8, device=dev)
+                    flags[part.rank, idx_loc] = 1
+                    part.all_gather_slab(flags)
+                    keep = flags[:, :part.pad].reshape(-1)
                     lay.csr_t_top = ops.csr_with_masked_sources(part.ahat_t, keep)
             grp, n_groups = self._backward_columns(lay, logits, idx_loc, Hs, Ws, (0, C), G)
         else:                                                  # "columns": full graph, own columns

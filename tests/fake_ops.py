@@ -80,6 +80,8 @@ def softmax_ce_sum(logits, idx, y, C=None):
 
 def hess_rhs(logits, idx, c0, ncols, delta, ldc, mode="reference", C=None):
     C = logits.shape[1] if C is None else C
+    if idx.numel() == 0 or delta.shape[0] == 0:            # a rank without train nodes / without rows
+        return delta
     V = O.hess_sqrt_rhs(logits[idx][:, :C], mode)          # [m, C(col), C]
     d3 = delta.view(delta.shape[0], -1, ldc)             # a wider row = zero padding columns behind the group
     for g in range(ncols):

@@ -150,7 +150,12 @@ def _lanes_worker(rank, world, port, out):
                                  ({"unit_min_width": 0, "rhs_tile_bytes": 2_500_000}, 2, True),  # six narrow groups
                                  ({"unit_min_width": 0, "hess_sqrt": "ggn"}, 6, True),
                                  ({"unit_rows": False}, 6, False),
-                                 ({"unit_min_width": 0, "fused_hess_spmm": False}, 6, True)):    # dense output layer
+                                 # output layer from all-gathered softmax statistics (opt-in), both modes, narrow groups
+                                 ({"unit_min_width": 0, "rows_hess_stats": True}, 6, True),
+                                 ({"unit_min_width": 0, "rows_hess_stats": True, "hess_sqrt": "ggn",
+                                   "unit_even_groups": False}, 8, True),
+                                 ({"unit_min_width": 0, "rows_hess_stats": True, "rhs_tile_bytes": 2_500_000}, 2, True),
+                                 ({"rows_hess_stats": True, "unit_rows": False}, 6, False)):    # needs unit_rows: dense
             ref_kw = ref if kw.get("hess_sqrt") != "ggn" else \
                 L.B200GGN(model, "classification", unit_slabs=False, hess_sqrt="ggn").kron(idx, y, N=len(y))
             be = L.B200GGN(model, "classification", process_group=dist.group.WORLD, backward_parallel="rows",
@@ -199,7 +204,7 @@ def _tiny_worker(rank, world, port, out):
             ref = L.B200GGN(model, "classification", unit_slabs=False).kron(idx, y, N=len(y))
             for mode in ("rows", "columns"):
                 be = L.B200GGN(model, "classification", process_group=dist.group.WORLD, backward_parallel=mode,
-                               unit_min_width=0)
+                               unit_min_width=0, rows_hess_stats=(nodes == 7))
                 loss, kron = be.kron(idx, y, N=len(y))
                 b = be.last_stats["partition"].bounds
                 empties += sum(b[r + 1] == b[r] for r in range(world))
