@@ -38,33 +38,31 @@ from .ops import CSR
 # Collectives of one communicator must not run concurrently.  torch launches a blocking collective (async_op=False)
 # on the CALLER's current stream, so the two lanes of the overlapped rows layout — each on its own stream — could put
 # two all-gathers of the same communicator on the device at once (seen once as a 600 s watchdog stall of the NCCL
-# parity test on small shapes, where the lanes' collectives are microseconds apart).  Every collective issued here
-# therefore first makes its stream wait for the previous one (an event recorded behind it, or the Work handle of an
-# asynchronous one): the host order, which is the same on every rank, becomes the device order.
-_LAST_COLLECTIVE: dict = {}
+# parity test on small shapes, where the lanes' collectives are microseconds apart).  A blocking collective issued
+# here on ANOTHER stream than the previous one therefore first makes its stream wait for an event recorded behind
+# that one: the host order, which is the same on every rank, becomes the device order.  Collectives that follow each
+# other on one stream are ordered anyway and are left alone; asynchronous ones (the deferred all-gathers of the
+# column-parallel backward) run on the group's own stream, and their callers wait for them before the next blocking
+# collective.
+_LAST_COLLECTIVE: dict = {}      # id(process group) -> (stream id, event recorded behind the last blocking collective)
 
 
 def _after_previous(pg, t: torch.Tensor, async_op: bool = False) -> None:
-    if not t.is_cuda:
+    if not t.is_cuda or async_op:
         return
     prev = _LAST_COLLECTIVE.get(id(pg))
-    if prev is None:
-        return
-    if isinstance(prev, torch.cuda.Event):
-        torch.cuda.current_stream(t.device).wait_event(prev)
-    elif not async_op:                  # asynchronous collectives share the group's own stream: ordered already
-        prev.wait()                     # Work of an asynchronous collective: the current stream waits for it
+    cur = torch.cuda.current_stream(t.device)
+    if prev is not None and prev[0] != cur.cuda_stream:
+        cur.wait_event(prev[1])
 
 
 def _issued(pg, t: torch.Tensor, work=None) -> None:
-    if not t.is_cuda:
+    if not t.is_cuda or work is not None:
         return
-    if work is not None:
-        _LAST_COLLECTIVE[id(pg)] = work
-    else:
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(t.device))
-        _LAST_COLLECTIVE[id(pg)] = ev
+    cur = torch.cuda.current_stream(t.device)
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    _LAST_COLLECTIVE[id(pg)] = (cur.cuda_stream, ev)
 
 
 @dataclass

@@ -66,3 +66,48 @@ def test_cpu_double_of_the_ragged_spmm_matches_the_dense_product():
     F.unit_pack_ragged(dense.reshape(n, g * h), act, g, first, flat, words)
     got = F.spmm_units(a, ops.UnitSlab(n, g, h, flat, words, None, ragged=True))
     assert torch.equal(got, F.spmm(a, dense.reshape(n, g * h)))
+
+
+def test_collectives_are_chained_across_streams_only(monkeypatch):
+    """dist._after_previous / _issued: a blocking collective waits for the previous one's event only when it is issued
+    on another stream (the two lanes of the rows layout); same-stream sequences and asynchronous collectives are left
+    alone.  Streams and events are stand-ins: the bookkeeping is what is tested."""
+    import types
+    import laplace_gnn_b200.dist as D
+    log = []
+
+    class Ev:
+        def record(self, s):
+            log.append(("record", s.cuda_stream))
+
+    class St:
+        def __init__(self, i):
+            self.cuda_stream = i
+
+        def wait_event(self, e):
+            log.append(("wait", self.cuda_stream))
+
+    cur = [St(1)]
+    shim = types.SimpleNamespace(cuda=types.SimpleNamespace(current_stream=lambda d=None: cur[0], Event=Ev),
+                                 Tensor=torch.Tensor)
+    monkeypatch.setattr(D, "torch", shim)
+    monkeypatch.setattr(D, "_LAST_COLLECTIVE", {})
+    t = types.SimpleNamespace(is_cuda=True, device=None)
+    pg = object()
+
+    def collective(async_op=False):
+        D._after_previous(pg, t, async_op)
+        D._issued(pg, t, object() if async_op else None)
+
+    collective()                      # first, stream 1
+    collective()                      # same stream: implicit order
+    cur[0] = St(2)
+    collective()                      # lane 2: waits for stream 1's event
+    collective(async_op=True)         # asynchronous: untouched
+    cur[0] = St(1)
+    collective()                      # back on stream 1: waits for stream 2's event
+    assert log == [("record", 1), ("record", 1), ("wait", 2), ("record", 2), ("wait", 1), ("record", 1)]
+    cpu = types.SimpleNamespace(is_cuda=False, device=None)
+    D._after_previous(pg, cpu)
+    D._issued(pg, cpu)                # CPU tensors (gloo): nothing recorded
+    assert len(log) == 6
