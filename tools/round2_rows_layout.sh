@@ -1,7 +1,7 @@
 #!/bin/bash
 # N GPUs: the row-partitioned backward ("rows", the north star's own partitioning) at the products shape — ragged
 # unit-compacted rows travelling (default) against dense slabs (--no-unit-rows), two column groups in flight against
-# one — after the NCCL parity tests and the single-GPU kernel tests of the ragged layout.
+# one, the output layer from all-gathered softmax statistics (--rows-hess-stats, opt-in) — after the NCCL parity tests and the single-GPU kernel tests of the ragged layout.
 #   /usr/local/graft/bin/gpurun --gpus 2 --timeout 1200 -- 'bash tools/round2_rows_layout.sh 2 [tests|bench|all]'
 set -u
 N=${1:-2}
@@ -16,10 +16,11 @@ if [ $WHAT = tests ] || [ $WHAT = all ]; then
   tail -3 gpurun_out/r2r_n${N}_tests.log | cut -c1-200
 fi
 if [ $WHAT = bench ] || [ $WHAT = all ]; then
-  for tag in ${TAGS:-rows rows_noov rows_dense}; do
+  for tag in ${TAGS:-rows rows_noov rows_dense rows_stats}; do
     fl="--backward-parallel rows"
     [ $tag = rows_noov ] && fl="$fl --no-overlap"
     [ $tag = rows_dense ] && fl="$fl --no-unit-rows"
+    [ $tag = rows_stats ] && fl="$fl --rows-hess-stats"
     par="--no-parity"; [ $tag = rows ] && par=""
     timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P \
         bench.py --gpus $N --steps ${STEPS:-10} --warmup 3 --no-e2e --no-cpu-baseline $par $fl > gpurun_out/r2r_n${N}_$tag.log 2>gpurun_out/r2r_n${N}_$tag.err
